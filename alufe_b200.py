@@ -1,0 +1,13 @@
+"""Import alias: ``import alufe_b200`` loads the package that lives in the directory
+``a-lightweight-unsupervised-feature-extractor-_b200/`` (not a valid Python identifier)."""
+import importlib.util
+import os
+import sys
+
+_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)),
+                    "a-lightweight-unsupervised-feature-extractor-_b200")
+_spec = importlib.util.spec_from_file_location(
+    "alufe_b200", os.path.join(_dir, "__init__.py"), submodule_search_locations=[_dir])
+_mod = importlib.util.module_from_spec(_spec)
+sys.modules["alufe_b200"] = _mod
+_spec.loader.exec_module(_mod)
