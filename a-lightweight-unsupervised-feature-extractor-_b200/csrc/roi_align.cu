@@ -1,0 +1,451 @@
+// ROI Align forward for sm_100a.
+//
+// Replaces torchvision.ops.roi_align as the reference calls it (tracking.py:214,
+// infer.py:163, trainingCard.py:71): [B,C,H,W] fp32 map + [K,5] rois -> [K,C,PH,PW].
+//
+// Design (DESIGN.md section "ROI Align"): the work unit is one warp per
+// (ROI, 32-channel tile), lane = channel.  Bilinear sampling is separable, and the
+// sampling weights depend on the ROI only, not on the channel, so each warp
+//   1. turns the ROI's PH*gh + PW*gw sample positions into two small dense weight
+//      tables Wy[FY][PH], Wx[FX][PW] over the ROI's footprint (FY x FX map cells);
+//   2. stages the footprint of its 32 channels into shared memory as V[cell][channel]
+//      (NHWC: coalesced 128 B cp.async per cell; NCHW: 16 B vector loads along x,
+//      transposed on the way in);
+//   3. accumulates out[ph][pw] = sum_x Wx[x][pw] * (sum_y Wy[y][ph] * V[y][x]) in
+//      registers (PH*PW accumulators per lane, every map value read exactly once);
+//   4. writes its [32][PH*PW] result tile -- contiguous in the NCHW output -- to shared
+//      memory and hands it to the TMA engine as ONE bulk async store
+//      (cp.async.bulk.global.shared::cta), so output traffic is full-line writes.
+// Footprints larger than the staging capacity, and output sizes without a template
+// instantiation, take exact but slower paths.  Sample coordinates are evaluated with
+// the same operation order as torchvision and without FMA contraction so that cell
+// selection agrees with the CPU op.
+#include "common.cuh"
+
+namespace b200 {
+namespace {
+
+constexpr int kWarpsPerCta = 2;
+constexpr int kFootCap = 8;     // max footprint rows / cols on the staged path (<= 64 cells x 32 ch = 8 KB)
+constexpr int kCellCap = kFootCap * kFootCap;
+
+struct Geom {
+    float sw, sh, bw, bh, count;
+    int gh, gw, b;
+};
+
+__device__ __forceinline__ Geom roi_geometry(const float* __restrict__ r, float scale, int sr,
+                                             int aligned, int PH, int PW) {
+    Geom g;
+    const float off = aligned ? 0.5f : 0.0f;
+    g.b = (int)r[0];
+    g.sw = __fsub_rn(__fmul_rn(r[1], scale), off);
+    g.sh = __fsub_rn(__fmul_rn(r[2], scale), off);
+    const float ew = __fsub_rn(__fmul_rn(r[3], scale), off);
+    const float eh = __fsub_rn(__fmul_rn(r[4], scale), off);
+    float rw = __fsub_rn(ew, g.sw), rh = __fsub_rn(eh, g.sh);
+    if (!aligned) {
+        rw = fmaxf(rw, 1.0f);
+        rh = fmaxf(rh, 1.0f);
+    }
+    g.bh = __fdiv_rn(rh, (float)PH);
+    g.bw = __fdiv_rn(rw, (float)PW);
+    g.gh = sr > 0 ? sr : (int)ceilf(g.bh);
+    g.gw = sr > 0 ? sr : (int)ceilf(g.bw);
+    const int n = g.gh * g.gw;
+    g.count = (float)(n > 1 ? n : 1);
+    return g;
+}
+
+// start + p*bin + (i + .5)*bin/grid, rounded step by step like the reference op.
+__device__ __forceinline__ float sample_pos(float start, int p, float bin, int i, int grid) {
+    const float a = __fadd_rn(start, __fmul_rn((float)p, bin));
+    const float b = __fdiv_rn(__fmul_rn((float)i + 0.5f, bin), (float)grid);
+    return __fadd_rn(a, b);
+}
+
+struct Tap {
+    int lo, hi;
+    float wlo, whi;
+    bool valid;
+};
+
+__device__ __forceinline__ Tap make_tap(float v, int dim) {
+    Tap t;
+    t.valid = (v >= -1.0f) && (v <= (float)dim);   // false for NaN as well
+    if (!(v > 0.0f)) v = 0.0f;
+    int lo = (int)fminf(v, (float)dim);
+    if (lo >= dim - 1) {
+        lo = dim - 1;
+        t.hi = lo;
+        v = (float)lo;
+    } else {
+        t.hi = lo + 1;
+    }
+    t.lo = lo;
+    t.whi = __fsub_rn(v, (float)lo);
+    t.wlo = __fsub_rn(1.0f, t.whi);
+    return t;
+}
+
+// Rows (or columns) of the map touched by any valid sample of one axis.  Sample positions are
+// monotone in (p, i), so the two extreme samples bound every other one; clamping them to the
+// validity window [-1, dim] gives a footprint that covers every valid tap (it may be one cell
+// larger than strictly needed, which only adds zero weights).
+__device__ __forceinline__ void axis_footprint(float start, float bin, int P, int grid, int dim, int* lo,
+                                               int* n) {
+    *lo = 0;
+    *n = 0;
+    if (grid <= 0) return;
+    const float a = sample_pos(start, 0, bin, 0, grid), b = sample_pos(start, P - 1, bin, grid - 1, grid);
+    const float mn = fmaxf(fminf(a, b), -1.0f), mx = fminf(fmaxf(a, b), (float)dim);
+    if (!(mn <= mx) || a != a || b != b) return;
+    const Tap t0 = make_tap(mn, dim), t1 = make_tap(mx, dim);
+    *lo = t0.lo;
+    *n = t1.hi - t0.lo + 1;
+}
+
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.wait_all;\n" ::: "memory");
+}
+
+// One bulk async copy shared -> global issued by a single lane (TMA engine, SASS UBLKCP).
+__device__ __forceinline__ void bulk_store(float* gdst, const float* ssrc, unsigned bytes) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(ssrc);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gdst), "r"(s),
+                 "r"(bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+}
+
+template <int PH, int PW>
+struct TileSmem {
+    static constexpr int kPHP = (PH + 3) & ~3;
+    static constexpr int kPWP = (PW + 3) & ~3;
+    static constexpr int kOutFloats = 32 * PH * PW;
+    static constexpr int kStageFloats = kCellCap * 32;
+    static constexpr int kMainFloats = kOutFloats > kStageFloats ? kOutFloats : kStageFloats;
+    static constexpr int kTabFloats = kFootCap * (kPHP + kPWP);
+    static constexpr int kFloatsPerWarp = kMainFloats + kTabFloats;
+    static constexpr int kBytesPerCta = kFloatsPerWarp * 4 * kWarpsPerCta;
+};
+
+// acc[ph][pw] += sum_x Wx[x][pw] * (sum_r Wy[r][ph] * V[r][x]); V comes from `loadv`.
+template <int PH, int PW, typename LoadV>
+__device__ __forceinline__ void separable_accumulate(float (&acc)[PH][PW], const float* sWy, const float* sWx,
+                                                     int FY, int FX, LoadV loadv) {
+    constexpr int PHP = (PH + 3) & ~3, PWP = (PW + 3) & ~3;
+    for (int x = 0; x < FX; ++x) {
+        float ty[PH];
+#pragma unroll
+        for (int a = 0; a < PH; ++a) ty[a] = 0.0f;
+        for (int r = 0; r < FY; ++r) {
+            const float v = loadv(r, x);
+            const float4* w4 = reinterpret_cast<const float4*>(sWy + r * PHP);
+#pragma unroll
+            for (int q = 0; q < PHP / 4; ++q) {
+                const float4 w = w4[q];
+                if (4 * q + 0 < PH) ty[4 * q + 0] = fmaf(w.x, v, ty[4 * q + 0]);
+                if (4 * q + 1 < PH) ty[4 * q + 1] = fmaf(w.y, v, ty[4 * q + 1]);
+                if (4 * q + 2 < PH) ty[4 * q + 2] = fmaf(w.z, v, ty[4 * q + 2]);
+                if (4 * q + 3 < PH) ty[4 * q + 3] = fmaf(w.w, v, ty[4 * q + 3]);
+            }
+        }
+        const float4* w4 = reinterpret_cast<const float4*>(sWx + x * PWP);
+#pragma unroll
+        for (int q = 0; q < PWP / 4; ++q) {
+            const float4 w = w4[q];
+            const float wv[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (4 * q + e < PW) {
+#pragma unroll
+                    for (int a = 0; a < PH; ++a) acc[a][4 * q + e] = fmaf(wv[e], ty[a], acc[a][4 * q + e]);
+                }
+        }
+    }
+}
+
+#ifndef B200_ROI_MIN_CTAS
+#define B200_ROI_MIN_CTAS 1
+#endif
+
+template <int PH, int PW, bool NHWC>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, B200_ROI_MIN_CTAS)
+roi_align_tile_kernel(const float* __restrict__ feat, int B, int C, int H, int W,
+                      const float* __restrict__ rois, long long K, float scale, int sr, int aligned,
+                      float* __restrict__ out, int ctiles) {
+    using L = TileSmem<PH, PW>;
+    constexpr int PHP = L::kPHP, PWP = L::kPWP, NB = PH * PW;
+    static_assert(PH <= 16 && PW <= 16, "one lane per output row/column");
+    extern __shared__ __align__(16) float smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long wi = (long long)blockIdx.x * kWarpsPerCta + warp;
+    if (wi >= K * ctiles) return;            // warps are independent: no block-wide barriers below
+    float* sMain = smem + (size_t)warp * L::kFloatsPerWarp;   // V staging / big tables, later the output tile
+    float* sTab = sMain + L::kMainFloats;
+
+    const long long k = wi / ctiles;
+    const int c0 = (int)(wi % ctiles) * 32;
+    const int cn = min(32, C - c0);
+    const Geom g = roi_geometry(rois + 5 * k, scale, sr, aligned, PH, PW);
+
+    int ymin, xmin, FY, FX;
+    axis_footprint(g.sh, g.bh, PH, g.gh, H, &ymin, &FY);
+    axis_footprint(g.sw, g.bw, PW, g.gw, W, &xmin, &FX);
+    if (g.b < 0 || g.b >= B || FY == 0 || FX == 0) FY = FX = 0;      // nothing sampled: zeros
+    const bool staged = FY <= kFootCap && FX <= kFootCap;
+    // Larger footprints keep their (bigger) weight tables in the output-tile area and read V
+    // straight from global memory; only absurdly large ones take the per-bin path.
+    const bool direct = !staged && (FY * PHP + FX * PWP) <= L::kMainFloats;
+
+    float acc[PH][PW];
+#pragma unroll
+    for (int a = 0; a < PH; ++a)
+#pragma unroll
+        for (int b = 0; b < PW; ++b) acc[a][b] = 0.0f;
+
+    if (staged || direct) {
+        // ---- dense separable weight tables over the footprint (lanes 0-15: y, 16-31: x) ------
+        float* sWy = staged ? sTab : sMain;
+        float* sWx = sWy + (staged ? kFootCap : FY) * PHP;
+        if (staged) {
+            for (int i = lane; i < L::kTabFloats / 4; i += 32) reinterpret_cast<float4*>(sTab)[i] = make_float4(0, 0, 0, 0);
+        } else {
+            for (int i = lane; i < FY * PHP + FX * PWP; i += 32) sMain[i] = 0.0f;
+        }
+        __syncwarp();
+        {
+            const int axis = lane >> 4, p = lane & 15;
+            const int Pn = axis ? PW : PH, grid = axis ? g.gw : g.gh, dim = axis ? W : H;
+            const float start = axis ? g.sw : g.sh, bin = axis ? g.bw : g.bh;
+            float* tab = (axis ? sWx : sWy) + p;
+            const int stride = axis ? PWP : PHP, lo0 = axis ? xmin : ymin;
+            if (p < Pn && FY)
+                for (int i = 0; i < grid; ++i) {              // column p of the table has one writer
+                    const Tap t = make_tap(sample_pos(start, p, bin, i, grid), dim);
+                    if (t.valid) {
+                        tab[(t.lo - lo0) * stride] += t.wlo;
+                        tab[(t.hi - lo0) * stride] += t.whi;
+                    }
+                }
+        }
+        if (staged) {
+            // ---- stage V[cell][channel] -----------------------------------------------------
+            const int ncell = FY * FX;
+            float* sV = sMain;
+            if (NHWC) {
+                const float* base = feat + (((size_t)g.b * H + ymin) * W + xmin) * C + c0 + lane;
+                if (lane < cn)
+                    for (int cell = 0; cell < ncell; ++cell) {
+                        const int r = cell / FX, x = cell - r * FX;
+                        cp_async4(sV + cell * 32 + lane, base + ((size_t)r * W + x) * C);
+                    }
+                cp_async_wait_all();
+            } else if (ncell) {
+                const float* plane0 = feat + ((size_t)g.b * C + c0) * H * W;
+                const bool vec = (W & 3) == 0 && ((reinterpret_cast<uintptr_t>(feat) & 15) == 0);
+                const int G = vec ? 4 : 1;
+                const int q0 = xmin / G, nq = (xmin + FX - 1) / G - q0 + 1;   // chunks per footprint row
+                int nqp = 1;
+                while (nqp < nq) nqp <<= 1;                         // lanes per row segment (<= 8)
+                const int per_it = 32 / nqp, sub = lane & (nqp - 1), slot = lane / nqp;
+                const int items = cn * FY;                           // item = r * cn + c (channel fastest)
+                const int xq = (q0 + sub) * G;
+                for (int base = 0; base < items; base += 4 * per_it) {
+                    float4 v[4];
+                    int rr[4], cc[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {                    // all loads of the batch first
+                        const int item = base + u * per_it + slot;
+                        rr[u] = -1;
+                        if (item < items && sub < nq) {
+                            rr[u] = item / cn;
+                            cc[u] = item - rr[u] * cn;
+                            const float* p = plane0 + ((size_t)cc[u] * H + ymin + rr[u]) * W + xq;
+                            if (vec) v[u] = __ldg(reinterpret_cast<const float4*>(p));
+                            else v[u].x = __ldg(p);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (rr[u] >= 0) {
+                            const float e4[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const int x = xq + e - xmin;
+                                if (e < G && x >= 0 && x < FX) sV[(rr[u] * FX + x) * 32 + cc[u]] = e4[e];
+                            }
+                        }
+                }
+            }
+            __syncwarp();
+            separable_accumulate<PH, PW>(acc, sWy, sWx, FY, FX,
+                                         [&](int r, int x) { return sV[(r * FX + x) * 32 + lane]; });
+        } else {
+            __syncwarp();
+            const int cl = lane < cn ? lane : 0;                     // idle lanes re-read channel 0
+            const float* base = NHWC ? feat + (((size_t)g.b * H + ymin) * W + xmin) * C + c0 + cl
+                                     : feat + (((size_t)g.b * C + c0 + cl) * H + ymin) * W + xmin;
+            const size_t rs = NHWC ? (size_t)W * C : (size_t)W, xs = NHWC ? (size_t)C : 1;
+            separable_accumulate<PH, PW>(acc, sWy, sWx, FY, FX,
+                                         [&](int r, int x) { return __ldg(base + r * rs + x * xs); });
+        }
+        __syncwarp();                          // every lane is done with V / the tables in sMain
+    } else {
+        // ---- exact last-resort path: per-bin direct 4-tap sampling ------------------------------
+        const size_t ps = NHWC ? (size_t)C : 1;
+        const float* base = feat + (NHWC ? (size_t)g.b * H * W * C + c0 + lane
+                                         : ((size_t)g.b * C + c0 + lane) * H * W);
+#pragma unroll 1
+        for (int bin = 0; bin < NB; ++bin) {
+            const int a = bin / PW, b = bin - a * PW;
+            float s = 0.0f;
+            for (int iy = 0; iy < g.gh; ++iy) {
+                const Tap ty = make_tap(sample_pos(g.sh, a, g.bh, iy, g.gh), H);
+                for (int ix = 0; ix < g.gw; ++ix) {
+                    const Tap tx = make_tap(sample_pos(g.sw, b, g.bw, ix, g.gw), W);
+                    if (ty.valid && tx.valid && lane < cn) {
+                        const float v1 = __ldg(base + ((size_t)ty.lo * W + tx.lo) * ps);
+                        const float v2 = __ldg(base + ((size_t)ty.lo * W + tx.hi) * ps);
+                        const float v3 = __ldg(base + ((size_t)ty.hi * W + tx.lo) * ps);
+                        const float v4 = __ldg(base + ((size_t)ty.hi * W + tx.hi) * ps);
+                        s += ty.wlo * tx.wlo * v1 + ty.wlo * tx.whi * v2 + ty.whi * tx.wlo * v3 +
+                             ty.whi * tx.whi * v4;
+                    }
+                }
+            }
+            sMain[lane * NB + bin] = s;        // parked in the output tile, scaled below
+        }
+        __syncwarp();
+#pragma unroll
+        for (int a = 0; a < PH; ++a)
+#pragma unroll
+            for (int b = 0; b < PW; ++b) acc[a][b] = sMain[lane * NB + a * PW + b];
+        __syncwarp();
+    }
+
+    // ---- mean over samples (1/count is exact for the power-of-two counts of sampling_ratio 1, 2, 4;
+    // otherwise within 1 ulp of the reference's division), output tile to shared memory ----------
+    const float inv = __fdiv_rn(1.0f, g.count);
+    float* myrow = sMain + lane * NB;
+    if ((NB & 3) == 0) {
+#pragma unroll
+        for (int q = 0; q < NB / 4; ++q)
+            reinterpret_cast<float4*>(myrow)[q] =
+                make_float4(acc[(4 * q) / PW][(4 * q) % PW] * inv, acc[(4 * q + 1) / PW][(4 * q + 1) % PW] * inv,
+                            acc[(4 * q + 2) / PW][(4 * q + 2) % PW] * inv, acc[(4 * q + 3) / PW][(4 * q + 3) % PW] * inv);
+    } else {
+#pragma unroll
+        for (int i = 0; i < NB; ++i) myrow[i] = acc[i / PW][i % PW] * inv;
+    }
+
+    // ---- one contiguous [cn][PH*PW] chunk of the NCHW output -----------------------------------
+    float* gdst = out + ((size_t)k * C + c0) * NB;
+    const unsigned bytes = (unsigned)cn * NB * 4u;
+    const bool bulk = ((reinterpret_cast<uintptr_t>(gdst) & 15) == 0) && (bytes & 15u) == 0;
+    if (bulk) {
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        __syncwarp();
+        if (lane == 0) bulk_store(gdst, sMain, bytes);
+        __syncwarp();
+    } else {
+        __syncwarp();
+        for (int i = lane; i < cn * NB; i += 32) gdst[i] = sMain[i];
+    }
+}
+
+// Any output size / any parameters: one thread per output element, direct sampling.
+template <bool NHWC>
+__global__ void __launch_bounds__(256)
+roi_align_generic_kernel(const float* __restrict__ feat, int B, int C, int H, int W,
+                         const float* __restrict__ rois, long long total, int PH, int PW, float scale,
+                         int sr, int aligned, float* __restrict__ out) {
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int pw = (int)(idx % PW), ph = (int)((idx / PW) % PH);
+        const int c = (int)((idx / ((long long)PW * PH)) % C);
+        const long long k = idx / ((long long)PW * PH * C);
+        const Geom g = roi_geometry(rois + 5 * k, scale, sr, aligned, PH, PW);
+        float s = 0.0f;
+        if (g.b >= 0 && g.b < B) {
+            const size_t ps = NHWC ? (size_t)C : 1;
+            const float* base = feat + (NHWC ? (size_t)g.b * H * W * C + c : ((size_t)g.b * C + c) * H * W);
+            for (int iy = 0; iy < g.gh; ++iy) {
+                const Tap ty = make_tap(sample_pos(g.sh, ph, g.bh, iy, g.gh), H);
+                for (int ix = 0; ix < g.gw; ++ix) {
+                    const Tap tx = make_tap(sample_pos(g.sw, pw, g.bw, ix, g.gw), W);
+                    if (ty.valid && tx.valid) {
+                        const float v1 = __ldg(base + ((size_t)ty.lo * W + tx.lo) * ps);
+                        const float v2 = __ldg(base + ((size_t)ty.lo * W + tx.hi) * ps);
+                        const float v3 = __ldg(base + ((size_t)ty.hi * W + tx.lo) * ps);
+                        const float v4 = __ldg(base + ((size_t)ty.hi * W + tx.hi) * ps);
+                        s += ty.wlo * tx.wlo * v1 + ty.wlo * tx.whi * v2 + ty.whi * tx.wlo * v3 +
+                             ty.whi * tx.whi * v4;
+                    }
+                }
+            }
+        }
+        out[idx] = __fdiv_rn(s, g.count);
+    }
+}
+
+template <int PH, int PW, bool NHWC>
+int launch_tile(const float* feat, int B, int C, int H, int W, const float* rois, long long K,
+                float scale, int sr, int aligned, float* out, cudaStream_t st) {
+    using L = TileSmem<PH, PW>;
+    static bool configured = false;          // per instantiation; the attribute is idempotent
+    auto kern = roi_align_tile_kernel<PH, PW, NHWC>;
+    if (!configured) {
+        B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kBytesPerCta));
+        configured = true;
+    }
+    const int ctiles = (C + 31) / 32;
+    const long long warps = K * ctiles;
+    const long long blocks = (warps + kWarpsPerCta - 1) / kWarpsPerCta;
+    if (blocks > 0x7fffffffLL) return fail(B200_EINVAL, "roi_align: too many ROI tiles (%lld)", blocks);
+    kern<<<(unsigned)blocks, kWarpsPerCta * 32, L::kBytesPerCta, st>>>(feat, B, C, H, W, rois, K, scale, sr,
+                                                                     aligned, out, ctiles);
+    return check_launch("roi_align_tile_kernel");
+}
+
+}  // namespace
+}  // namespace b200
+
+extern "C" int b200_roi_align_fwd_f32(const float* feat, int layout, int B, int C, int H, int W,
+                                      const float* rois, int64_t K, int PH, int PW, float spatial_scale,
+                                      int sampling_ratio, int aligned, float* out, void* stream) {
+    using namespace b200;
+    B200_REQUIRE(layout == B200_LAYOUT_NCHW || layout == B200_LAYOUT_NHWC, "roi_align: bad layout %d", layout);
+    B200_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, "roi_align: bad feature shape [%d,%d,%d,%d]", B, C, H, W);
+    B200_REQUIRE(PH > 0 && PW > 0, "roi_align: bad output size (%d,%d)", PH, PW);
+    B200_REQUIRE(K >= 0, "roi_align: negative ROI count");
+    if (K == 0) return B200_OK;
+    B200_REQUIRE(feat && rois && out, "roi_align: null pointer");
+    cudaStream_t st = as_stream(stream);
+    const bool nhwc = layout == B200_LAYOUT_NHWC;
+#define B200_TILE(ph, pw)                                                                              \
+    if (PH == ph && PW == pw)                                                                          \
+        return nhwc ? launch_tile<ph, pw, true>(feat, B, C, H, W, rois, K, spatial_scale, sampling_ratio, \
+                                                aligned, out, st)                                      \
+                    : launch_tile<ph, pw, false>(feat, B, C, H, W, rois, K, spatial_scale,             \
+                                                 sampling_ratio, aligned, out, st);
+    B200_TILE(10, 10)
+    B200_TILE(7, 7)
+#undef B200_TILE
+    const long long total = (long long)K * C * PH * PW;
+    const long long want = (total + 255) / 256;
+    const unsigned blocks = (unsigned)(want < (long long)kSMs * 32 ? want : (long long)kSMs * 32);
+    if (nhwc)
+        roi_align_generic_kernel<true><<<blocks, 256, 0, st>>>(feat, B, C, H, W, rois, total, PH, PW,
+                                                               spatial_scale, sampling_ratio, aligned, out);
+    else
+        roi_align_generic_kernel<false><<<blocks, 256, 0, st>>>(feat, B, C, H, W, rois, total, PH, PW,
+                                                                spatial_scale, sampling_ratio, aligned, out);
+    return check_launch("roi_align_generic_kernel");
+}

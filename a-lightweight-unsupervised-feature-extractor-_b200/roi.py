@@ -1,0 +1,93 @@
+"""ROI Align operators with the reference's Python surface, backed by libb200track.
+
+* ``roi_align``                  - torchvision.ops.roi_align signature (tracking.py:203,214).
+* ``roi_align_from_input_boxes`` - MainInfer.roi_align_from_input_boxes, tracking.py:193-221
+                                   (= tracking_win.py:239-267, infer.py:143-170).
+* ``preprocess_roi``             - PreProcess._preprocess_roi, trainingCard.py:24-79.
+"""
+from typing import List, Sequence, Tuple, Union
+
+import torch
+
+from . import _lib
+
+
+def _pair(v):
+    return (int(v), int(v)) if isinstance(v, int) else (int(v[0]), int(v[1]))
+
+
+def _boxes_to_rois(boxes, device):
+    if isinstance(boxes, (list, tuple)):
+        parts = []
+        for i, b in enumerate(boxes):
+            if b.dim() != 2 or b.size(1) != 4:
+                raise ValueError("each element of the box list must be Tensor[L, 4]")
+            idx = torch.full((b.size(0), 1), float(i), dtype=torch.float32, device=b.device)
+            parts.append(torch.cat([idx, b.to(torch.float32)], dim=1))
+        rois = torch.cat(parts, dim=0) if parts else torch.zeros((0, 5), dtype=torch.float32)
+    else:
+        if boxes.dim() != 2 or boxes.size(1) != 5:
+            raise ValueError("boxes must be Tensor[K, 5] (batch index in column 0) or a list of Tensor[L, 4]")
+        rois = boxes
+    return rois.to(device=device, dtype=torch.float32).contiguous()
+
+
+def roi_align(input: torch.Tensor, boxes: Union[torch.Tensor, Sequence[torch.Tensor]],
+              output_size: Union[int, Tuple[int, int]], spatial_scale: float = 1.0,
+              sampling_ratio: int = -1, aligned: bool = False) -> torch.Tensor:
+    """Drop-in for ``torchvision.ops.roi_align`` (forward only, float32 maps).
+
+    ``input`` may be contiguous NCHW or ``torch.channels_last``; both are read in place.
+    Returns a new contiguous ``[K, C, PH, PW]`` float32 tensor on ``input``'s device.
+    """
+    _lib.require_cuda(input, "input")
+    if input.dim() != 4:
+        raise ValueError("input must be [B, C, H, W]")
+    if input.dtype != torch.float32:
+        raise TypeError("roi_align: float32 feature maps only (got %s)" % input.dtype)
+    B, C, H, W = input.shape
+    if input.is_contiguous():
+        layout = _lib.LAYOUT_NCHW
+    elif input.is_contiguous(memory_format=torch.channels_last):
+        layout = _lib.LAYOUT_NHWC
+    else:
+        input, layout = input.contiguous(), _lib.LAYOUT_NCHW
+    rois = _boxes_to_rois(boxes, input.device)
+    PH, PW = _pair(output_size)
+    K = rois.size(0)
+    out = torch.empty((K, C, PH, PW), dtype=torch.float32, device=input.device)
+    with torch.cuda.device(input.device):
+        rc = _lib.lib().b200_roi_align_fwd_f32(
+            _lib.ptr(input), layout, B, C, H, W, _lib.ptr(rois), K, PH, PW, float(spatial_scale),
+            int(sampling_ratio), int(bool(aligned)), _lib.ptr(out), _lib.stream_ptr(input.device))
+    _lib.check(rc)
+    return out
+
+
+def roi_align_from_input_boxes(feat: torch.Tensor, boxes_in: List[List[float]], input_hw: Tuple[int, int],
+                               out_size=(7, 7), aligned: bool = True, sampling_ratio: int = 2) -> torch.Tensor:
+    """tracking.py:193-221: boxes are in letterboxed-input pixels, scale = Hf / H_in, batch 0."""
+    H_in, _ = input_hw
+    Hf = feat.shape[2]
+    rois = torch.tensor([[0.0, b[0], b[1], b[2], b[3]] for b in boxes_in], dtype=torch.float32).reshape(-1, 5)
+    return roi_align(feat, rois.to(feat.device), out_size, Hf / float(H_in), sampling_ratio, aligned)
+
+
+def preprocess_roi(feat: torch.Tensor, bboxes_xyxy: torch.Tensor, img_hw: Tuple[int, int],
+                   output_size=(10, 10), sampling_ratio: int = 2, aligned: bool = True,
+                   enforce_min_size: float = 1.0) -> torch.Tensor:
+    """trainingCard.py:24-79: box prep in feature coordinates, then roi_align(scale=1)."""
+    assert feat.dim() == 4 and feat.size(0) == 1, f"feat shape expected [1,C,H,W], got {feat.shape}"
+    b = bboxes_xyxy.to(device=feat.device, dtype=torch.float32).reshape(-1, 4)
+    _, _, Hf, Wf = feat.shape
+    img_h, img_w = img_hw
+    x1, x2 = torch.minimum(b[:, 0], b[:, 2]), torch.maximum(b[:, 0], b[:, 2])
+    y1, y2 = torch.minimum(b[:, 1], b[:, 3]), torch.maximum(b[:, 1], b[:, 3])
+    sx, sy = Wf / float(img_w), Hf / float(img_h)
+    x1, x2 = (x1 * sx).clamp(0, Wf - 1), (x2 * sx).clamp(0, Wf - 1)
+    y1, y2 = (y1 * sy).clamp(0, Hf - 1), (y2 * sy).clamp(0, Hf - 1)
+    if enforce_min_size > 0:
+        x2 = torch.maximum(x2, x1 + enforce_min_size).clamp(0, Wf - 1)
+        y2 = torch.maximum(y2, y1 + enforce_min_size).clamp(0, Hf - 1)
+    rois = torch.stack([torch.zeros_like(x1), x1, y1, x2, y2], dim=1)
+    return roi_align(feat, rois, output_size, 1.0, sampling_ratio, aligned)

@@ -1,0 +1,135 @@
+"""GPU parity: b200 ROI Align (through the C ABI) against the oracle, the golden fixtures
+from the live reference, and the installed torchvision op."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import assert_close, load_golden
+from oracle import native
+
+pytestmark = pytest.mark.gpu
+
+import alufe_b200  # noqa: E402,F401
+from alufe_b200 import roi, synth  # noqa: E402
+
+
+def _run(feat, rois, ps, scale, sr, al, nhwc=False):
+    f = torch.from_numpy(feat).cuda()
+    if nhwc:
+        f = f.contiguous(memory_format=torch.channels_last)
+    out = roi.roi_align(f, torch.from_numpy(rois).cuda(), ps, scale, sr, al)
+    torch.cuda.synchronize()
+    return out.cpu().numpy()
+
+
+@pytest.mark.parametrize("nhwc", [False, True])
+def test_roi_vs_golden(nhwc):
+    g = load_golden("roi")
+    for tag in "abcd":
+        ph, pw, sr, al = (int(v) for v in g["arg_" + tag])
+        got = _run(g["feat"], g["rois"], (ph, pw), 20 / 640.0, sr, bool(al), nhwc)
+        assert_close(got, g["out_" + tag], what="golden roi %s nhwc=%s" % (tag, nhwc))
+
+
+@pytest.mark.parametrize("nhwc", [False, True])
+@pytest.mark.parametrize("cfg", ["c1", "c2", "c5"])
+@pytest.mark.parametrize("ps", [(10, 10), (7, 7)])
+def test_roi_vs_oracle_named_shapes(cfg, ps, nhwc):
+    Hf, Wf, H_in, W_in, n = synth.CONFIGS[cfg]
+    C = 512 if cfg != "c5" else 96
+    feat = synth.feature_map(0, 1, C, Hf, Wf)
+    rng = np.random.default_rng(3)
+    boxes = np.concatenate([synth.random_boxes(rng, n, H_in, W_in), synth.edge_case_boxes(H_in, W_in)])
+    rois = np.concatenate([np.zeros((len(boxes), 1)), boxes], 1).astype(np.float32)
+    scale = Hf / float(H_in)
+    want = native.roi_align(feat, rois, ps, scale, 2, True)
+    assert_close(_run(feat, rois, ps, scale, 2, True, nhwc), want, what=cfg)
+
+
+@pytest.mark.parametrize("nhwc", [False, True])
+def test_roi_batched_maps_odd_shapes(nhwc):
+    """c3-style batch indices, C not a multiple of 32, W not a multiple of 4, large boxes
+    (slow path), adaptive sampling, not-aligned mode, out-of-range batch index -> zeros."""
+    rng = np.random.default_rng(5)
+    feat = rng.standard_normal((5, 70, 23, 37), dtype=np.float32)
+    boxes = rng.uniform(-100, 1300, (64, 4))
+    boxes[:8] = [0, 0, 1184, 736]                       # whole-map boxes
+    boxes[8:16, 2:] = boxes[8:16, :2] + rng.uniform(200, 600, (8, 2))
+    rois = np.concatenate([rng.integers(0, 5, (64, 1)).astype(np.float64), boxes], 1).astype(np.float32)
+    for ps, sr, al in [((10, 10), 2, True), ((7, 7), 2, False), ((10, 10), -1, True), ((7, 7), 0, False),
+                       ((10, 10), 3, True), ((4, 6), 2, True), ((1, 1), -1, False)]:
+        want = native.roi_align(feat, rois, ps, 1 / 32.0, sr, al)
+        assert_close(_run(feat, rois, ps, 1 / 32.0, sr, al, nhwc), want, what="odd %s %s %s" % (ps, sr, al))
+    bad = rois.copy()
+    bad[3, 0] = 9
+    got = _run(feat, bad, (10, 10), 1 / 32.0, 2, True, nhwc)
+    assert np.all(got[3] == 0) and np.isfinite(got).all()
+
+
+def test_roi_vs_torchvision_cuda_and_cpu():
+    tv = pytest.importorskip("torchvision")
+    feat = synth.feature_map(1, 2, 512, 40, 40)
+    rng = np.random.default_rng(9)
+    boxes = synth.random_boxes(rng, 64, 1280, 1280)
+    rois = np.concatenate([rng.integers(0, 2, (64, 1)).astype(np.float64), boxes], 1).astype(np.float32)
+    got = _run(feat, rois, (10, 10), 40 / 1280.0, 2, True)
+    cpu = tv.ops.roi_align(torch.from_numpy(feat), torch.from_numpy(rois), (10, 10), 40 / 1280.0, 2, True).numpy()
+    assert_close(got, cpu, what="tv cpu")
+    gpu = tv.ops.roi_align(torch.from_numpy(feat).cuda(), torch.from_numpy(rois).cuda(), (10, 10), 40 / 1280.0, 2, True)
+    # torchvision's own CUDA kernel is only a second opinion: it differs from its CPU op (the
+    # parity contract) by up to ~2e-5 absolute on these inputs, so it gets a looser bound.
+    assert_close(got, gpu.cpu().numpy(), rtol=1e-4, atol=1e-4, what="tv cuda")
+
+
+def test_roi_wrappers_match_reference_call_conventions():
+    """tracking.py:193-221 and trainingCard.py:24-79 calling conventions."""
+    feat = synth.feature_map(2, 1, 64, 20, 20)
+    boxes = synth.random_boxes(np.random.default_rng(2), 8, 640, 640)
+    f = torch.from_numpy(feat).cuda()
+    got = roi.roi_align_from_input_boxes(f, boxes.tolist(), (640, 640)).cpu().numpy()
+    rois = np.concatenate([np.zeros((8, 1)), boxes], 1).astype(np.float32)
+    assert got.shape == (8, 64, 7, 7)
+    assert_close(got, native.roi_align(feat, rois, (7, 7), 20 / 640.0, 2, True))
+    # _preprocess_roi: sorted, scaled per axis, clamped, min size 1, spatial_scale 1
+    b = boxes.copy()
+    b[0] = [300, 300, 250, 240]
+    b[1] = [630, 630, 700, 700]
+    got = roi.preprocess_roi(f, torch.from_numpy(b), (640, 640)).cpu().numpy()
+    x1, x2 = np.minimum(b[:, 0], b[:, 2]), np.maximum(b[:, 0], b[:, 2])
+    y1, y2 = np.minimum(b[:, 1], b[:, 3]), np.maximum(b[:, 1], b[:, 3])
+    fb = np.stack([x1, y1, x2, y2], 1).astype(np.float32) * np.float32(20 / 640.0)
+    fb = np.clip(fb, 0, 19)
+    fb[:, 2] = np.clip(np.maximum(fb[:, 2], fb[:, 0] + 1), 0, 19)
+    fb[:, 3] = np.clip(np.maximum(fb[:, 3], fb[:, 1] + 1), 0, 19)
+    r2 = np.concatenate([np.zeros((8, 1), np.float32), fb], 1)
+    assert_close(got, native.roi_align(feat, r2, (10, 10), 1.0, 2, True))
+    with pytest.raises(AssertionError):
+        roi.preprocess_roi(torch.zeros(2, 4, 5, 5).cuda(), torch.zeros(1, 4), (10, 10))
+
+
+def test_roi_full_size_properties():
+    """BASELINE config 3 size ([4096,512,10,10]): size-independent checks only.
+    (i) a constant map gives the constant for fully-inside boxes; (ii) linearity in the map;
+    (iii) a random subset of ROIs agrees with the oracle."""
+    Bm, C, Hf, Wf = 256, 512, 40, 40
+    rng = np.random.default_rng(0)
+    boxes = np.concatenate([synth.random_boxes(rng, 16, 1280, 1280) for _ in range(Bm)])
+    rois = np.concatenate([np.repeat(np.arange(Bm), 16)[:, None].astype(np.float64), boxes], 1).astype(np.float32)
+    r = torch.from_numpy(rois).cuda()
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    a = torch.randn((Bm, C, Hf, Wf), device="cuda", generator=gen)
+    b = torch.randn((Bm, C, Hf, Wf), device="cuda", generator=gen)
+    ya = roi.roi_align(a, r, (10, 10), 40 / 1280.0, 2, True)
+    yb = roi.roi_align(b, r, (10, 10), 40 / 1280.0, 2, True)
+    ys = roi.roi_align(a * 2 + b, r, (10, 10), 40 / 1280.0, 2, True)
+    assert ya.shape == (4096, 512, 10, 10)
+    assert torch.allclose(ys, 2 * ya + yb, rtol=1e-5, atol=1e-5)
+    ones = roi.roi_align(torch.full_like(a, 3.25), r, (10, 10), 40 / 1280.0, 2, True)
+    assert torch.allclose(ones, torch.full_like(ones, 3.25), rtol=1e-6, atol=0)
+    pick = rng.choice(4096, 24, replace=False)
+    maps = np.unique(rois[pick, 0].astype(int))
+    sub_feat = a[maps].cpu().numpy()
+    sub_rois = rois[pick].copy()
+    sub_rois[:, 0] = np.searchsorted(maps, sub_rois[:, 0].astype(int))
+    want = native.roi_align(sub_feat, sub_rois, (10, 10), 40 / 1280.0, 2, True)
+    assert_close(ya[torch.from_numpy(pick).cuda()].cpu().numpy(), want, what="c3 subset")
