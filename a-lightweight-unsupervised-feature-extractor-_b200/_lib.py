@@ -48,7 +48,7 @@ SIGNATURES = {
     "b200_pair_cost_f32": (_I, [_P, _P, _P, _P, _P, _I, _I, _F, _F, _F, _F, _F, _F, _P, _P, _P, _P, _P, _I, _P]),
     "b200_kalman_init": (_I, [_P, _I, _P, _P, _P, _P]),
     "b200_kalman_predict": (_I, [_P, _P, _P, _I, _P, _P, _P]),
-    "b200_kalman_update": (_I, [_P, _P, _P, _I, _P, _P, _P, _P]),
+    "b200_kalman_update": (_I, [_P, _P, _P, _I, _P, _P, _I, _P, _P]),
     "b200_maha_gate": (_I, [_P, _P, _P, _I, _P, _I, _P, _D, _F, _P, _I, _P, _I, _P]),
     "b200_lsap_f32": (_I, [_P, _I, _L, _I, _I, _I, _D, _P, _P, _P, _P]),
     "b200_tracker_create": (_I, [ctypes.POINTER(_P), _I, _I, _I, ctypes.POINTER(tracker_conf)]),

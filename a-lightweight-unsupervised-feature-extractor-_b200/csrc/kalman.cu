@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(kKfThreads) kalman_predict_kernel(double* gx, 
 
 __global__ void __launch_bounds__(kKfThreads) kalman_update_kernel(double* gx, double* gP, uint8_t* stage, int M,
                                                                    const int32_t* __restrict__ det_of_track,
-                                                                   const double* __restrict__ boxes,
+                                                                   const double* __restrict__ boxes, int meas_is_z,
                                                                    const float* __restrict__ r_diag) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= M) return;
@@ -71,7 +71,12 @@ __global__ void __launch_bounds__(kKfThreads) kalman_update_kernel(double* gx, d
     double b[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) { r[k] = r_diag[k]; b[k] = boxes[(size_t)j * 4 + k]; }
-    kf::box_to_z(b, z);
+    if (meas_is_z) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) z[k] = (float)b[k];
+    } else {
+        kf::box_to_z(b, z);
+    }
     double x[8], P[64];
     load_state(gx, gP, i, x, P);
     stage[i] = (uint8_t)kf::update(x, P, stage[i], z, r);
@@ -135,12 +140,12 @@ extern "C" int b200_kalman_predict(double* x, double* P, const uint8_t* stage, i
 }
 
 extern "C" int b200_kalman_update(double* x, double* P, uint8_t* stage, int M, const int32_t* det_of_track,
-                                  const double* boxes_xyxy, const float* r_diag, void* stream) {
+                                  const double* meas, int meas_is_z, const float* r_diag, void* stream) {
     B200_REQUIRE(M >= 0, "kalman_update: negative M");
     if (M == 0) return B200_OK;
-    B200_REQUIRE(x && P && stage && det_of_track && boxes_xyxy && r_diag, "kalman_update: null pointer");
+    B200_REQUIRE(x && P && stage && det_of_track && meas && r_diag, "kalman_update: null pointer");
     kalman_update_kernel<<<(M + kKfThreads - 1) / kKfThreads, kKfThreads, 0, as_stream(stream)>>>(
-        x, P, stage, M, det_of_track, boxes_xyxy, r_diag);
+        x, P, stage, M, det_of_track, meas, meas_is_z, r_diag);
     return check_launch("kalman_update_kernel");
 }
 

@@ -1,0 +1,774 @@
+// GPU-resident multi-stream tracker: Tracking.update (model/mainTracking.py:450-610) as five
+// kernels per frame-step, batched over independent streams (one CTA, or one grid slice, each).
+//
+//   begin   (CTA / stream)  :467-487  empty-frame shortcut, predict_all, main/ReID row split,
+//                                     detection prep (unit embeddings, z, float32 boxes), gate prep
+//   cost<1> (grid)          :496-511  bank top-k appearance + box + conf terms + Mahalanobis gate,
+//                                     written once as C and C^T
+//   assign<1> (CTA / stream):514-538  LSAP + cost_max filter, update_matched, mark_missed
+//   cost<2> (grid)          :552-558  ReID-only appearance cost for long-lost rows x leftover dets
+//   assign<2> (CTA / stream):560-610  LSAP, update_matched, mark_missed, births, purge, result table
+//
+// State never leaves the device.  Tracks live in fixed physical slots (banks are never moved);
+// `order` lists the live slots by ascending track id, which is the row order the reference uses
+// (sorted(rows_main), :486-487) because ids are handed out monotonically (:371-372).
+#include <string.h>
+
+#include <new>
+
+#include "assoc_cost.cuh"
+#include "kalman.cuh"
+#include "lsap.cuh"
+
+namespace b200 {
+namespace trk {
+
+constexpr int kThreads = 256;
+constexpr int kHdr = 8;                 // ints per stream in hdr / cnt
+enum { H_NLIVE = 0, H_NEXT = 1, H_NFREE = 2 };
+enum { C_M1 = 0, C_M2 = 1, C_NU = 2, C_MODE = 3, C_NMATCH = 4, C_NUT = 5, C_STATUS = 6 };
+enum { MODE_SKIP = 0, MODE_EMPTY = 1, MODE_NORMAL = 2 };
+enum { R_NMATCH = 0, R_NUT = 1, R_NUD = 2, R_NLIVE = 3, R_NEXT = 4, R_STATUS = 5, R_M1 = 6, R_M2 = 7, R_HDR = 8 };
+
+struct Dev {
+    int S, MT, MD, HIST, res_stride;
+    // persistent state
+    double *kf_x, *kf_P, *last_bbox, *last_conf, *last_cost;
+    uint8_t* kf_stage;
+    float *ema, *bank;
+    int *bank_len, *bank_head, *tid, *miss, *age, *last_frame, *order, *free_list, *hdr;
+    // per-step scratch
+    float *det_unit, *det_z, *det_boxf, *det_conff, *prev_boxf, *prev_conff, *C1, *C1T, *C2, *C2T;
+    double* gate_SI;
+    int *rows_main, *rows_reid, *cnt, *ud1, *det_used, *m_row, *m_det, *m_app, *tmp;
+    // configuration
+    cost::PairWeights pw;
+    double maha_thr, cost_max, conf_update_min, cost_update_max, reid_only_cost_max, init_conf_min;
+    float ema_a, ema_b;
+    int topk, max_age, lost_reid_after;
+    // this step's inputs / output
+    const int* n_det;
+    const double *boxes, *confs;
+    const float* embs;
+    const int* frame_id;
+    int* result;
+};
+
+__device__ __forceinline__ int* res_matches(const Dev& d, int* res) { return res + R_HDR; }
+__device__ __forceinline__ int* res_ut(const Dev& d, int* res) { return res + R_HDR + 2 * d.MD; }
+__device__ __forceinline__ int* res_ud(const Dev& d, int* res) { return res + R_HDR + 2 * d.MD + d.MT; }
+
+// Ordered stream compaction over [0, n): emit(position, i) for every i with pred(i), ascending.
+// All threads of the CTA must call; returns the count.  scratch: kThreads / 32 ints of smem.
+template <typename Pred, typename Emit>
+__device__ inline int block_compact(int n, Pred pred, Emit emit, int* scratch) {
+    int base = 0;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int i0 = 0; i0 < n; i0 += blockDim.x) {
+        const int i = i0 + threadIdx.x;
+        const bool p = i < n && pred(i);
+        const unsigned m = __ballot_sync(0xffffffffu, p);
+        if (lane == 0) scratch[w] = __popc(m);
+        __syncthreads();
+        int off = 0, tot = 0;
+        for (int k = 0; k < nw; ++k) {
+            const int c = scratch[k];
+            if (k < w) off += c;
+            tot += c;
+        }
+        if (p) emit(base + off + __popc(m & ((1u << lane) - 1u)), i);
+        base += tot;
+        __syncthreads();
+    }
+    return base;
+}
+
+__device__ __forceinline__ void load_kf(const Dev& d, size_t slot, double* x, double* P) {
+    const double2* px = reinterpret_cast<const double2*>(d.kf_x + slot * 8);
+    const double2* pP = reinterpret_cast<const double2*>(d.kf_P + slot * 64);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const double2 v = px[k]; x[2 * k] = v.x; x[2 * k + 1] = v.y; }
+#pragma unroll
+    for (int k = 0; k < 32; ++k) { const double2 v = pP[k]; P[2 * k] = v.x; P[2 * k + 1] = v.y; }
+}
+__device__ __forceinline__ void store_kf(const Dev& d, size_t slot, const double* x, const double* P) {
+    double2* px = reinterpret_cast<double2*>(d.kf_x + slot * 8);
+    double2* pP = reinterpret_cast<double2*>(d.kf_P + slot * 64);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) px[k] = make_double2(x[2 * k], x[2 * k + 1]);
+#pragma unroll
+    for (int k = 0; k < 32; ++k) pP[k] = make_double2(P[2 * k], P[2 * k + 1]);
+}
+
+// purge_dead (:357-360): drop slots with miss > max_age from `order`, return them to the free list.
+__device__ inline void purge(const Dev& d, int s, int nl, int* scratch) {
+    int* order = d.order + (size_t)s * d.MT;
+    int* tmp = d.tmp + (size_t)s * d.MT;
+    int* fl = d.free_list + (size_t)s * d.MT;
+    int* hdr = d.hdr + s * kHdr;
+    const size_t sb = (size_t)s * d.MT;
+    for (int i = threadIdx.x; i < nl; i += blockDim.x) tmp[i] = order[i];
+    __syncthreads();
+    const int nfree = hdr[H_NFREE];
+    const int keep = block_compact(nl, [&](int i) { return d.miss[sb + tmp[i]] <= d.max_age; },
+                                   [&](int pos, int i) { order[pos] = tmp[i]; }, scratch);
+    const int dead = block_compact(nl, [&](int i) { return d.miss[sb + tmp[i]] > d.max_age; },
+                                   [&](int pos, int i) { fl[nfree + pos] = tmp[i]; }, scratch);
+    if (threadIdx.x == 0) { hdr[H_NLIVE] = keep; hdr[H_NFREE] = nfree + dead; }
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) begin_kernel(Dev d) {
+    __shared__ int scratch[kThreads / 32];
+    const int s = blockIdx.x, tid = threadIdx.x;
+    int* hdr = d.hdr + s * kHdr;
+    int* cnt = d.cnt + s * kHdr;
+    int* res = d.result + (size_t)s * d.res_stride;
+    const size_t sb = (size_t)s * d.MT, db = (size_t)s * d.MD;
+    const int n = d.n_det[s], nl = hdr[H_NLIVE];
+    int* order = d.order + sb;
+    if (n < 0) {                                   // stream idle this step
+        if (tid == 0) {
+            cnt[C_MODE] = MODE_SKIP;
+            res[R_NMATCH] = res[R_NUT] = res[R_NUD] = res[R_STATUS] = res[R_M1] = res[R_M2] = 0;
+            res[R_NLIVE] = nl;
+            res[R_NEXT] = hdr[H_NEXT];
+        }
+        return;
+    }
+    if (n == 0) {                                  // :467-471 -- every track missed, NO predict
+        int* ut = res_ut(d, res);
+        for (int p = tid; p < nl; p += blockDim.x) {
+            const size_t slot = sb + order[p];
+            d.miss[slot] += 1;
+            ut[p] = d.tid[slot];
+        }
+        __syncthreads();
+        purge(d, s, nl, scratch);
+        if (tid == 0) {
+            cnt[C_MODE] = MODE_EMPTY;
+            res[R_NMATCH] = 0; res[R_NUT] = nl; res[R_NUD] = 0; res[R_STATUS] = 0; res[R_M1] = res[R_M2] = 0;
+            res[R_NLIVE] = hdr[H_NLIVE];
+            res[R_NEXT] = hdr[H_NEXT];
+        }
+        return;
+    }
+    // ---- detections: unit embeddings (:167-168), z (KalmanFilter.py:5-16), float32 boxes/confs ----
+    for (int j = tid >> 5; j < n; j += blockDim.x >> 5) {
+        const float4 v = reinterpret_cast<const float4*>(d.embs + (db + j) * cost::kD)[tid & 31];
+        reinterpret_cast<float4*>(d.det_unit + (db + j) * cost::kD)[tid & 31] = cost::unit_row(v);
+    }
+    for (int j = tid; j < n; j += blockDim.x) {
+        double b[4];
+        float z[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { b[k] = d.boxes[(db + j) * 4 + k]; d.det_boxf[(db + j) * 4 + k] = (float)b[k]; }
+        kf::box_to_z(b, z);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) d.det_z[(db + j) * 4 + k] = z[k];
+        d.det_conff[db + j] = (float)d.confs[db + j];
+        d.det_used[db + j] = 0;
+    }
+    // ---- predict_all (:340-345) ----------------------------------------------------------------
+    const float q[8] = {1.f, 1.f, 1.f, 1.f, 100.f, 100.f, 100.f, 100.f};    // KalmanFilter.py:91-95
+    for (int p = tid; p < nl; p += blockDim.x) {
+        const size_t slot = sb + order[p];
+        double x[8], P[64], b[4];
+        load_kf(d, slot, x, P);
+        kf::predict(x, P, d.kf_stage[slot], q);
+        store_kf(d, slot, x, P);
+        kf::x_to_box(x, b);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) d.last_bbox[slot * 4 + k] = b[k];
+    }
+    __syncthreads();
+    // ---- rows_main / rows_reid in ascending track-id order (:478-487) -----------------------------
+    int* rm = d.rows_main + sb;
+    int* rr = d.rows_reid + sb;
+    const int M1 = block_compact(nl, [&](int i) { return d.miss[sb + order[i]] <= d.lost_reid_after; },
+                                 [&](int pos, int i) { rm[pos] = order[i]; }, scratch);
+    const int M2 = block_compact(nl, [&](int i) { return d.miss[sb + order[i]] > d.lost_reid_after; },
+                                 [&](int pos, int i) { rr[pos] = order[i]; }, scratch);
+    // ---- per-row inputs of the stage-1 cost: predicted boxes as float32, gate inverse --------------
+    const float rdiag[4] = {1.f, 1.f, 1.f, 1.f};                           // KalmanFilter.py:98-99
+    for (int r = tid; r < M1; r += blockDim.x) {
+        const size_t slot = sb + rm[r];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) d.prev_boxf[(sb + r) * 4 + k] = (float)d.last_bbox[slot * 4 + k];
+        d.prev_conff[sb + r] = (float)d.last_conf[slot];
+        double P4[64];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) P4[a * 8 + b] = d.kf_P[slot * 64 + a * 8 + b];
+        kf::Gate g;
+        kf::gate_prepare(d.kf_x + slot * 8, P4, d.kf_stage[slot], rdiag, &g);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) d.gate_SI[(sb + r) * 16 + k] = g.SI[k];
+    }
+    if (tid == 0) {
+        cnt[C_M1] = M1; cnt[C_M2] = M2; cnt[C_NU] = 0; cnt[C_MODE] = MODE_NORMAL;
+        cnt[C_NMATCH] = 0; cnt[C_NUT] = 0; cnt[C_STATUS] = 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// STAGE 1: rows_main x all detections, full cost + gate.  STAGE 2: rows_reid x leftover dets, C_app.
+template <int STAGE>
+__global__ void __launch_bounds__(cost::kThreads) cost_kernel(Dev d) {
+    extern __shared__ __align__(16) float smem[];
+    const int s = blockIdx.z, r = blockIdx.y, j0 = blockIdx.x * cost::kTileN;
+    const int* cnt = d.cnt + s * kHdr;
+    if (cnt[C_MODE] != MODE_NORMAL) return;
+    const int M = STAGE == 1 ? cnt[C_M1] : cnt[C_M2];
+    const int N = STAGE == 1 ? d.n_det[s] : cnt[C_NU];
+    if (r >= M || j0 >= N) return;
+    const size_t sb = (size_t)s * d.MT, db = (size_t)s * d.MD;
+    const size_t slot = sb + (STAGE == 1 ? d.rows_main : d.rows_reid)[sb + r];
+    int T = d.bank_len[slot];
+    const float* rows = d.bank + slot * d.HIST * cost::kD;
+    if (T <= 0) { rows = d.ema + slot * cost::kD; T = 1; }        // :180-182 fallback to the EMA
+    // stage 2 gathers the leftover detections through ud1
+    __shared__ int s_idx[cost::kTileN];
+    if (threadIdx.x < cost::kTileN) {
+        const int j = j0 + threadIdx.x;
+        s_idx[threadIdx.x] = j < N ? (STAGE == 1 ? j : d.ud1[db + j]) : 0;
+    }
+    __syncthreads();
+    // app_cost_tile reads det rows [j0, j0+kTileN) of a [N][128] matrix; give it a gathered view.
+    const int tc = cost::bank_cap(T);
+    float* sBank = smem;
+    float* sDet = sBank + tc * cost::kD;
+    float* sSim = sDet + cost::kTileN * cost::kDetStride;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int t = warp; t < tc; t += cost::kThreads / 32) {
+        float4 v = make_float4(0, 0, 0, 0);
+        if (t < T) v = cost::unit_row(reinterpret_cast<const float4*>(rows + (size_t)t * cost::kD)[lane]);
+        reinterpret_cast<float4*>(sBank + t * cost::kD)[lane] = v;
+    }
+    for (int j = warp; j < cost::kTileN; j += cost::kThreads / 32) {
+        float4 v = make_float4(0, 0, 0, 0);
+        if (j0 + j < N) v = reinterpret_cast<const float4*>(d.det_unit + (db + s_idx[j]) * cost::kD)[lane];
+        reinterpret_cast<float4*>(sDet + j * cost::kDetStride)[lane] = v;
+    }
+    __syncthreads();
+    const float c_app = cost::sims_and_topk(sBank, sDet, sSim, tc, T, d.topk, true);
+    const int j = j0 + tid;
+    if (tid >= cost::kTileN || j >= N) return;
+    if (STAGE == 2) {
+        d.C2[(sb + r) * d.MD + j] = c_app;
+        d.C2T[(db + j) * d.MT + r] = c_app;
+        return;
+    }
+    const cost::PairCost pc = cost::pair_cost(d.prev_boxf + (sb + r) * 4, d.det_boxf + (db + j) * 4,
+                                              d.prev_conff[sb + r], d.det_conff[db + j], d.pw, c_app);
+    float total = pc.total;
+    const double d2 = kf::gate_d2(d.gate_SI + (sb + r) * 16, d.kf_x + slot * 8, d.kf_stage[slot],
+                                  d.det_z + (db + j) * 4);
+    if (d2 > d.maha_thr) total = 1e9f;                                  // :335-336
+    d.C1[(sb + r) * d.MD + j] = total;
+    d.C1T[(db + j) * d.MT + r] = total;
+}
+
+// update_matched (:375-448) for `nm` (row, det) pairs listed in m_row / m_det (det = global index).
+__device__ inline void update_matched(const Dev& d, int s, int nm, const int* rows, const float* C, int ldc,
+                                      const int* m_col, double cost_update_max, double maha_thr) {
+    const size_t sb = (size_t)s * d.MT, db = (size_t)s * d.MD;
+    const int frame = d.frame_id[s];
+    const float rdiag[4] = {1.f, 1.f, 1.f, 1.f};
+    for (int qd = threadIdx.x; qd < nm; qd += blockDim.x) {
+        const int r = d.m_row[sb + qd], j = d.m_det[sb + qd];
+        const size_t slot = sb + rows[r];
+        double x[8], P[64];
+        load_kf(d, slot, x, P);
+        const int st = kf::update(x, P, d.kf_stage[slot], d.det_z + (db + j) * 4, rdiag);
+        d.kf_stage[slot] = (uint8_t)st;
+        store_kf(d, slot, x, P);
+        const double conf = d.confs[db + j];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) d.last_bbox[slot * 4 + k] = d.boxes[(db + j) * 4 + k];
+        d.last_conf[slot] = conf;
+        d.last_frame[slot] = frame;
+        d.age[slot] += 1;
+        d.miss[slot] = 0;
+        const double c = (double)C[(size_t)r * ldc + m_col[qd]];
+        d.last_cost[slot] = c;
+        int app = !(conf < d.conf_update_min) && !(c > cost_update_max);          // :418-421
+        if (app && maha_thr < 1e17) {                                            // :424-426 posterior gate
+            kf::Gate g;
+            kf::gate_prepare(x, P, st, rdiag, &g);
+            if (kf::gate_d2(g.SI, g.xs, st, d.det_z + (db + j) * 4) > maha_thr) app = 0;
+        }
+        d.m_app[sb + qd] = app;
+    }
+    __syncthreads();
+    // EMA + bank push (:429-448), one warp per match
+    const int lane = threadIdx.x & 31;
+    for (int qd = threadIdx.x >> 5; qd < nm; qd += blockDim.x >> 5) {
+        if (!d.m_app[sb + qd]) continue;
+        const size_t slot = sb + rows[d.m_row[sb + qd]];
+        const float4 e = reinterpret_cast<const float4*>(d.det_unit + (db + d.m_det[sb + qd]) * cost::kD)[lane];
+        float4* pe = reinterpret_cast<float4*>(d.ema + slot * cost::kD) + lane;
+        const float4 o = *pe;
+        float4 f;
+        f.x = __fadd_rn(__fmul_rn(d.ema_a, o.x), __fmul_rn(d.ema_b, e.x));
+        f.y = __fadd_rn(__fmul_rn(d.ema_a, o.y), __fmul_rn(d.ema_b, e.y));
+        f.z = __fadd_rn(__fmul_rn(d.ema_a, o.z), __fmul_rn(d.ema_b, e.z));
+        f.w = __fadd_rn(__fmul_rn(d.ema_a, o.w), __fmul_rn(d.ema_b, e.w));
+        *pe = cost::unit_row(f);
+        int len = d.bank_len[slot], head = d.bank_head[slot], pos;
+        if (len < d.HIST) { pos = (head + len) % d.HIST; ++len; }
+        else { pos = head; head = (head + 1) % d.HIST; }
+        reinterpret_cast<float4*>(d.bank + (slot * d.HIST + pos) * cost::kD)[lane] = e;
+        __syncwarp();
+        if (lane == 0) { d.bank_len[slot] = len; d.bank_head[slot] = head; }
+    }
+    __syncthreads();
+}
+
+// hungarian_assign (hung.py:5-45) for this stream's matrix; fills m_row/m_det, marks misses.
+// Returns the number of matches; *n_unmatched_rows is the count appended to the unmatched list.
+template <int STAGE>
+__global__ void __launch_bounds__(kThreads) assign_kernel(Dev d, int smem_matrix_floats) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int scratch[kThreads / 32];
+    __shared__ int s_rc;
+    const int s = blockIdx.x, tid = threadIdx.x;
+    int* cnt = d.cnt + s * kHdr;
+    if (cnt[C_MODE] != MODE_NORMAL) return;
+    int* hdr = d.hdr + s * kHdr;
+    int* res = d.result + (size_t)s * d.res_stride;
+    const size_t sb = (size_t)s * d.MT, db = (size_t)s * d.MD;
+    const int M = STAGE == 1 ? cnt[C_M1] : cnt[C_M2];
+    const int N = STAGE == 1 ? d.n_det[s] : cnt[C_NU];
+    const int* rows = (STAGE == 1 ? d.rows_main : d.rows_reid) + sb;
+    const float* C = (STAGE == 1 ? d.C1 : d.C2) + sb * d.MD;
+    const float* CT = (STAGE == 1 ? d.C1T : d.C2T) + db * d.MT;
+    const double cmax = STAGE == 1 ? d.cost_max : d.reid_only_cost_max;
+    const int match0 = STAGE == 1 ? 0 : cnt[C_NMATCH], ut0 = STAGE == 1 ? 0 : cnt[C_NUT];
+    int* out_m = res_matches(d, res);
+    int* out_ut = res_ut(d, res);
+    int* m_col = d.tmp + sb;                        // column (local det index) of each match
+    int n_match = 0, n_ut = 0, n_left = N;
+
+    if (M > 0 && N > 0) {
+        const bool tall = M > N;
+        const int R = tall ? N : M, Cc = tall ? M : N;
+        const float* costp = tall ? CT : C;
+        int ld = tall ? d.MT : d.MD;
+        const lsap::Work w = lsap::carve(smem_raw, R, Cc);
+        if ((size_t)R * Cc <= (size_t)smem_matrix_floats) {
+            float* sc = reinterpret_cast<float*>(smem_raw + lsap::work_bytes(R, Cc));
+            for (int i = 0; i < R; ++i)
+                for (int j = tid; j < Cc; j += blockDim.x) sc[(size_t)i * Cc + j] = costp[(size_t)i * ld + j];
+            costp = sc;
+            ld = Cc;
+        }
+        __syncthreads();
+        const int nt = Cc <= 128 ? 32 : (Cc <= 512 ? 128 : kThreads);
+        if (tid < nt) {
+            const int rc = lsap::solve(costp, R, Cc, ld, w, tid, nt);
+            if (tid == 0) s_rc = rc;
+        }
+        __syncthreads();
+        if (s_rc != B200_OK) {                      // NaN / infeasible: scipy would raise
+            if (tid == 0) cnt[C_STATUS] = s_rc;
+        } else {
+            const int* col = tall ? w.r4c : w.c4r;  // assigned column of row r (-1: unassigned)
+            auto is_match = [&](int r) {
+                const int j = col[r];
+                return j >= 0 && (double)C[(size_t)r * d.MD + j] <= cmax;      // hung.py:35-40
+            };
+            n_match = block_compact(M, is_match, [&](int pos, int r) {
+                const int jl = col[r], j = STAGE == 1 ? jl : d.ud1[db + jl];
+                d.m_row[sb + pos] = r;
+                d.m_det[sb + pos] = j;
+                m_col[pos] = jl;
+                d.det_used[db + j] = 1;
+                out_m[2 * (match0 + pos)] = d.tid[sb + rows[r]];
+                out_m[2 * (match0 + pos) + 1] = j;
+            }, scratch);
+            n_ut = block_compact(M, [&](int r) { return !is_match(r); }, [&](int pos, int r) {
+                const size_t slot = sb + rows[r];
+                d.miss[slot] += 1;                                              // mark_missed :347-355
+                out_ut[ut0 + pos] = d.tid[slot];
+            }, scratch);
+            __syncthreads();
+            update_matched(d, s, n_match, rows, C, d.MD, m_col,
+                           STAGE == 1 ? d.cost_update_max : d.reid_only_cost_max, STAGE == 1 ? d.maha_thr : 1e18);
+        }
+    } else if (M > 0) {                             // no detections left for these rows: all missed
+        for (int r = tid; r < M; r += blockDim.x) {
+            const size_t slot = sb + rows[r];
+            d.miss[slot] += 1;
+            out_ut[ut0 + r] = d.tid[slot];
+        }
+        n_ut = M;
+        __syncthreads();
+    }
+
+    if (STAGE == 1) {
+        // leftover detections, ascending (hung.py:43)
+        n_left = block_compact(N, [&](int j) { return d.det_used[db + j] == 0; },
+                               [&](int pos, int j) { d.ud1[db + pos] = j; }, scratch);
+        if (tid == 0) { cnt[C_NU] = n_left; cnt[C_NMATCH] = n_match; cnt[C_NUT] = n_ut; }
+        return;
+    }
+
+    // ---- stage 2 tail: leftover dets, births (:362-373), purge (:357-360), result table ------------
+    int* out_ud = res_ud(d, res);
+    n_left = block_compact(N, [&](int jl) { return d.det_used[db + d.ud1[db + jl]] == 0; },
+                           [&](int pos, int jl) { out_ud[pos] = d.ud1[db + jl]; }, scratch);
+    const int nl = hdr[H_NLIVE], nfree = hdr[H_NFREE], next_id = hdr[H_NEXT];
+    int* order = d.order + sb;
+    const int* fl = d.free_list + sb;
+    int* born = d.m_row + sb;                       // det index of each birth, in order
+    const int want = block_compact(n_left, [&](int k) { return !(d.confs[db + out_ud[k]] < d.init_conf_min); },
+                                   [&](int pos, int k) { born[pos] = out_ud[k]; }, scratch);
+    const int nb = min(want, nfree);
+    const int frame = d.frame_id[s];
+    for (int b = tid; b < nb; b += blockDim.x) {
+        const int j = born[b], sl = fl[nfree - 1 - b];
+        const size_t slot = sb + sl;
+        double x[8], P[64], box[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { box[k] = d.boxes[(db + j) * 4 + k]; d.last_bbox[slot * 4 + k] = box[k]; }
+        kf::init_state(box, x, P);
+        store_kf(d, slot, x, P);
+        d.kf_stage[slot] = 0;
+        d.last_conf[slot] = d.confs[db + j];
+        d.last_cost[slot] = __longlong_as_double(0x7ff8000000000000LL);      // None
+        d.last_frame[slot] = frame;
+        d.tid[slot] = next_id + b;
+        d.miss[slot] = 0;
+        d.age[slot] = 1;
+        d.bank_len[slot] = 1;
+        d.bank_head[slot] = 0;
+        order[nl + b] = sl;
+    }
+    for (int i = tid; i < nb * (cost::kD / 4); i += blockDim.x) {              // creat_item :98-139
+        const int b = i / (cost::kD / 4), k = i % (cost::kD / 4);
+        const size_t slot = sb + fl[nfree - 1 - b];
+        const float4 e = reinterpret_cast<const float4*>(d.det_unit + (db + born[b]) * cost::kD)[k];
+        reinterpret_cast<float4*>(d.ema + slot * cost::kD)[k] = e;
+        reinterpret_cast<float4*>(d.bank + slot * d.HIST * cost::kD)[k] = e;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        hdr[H_NLIVE] = nl + nb;
+        hdr[H_NFREE] = nfree - nb;
+        hdr[H_NEXT] = next_id + nb;
+        if (want > nb && cnt[C_STATUS] == 0) cnt[C_STATUS] = B200_ECAPACITY;
+    }
+    __syncthreads();
+    purge(d, s, nl + nb, scratch);
+    if (tid == 0) {
+        res[R_NMATCH] = match0 + n_match;
+        res[R_NUT] = ut0 + n_ut;
+        res[R_NUD] = n_left;
+        res[R_NLIVE] = hdr[H_NLIVE];
+        res[R_NEXT] = hdr[H_NEXT];
+        res[R_STATUS] = cnt[C_STATUS];
+        res[R_M1] = cnt[C_M1];
+        res[R_M2] = cnt[C_M2];
+    }
+}
+
+// Packs one stream's live tracks, ascending track id, for b200_tracker_export.
+__global__ void export_kernel(Dev d, int s, int* ids, double* x, double* P, uint8_t* stage, float* ema, float* bank,
+                              int* bank_len, int* miss, int* age, double* last_bbox, double* last_conf,
+                              double* last_cost) {
+    const size_t sb = (size_t)s * d.MT;
+    const int nl = d.hdr[s * kHdr + H_NLIVE];
+    for (int p = blockIdx.x; p < nl; p += gridDim.x) {
+        const size_t slot = sb + d.order[sb + p];
+        const int t = threadIdx.x;
+        if (t == 0) {
+            ids[p] = d.tid[slot]; stage[p] = d.kf_stage[slot]; bank_len[p] = d.bank_len[slot];
+            miss[p] = d.miss[slot]; age[p] = d.age[slot]; last_conf[p] = d.last_conf[slot];
+            last_cost[p] = d.last_cost[slot];
+        }
+        if (t < 8) x[(size_t)p * 8 + t] = d.kf_x[slot * 8 + t];
+        if (t < 4) last_bbox[(size_t)p * 4 + t] = d.last_bbox[slot * 4 + t];
+        if (t < 64) P[(size_t)p * 64 + t] = d.kf_P[slot * 64 + t];
+        if (t < cost::kD) ema[(size_t)p * cost::kD + t] = d.ema[slot * cost::kD + t];
+        const int len = d.bank_len[slot], head = d.bank_head[slot];
+        for (int i = t; i < d.HIST * cost::kD; i += blockDim.x) {
+            const int row = i / cost::kD, k = i % cost::kD;
+            bank[((size_t)p * d.HIST + row) * cost::kD + k] =
+                row < len ? d.bank[(slot * d.HIST + (head + row) % d.HIST) * cost::kD + k] : 0.0f;
+        }
+    }
+}
+
+__global__ void reset_kernel(Dev d) {
+    const int s = blockIdx.x;
+    for (int i = threadIdx.x; i < d.MT; i += blockDim.x) d.free_list[(size_t)s * d.MT + i] = d.MT - 1 - i;
+    if (threadIdx.x == 0) {
+        d.hdr[s * kHdr + H_NLIVE] = 0;
+        d.hdr[s * kHdr + H_NEXT] = 0;
+        d.hdr[s * kHdr + H_NFREE] = d.MT;
+    }
+}
+
+}  // namespace trk
+}  // namespace b200
+
+using namespace b200;
+
+struct b200_tracker {
+    trk::Dev d;
+    void* arena = nullptr;          // one device allocation holding state + scratch + inputs + result
+    void* pinned = nullptr;         // host staging for step_host (inputs then result)
+    size_t in_bytes = 0, res_bytes = 0;
+    int* in_ndet = nullptr; int* in_frame = nullptr; double* in_boxes = nullptr; double* in_confs = nullptr;
+    float* in_embs = nullptr; int* dev_result = nullptr;
+    int rows_ub = 0;                // upper bound on live tracks of any stream (sizes the cost grids)
+    size_t assign_smem = 0;
+    int smem_matrix_floats = 0;
+};
+
+namespace {
+
+struct Carver {
+    size_t off = 0;
+    template <typename T> size_t take(size_t n) {
+        off = (off + 255) & ~(size_t)255;
+        const size_t at = off;
+        off += n * sizeof(T);
+        return at;
+    }
+};
+
+}  // namespace
+
+extern "C" int b200_tracker_create(b200_tracker** out, int n_streams, int max_tracks, int max_dets,
+                                   const b200_tracker_conf* conf) {
+    B200_REQUIRE(out && conf, "tracker_create: null pointer");
+    B200_REQUIRE(n_streams >= 1 && n_streams <= 65535, "tracker_create: n_streams %d out of range", n_streams);
+    B200_REQUIRE(max_tracks >= 1 && max_tracks <= 4096 && max_dets >= 1 && max_dets <= 4096,
+                 "tracker_create: capacities out of range (tracks %d, dets %d)", max_tracks, max_dets);
+    B200_REQUIRE(conf->hist_max >= 1 && conf->hist_max <= cost::kMaxBank, "tracker_create: hist_max %d outside [1,%d]",
+                 conf->hist_max, cost::kMaxBank);
+    B200_REQUIRE(conf->emb_top_k >= 1, "tracker_create: emb_top_k must be >= 1");
+    b200_tracker* t = new (std::nothrow) b200_tracker();
+    B200_REQUIRE(t, "tracker_create: out of host memory");
+    trk::Dev& d = t->d;
+    memset(&d, 0, sizeof(d));
+    const size_t S = n_streams, MT = max_tracks, MD = max_dets, H = conf->hist_max;
+    d.S = n_streams; d.MT = max_tracks; d.MD = max_dets; d.HIST = conf->hist_max;
+    d.res_stride = trk::R_HDR + 2 * max_dets + max_tracks + max_dets;
+    Carver c;
+#define TAKE(field, T, n) const size_t o_##field = c.take<T>(n)
+    TAKE(kf_x, double, S * MT * 8); TAKE(kf_P, double, S * MT * 64); TAKE(last_bbox, double, S * MT * 4);
+    TAKE(last_conf, double, S * MT); TAKE(last_cost, double, S * MT); TAKE(kf_stage, uint8_t, S * MT);
+    TAKE(ema, float, S * MT * 128); TAKE(bank, float, S * MT * H * 128);
+    TAKE(bank_len, int, S * MT); TAKE(bank_head, int, S * MT); TAKE(tid, int, S * MT); TAKE(miss, int, S * MT);
+    TAKE(age, int, S * MT); TAKE(last_frame, int, S * MT); TAKE(order, int, S * MT); TAKE(free_list, int, S * MT);
+    TAKE(hdr, int, S * trk::kHdr);
+    TAKE(det_unit, float, S * MD * 128); TAKE(det_z, float, S * MD * 4); TAKE(det_boxf, float, S * MD * 4);
+    TAKE(det_conff, float, S * MD); TAKE(prev_boxf, float, S * MT * 4); TAKE(prev_conff, float, S * MT);
+    TAKE(C1, float, S * MT * MD); TAKE(C1T, float, S * MT * MD); TAKE(C2, float, S * MT * MD);
+    TAKE(C2T, float, S * MT * MD); TAKE(gate_SI, double, S * MT * 16);
+    TAKE(rows_main, int, S * MT); TAKE(rows_reid, int, S * MT); TAKE(cnt, int, S * trk::kHdr);
+    TAKE(ud1, int, S * MD); TAKE(det_used, int, S * MD); TAKE(m_row, int, S * MT); TAKE(m_det, int, S * MT);
+    TAKE(m_app, int, S * MT); TAKE(tmp, int, S * MT);
+    // inputs (one contiguous block so step_host needs a single H2D copy) and the result table
+    const size_t o_in = c.take<double>(0);
+    TAKE(in_ndet, int, S); TAKE(in_frame, int, S); TAKE(in_boxes, double, S * MD * 4); TAKE(in_confs, double, S * MD);
+    TAKE(in_embs, float, S * MD * 128);
+    const size_t in_end = c.off;
+    TAKE(result, int, S * (size_t)d.res_stride);
+#undef TAKE
+    cudaError_t e = cudaMalloc(&t->arena, c.off);
+    if (e != cudaSuccess) {
+        delete t;
+        return fail(B200_ECUDA, "tracker_create: cudaMalloc(%zu bytes): %s", c.off, cudaGetErrorString(e));
+    }
+    char* base = static_cast<char*>(t->arena);
+    cudaMemset(base, 0, c.off);
+#define PTR(field, T) d.field = reinterpret_cast<T*>(base + o_##field)
+    PTR(kf_x, double); PTR(kf_P, double); PTR(last_bbox, double); PTR(last_conf, double); PTR(last_cost, double);
+    PTR(kf_stage, uint8_t); PTR(ema, float); PTR(bank, float); PTR(bank_len, int); PTR(bank_head, int); PTR(tid, int);
+    PTR(miss, int); PTR(age, int); PTR(last_frame, int); PTR(order, int); PTR(free_list, int); PTR(hdr, int);
+    PTR(det_unit, float); PTR(det_z, float); PTR(det_boxf, float); PTR(det_conff, float); PTR(prev_boxf, float);
+    PTR(prev_conff, float); PTR(C1, float); PTR(C1T, float); PTR(C2, float); PTR(C2T, float); PTR(gate_SI, double);
+    PTR(rows_main, int); PTR(rows_reid, int); PTR(cnt, int); PTR(ud1, int); PTR(det_used, int); PTR(m_row, int);
+    PTR(m_det, int); PTR(m_app, int); PTR(tmp, int);
+#undef PTR
+    t->in_ndet = reinterpret_cast<int*>(base + o_in_ndet);
+    t->in_frame = reinterpret_cast<int*>(base + o_in_frame);
+    t->in_boxes = reinterpret_cast<double*>(base + o_in_boxes);
+    t->in_confs = reinterpret_cast<double*>(base + o_in_confs);
+    t->in_embs = reinterpret_cast<float*>(base + o_in_embs);
+    t->dev_result = reinterpret_cast<int*>(base + o_result);
+    t->in_bytes = in_end - o_in;
+    t->res_bytes = S * (size_t)d.res_stride * sizeof(int);
+    e = cudaMallocHost(&t->pinned, t->in_bytes + t->res_bytes + 256);
+    if (e != cudaSuccess) {
+        cudaFree(t->arena);
+        delete t;
+        return fail(B200_ECUDA, "tracker_create: cudaMallocHost: %s", cudaGetErrorString(e));
+    }
+    // host offsets inside the pinned block mirror the device input block
+    d.pw = cost::PairWeights{(float)conf->w_app, (float)conf->w_bbox, (float)conf->w_conf, (float)conf->alpha,
+                             (float)conf->beta, 1e-6f};
+    d.maha_thr = conf->maha_thr; d.cost_max = conf->cost_max; d.conf_update_min = conf->conf_update_min;
+    d.cost_update_max = conf->cost_update_max; d.reid_only_cost_max = conf->reid_only_cost_max;
+    d.init_conf_min = conf->init_conf_min;
+    d.ema_a = (float)conf->ema_alpha;
+    d.ema_b = (float)(1.0 - conf->ema_alpha);
+    d.topk = conf->emb_top_k; d.max_age = conf->max_age; d.lost_reid_after = conf->lost_reid_after;
+    // shared memory of the assignment kernels: LSAP work arrays + the matrix when it fits
+    const int Rm = max_tracks < max_dets ? max_tracks : max_dets, Cm = max_tracks < max_dets ? max_dets : max_tracks;
+    const size_t wb = lsap::work_bytes(Rm, Cm), budget = 200 * 1024;
+    if (wb > budget) {
+        cudaFreeHost(t->pinned); cudaFree(t->arena); delete t;
+        return fail(B200_EINVAL, "tracker_create: %d x %d exceeds the assignment kernel's shared memory", max_tracks, max_dets);
+    }
+    size_t mat = (size_t)Rm * Cm * sizeof(float);
+    if (wb + mat > budget) mat = budget - wb;
+    t->smem_matrix_floats = (int)(mat / sizeof(float));
+    t->assign_smem = wb + mat;
+    cudaFuncSetAttribute(trk::assign_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t->assign_smem);
+    cudaFuncSetAttribute(trk::assign_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t->assign_smem);
+    cudaFuncSetAttribute(trk::cost_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cost::smem_bytes(cost::kMaxBank));
+    cudaFuncSetAttribute(trk::cost_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cost::smem_bytes(cost::kMaxBank));
+    trk::reset_kernel<<<n_streams, 128>>>(d);
+    e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        cudaFreeHost(t->pinned); cudaFree(t->arena); delete t;
+        return fail(B200_ECUDA, "tracker_create: %s", cudaGetErrorString(e));
+    }
+    g_launches.fetch_add(1);
+    t->rows_ub = 0;
+    *out = t;
+    return B200_OK;
+}
+
+extern "C" void b200_tracker_destroy(b200_tracker* t) {
+    if (!t) return;
+    cudaFreeHost(t->pinned);
+    cudaFree(t->arena);
+    delete t;
+}
+
+extern "C" int b200_tracker_reset(b200_tracker* t, void* stream) {
+    B200_REQUIRE(t, "tracker_reset: null handle");
+    trk::reset_kernel<<<t->d.S, 128, 0, as_stream(stream)>>>(t->d);
+    t->rows_ub = 0;
+    return check_launch("reset_kernel");
+}
+
+extern "C" int b200_tracker_result_stride(const b200_tracker* t) { return t ? t->d.res_stride : 0; }
+
+extern "C" int b200_tracker_step(b200_tracker* t, const int32_t* n_det, const double* boxes, const double* confs,
+                                 const float* embs, const int32_t* frame_id, int32_t* result, void* stream) {
+    B200_REQUIRE(t && n_det && boxes && confs && embs && frame_id && result, "tracker_step: null pointer");
+    cudaStream_t st = as_stream(stream);
+    trk::Dev d = t->d;
+    d.n_det = n_det; d.boxes = boxes; d.confs = confs; d.embs = embs; d.frame_id = frame_id; d.result = result;
+    const int tiles = (d.MD + cost::kTileN - 1) / cost::kTileN;
+    const size_t csm = cost::smem_bytes(d.HIST);
+    trk::begin_kernel<<<d.S, trk::kThreads, 0, st>>>(d);
+    int rc = check_launch("trk begin_kernel");
+    if (rc) return rc;
+    if (t->rows_ub > 0) {
+        trk::cost_kernel<1><<<dim3(tiles, t->rows_ub, d.S), cost::kThreads, csm, st>>>(d);
+        if ((rc = check_launch("trk cost_kernel<1>"))) return rc;
+    }
+    trk::assign_kernel<1><<<d.S, trk::kThreads, t->assign_smem, st>>>(d, t->smem_matrix_floats);
+    if ((rc = check_launch("trk assign_kernel<1>"))) return rc;
+    if (t->rows_ub > 0) {
+        trk::cost_kernel<2><<<dim3(tiles, t->rows_ub, d.S), cost::kThreads, csm, st>>>(d);
+        if ((rc = check_launch("trk cost_kernel<2>"))) return rc;
+    }
+    trk::assign_kernel<2><<<d.S, trk::kThreads, t->assign_smem, st>>>(d, t->smem_matrix_floats);
+    if ((rc = check_launch("trk assign_kernel<2>"))) return rc;
+    // without a read-back the live-track bound can only grow by the detections of this step
+    t->rows_ub = t->rows_ub + d.MD < d.MT ? t->rows_ub + d.MD : d.MT;
+    return B200_OK;
+}
+
+extern "C" int b200_tracker_step_host(b200_tracker* t, const int32_t* n_det_host, const double* boxes_host,
+                                      const double* confs_host, const float* embs_host, const int32_t* frame_id_host,
+                                      int32_t* result_host, void* stream) {
+    B200_REQUIRE(t && n_det_host && frame_id_host && result_host, "tracker_step_host: null pointer");
+    cudaStream_t st = as_stream(stream);
+    const trk::Dev& d = t->d;
+    char* pin = static_cast<char*>(t->pinned);
+    char* dev_in = reinterpret_cast<char*>(t->in_ndet);
+    auto host_of = [&](const void* dev_ptr) { return pin + (reinterpret_cast<const char*>(dev_ptr) - dev_in); };
+    int* h_ndet = reinterpret_cast<int*>(host_of(t->in_ndet));
+    int* h_frame = reinterpret_cast<int*>(host_of(t->in_frame));
+    double* h_boxes = reinterpret_cast<double*>(host_of(t->in_boxes));
+    double* h_confs = reinterpret_cast<double*>(host_of(t->in_confs));
+    float* h_embs = reinterpret_cast<float*>(host_of(t->in_embs));
+    for (int s = 0; s < d.S; ++s) {
+        const int n = n_det_host[s];
+        B200_REQUIRE(n <= d.MD, "tracker_step_host: stream %d has %d detections, capacity %d", s, n, d.MD);
+        h_ndet[s] = n;
+        h_frame[s] = frame_id_host[s];
+        if (n > 0) {
+            B200_REQUIRE(boxes_host && confs_host && embs_host, "tracker_step_host: null detection arrays");
+            memcpy(h_boxes + (size_t)s * d.MD * 4, boxes_host + (size_t)s * d.MD * 4, sizeof(double) * 4 * n);
+            memcpy(h_confs + (size_t)s * d.MD, confs_host + (size_t)s * d.MD, sizeof(double) * n);
+            memcpy(h_embs + (size_t)s * d.MD * 128, embs_host + (size_t)s * d.MD * 128, sizeof(float) * 128 * n);
+        }
+    }
+    B200_CUDA(cudaMemcpyAsync(dev_in, pin, t->in_bytes, cudaMemcpyHostToDevice, st));
+    const int rc = b200_tracker_step(t, t->in_ndet, t->in_boxes, t->in_confs, t->in_embs, t->in_frame, t->dev_result, stream);
+    if (rc) return rc;
+    char* h_res = pin + ((t->in_bytes + 255) & ~(size_t)255);
+    B200_CUDA(cudaMemcpyAsync(h_res, t->dev_result, t->res_bytes, cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaStreamSynchronize(st));
+    memcpy(result_host, h_res, t->res_bytes);
+    int ub = 0;
+    for (int s = 0; s < d.S; ++s) {
+        const int nl = result_host[(size_t)s * d.res_stride + trk::R_NLIVE];
+        ub = nl > ub ? nl : ub;
+    }
+    t->rows_ub = ub;                                    // exact after a read-back
+    return B200_OK;
+}
+
+extern "C" int b200_tracker_export(b200_tracker* t, int stream_idx, int32_t* ids, double* x, double* P, uint8_t* stage,
+                                   float* ema, float* bank, int32_t* bank_len, int32_t* miss, int32_t* age,
+                                   double* last_bbox, double* last_conf, double* last_cost, int32_t* next_id,
+                                   void* stream) {
+    B200_REQUIRE(t, "tracker_export: null handle");
+    const trk::Dev& d = t->d;
+    B200_REQUIRE(stream_idx >= 0 && stream_idx < d.S, "tracker_export: stream %d out of range", stream_idx);
+    cudaStream_t st = as_stream(stream);
+    const size_t MT = d.MT, H = d.HIST;
+    Carver c;
+    const size_t o_ids = c.take<int>(MT), o_x = c.take<double>(MT * 8), o_P = c.take<double>(MT * 64),
+                 o_stage = c.take<uint8_t>(MT), o_ema = c.take<float>(MT * 128), o_bank = c.take<float>(MT * H * 128),
+                 o_bl = c.take<int>(MT), o_miss = c.take<int>(MT), o_age = c.take<int>(MT),
+                 o_lb = c.take<double>(MT * 4), o_lc = c.take<double>(MT), o_lk = c.take<double>(MT);
+    char* buf = nullptr;
+    B200_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&buf), c.off, st));
+    trk::export_kernel<<<d.MT < 256 ? d.MT : 256, 128, 0, st>>>(
+        d, stream_idx, reinterpret_cast<int*>(buf + o_ids), reinterpret_cast<double*>(buf + o_x),
+        reinterpret_cast<double*>(buf + o_P), reinterpret_cast<uint8_t*>(buf + o_stage),
+        reinterpret_cast<float*>(buf + o_ema), reinterpret_cast<float*>(buf + o_bank), reinterpret_cast<int*>(buf + o_bl),
+        reinterpret_cast<int*>(buf + o_miss), reinterpret_cast<int*>(buf + o_age), reinterpret_cast<double*>(buf + o_lb),
+        reinterpret_cast<double*>(buf + o_lc), reinterpret_cast<double*>(buf + o_lk));
+    int rc = check_launch("trk export_kernel");
+    if (rc) return rc;
+    int hdr[trk::kHdr];
+    B200_CUDA(cudaMemcpyAsync(hdr, d.hdr + stream_idx * trk::kHdr, sizeof(hdr), cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaStreamSynchronize(st));
+    const size_t n = hdr[trk::H_NLIVE];
+#define PULL(dst, off, T, per) if (dst && n) B200_CUDA(cudaMemcpyAsync(dst, buf + off, sizeof(T) * (per) * n, cudaMemcpyDeviceToHost, st))
+    PULL(ids, o_ids, int, 1); PULL(x, o_x, double, 8); PULL(P, o_P, double, 64); PULL(stage, o_stage, uint8_t, 1);
+    PULL(ema, o_ema, float, 128); PULL(bank, o_bank, float, H * 128); PULL(bank_len, o_bl, int, 1);
+    PULL(miss, o_miss, int, 1); PULL(age, o_age, int, 1); PULL(last_bbox, o_lb, double, 4);
+    PULL(last_conf, o_lc, double, 1); PULL(last_cost, o_lk, double, 1);
+#undef PULL
+    if (next_id) *next_id = hdr[trk::H_NEXT];
+    B200_CUDA(cudaStreamSynchronize(st));
+    B200_CUDA(cudaFreeAsync(buf, st));
+    return (int)n;
+}

@@ -1,0 +1,318 @@
+"""GPU-resident tracker with the reference's surface (model/mainTracking.py).
+
+* ``Tracking``            - drop-in for the reference class: ``Tracking().update(obj)`` returns
+                            ``(matches_tid, unmatched_track_ids, unmatched_dets)`` (mainTracking.py:450-610).
+* ``MultiStreamTracker``  - the same association step for S independent video streams per launch
+                            (the batching the reference lacks).
+
+All state (Kalman filters, EMA embeddings, history banks, ages) lives on the device inside a
+``b200_tracker`` handle; one ``update`` is one host->device copy of the detections, five kernels and
+one device->host copy of a small result table.  There is no CPU fallback.
+"""
+import ctypes
+from typing import Any, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import yaml
+
+from . import _lib, cost as cost_ops, kalman as kalman_ops
+
+# mainTracking.py:55-96 -- defaults used when a key is missing from the YAML `tracker` block.
+CODE_DEFAULTS = dict(
+    init_conf_min=0.5, hist_max=10, emb_top_k=5, app_tau=0.07, eps=1e-12, w_app=1.0, w_bbox=0.3, w_conf=0.2,
+    alpha=1.0, beta=0.5, unmatch_cost=10.0, cost_max=50.0, max_age=30, ema_alpha=0.9, conf_update_min=0.55,
+    cost_update_max=30.0, maha_thr=9.49, lost_reid_after=60, reid_sim_min=0.6)
+
+# model/conf/conf.yaml:2-24 -- the tracker block the reference ships.
+SHIPPED_CONF = dict(
+    init_conf_min=0.5, hist_max=30, emb_top_k=5, app_tau=0.07, eps=1e-12, w_app=1.0, w_bbox=0.3, w_conf=0.2,
+    alpha=1.0, beta=0.5, unmatch_cost=10.0, cost_max=50.0, max_age=120, ema_alpha=0.9, conf_update_min=0.55,
+    cost_update_max=30.0, maha_thr=9.49, lost_reid_after=50, reid_sim_min=0.6, reid_only_cost_max=0.4)
+
+R_NMATCH, R_NUT, R_NUD, R_NLIVE, R_NEXT, R_STATUS, R_M1, R_M2, R_HDR = range(9)
+
+
+def load_conf(path: str) -> Dict[str, Any]:
+    """mainTracking.py:11-13."""
+    with open(path, "r", encoding="utf-8") as f:
+        return yaml.safe_load(f)
+
+
+def resolve_conf(tcfg: Dict[str, Any]) -> Dict[str, Any]:
+    """Applies the reference's per-key defaults and the reid_only_cost_max rule (:92-96)."""
+    c = dict(CODE_DEFAULTS)
+    c.update({k: v for k, v in tcfg.items() if v is not None})
+    if "reid_only_cost_max" not in tcfg:
+        c["reid_only_cost_max"] = 1.0 - float(c["reid_sim_min"])
+    for k in ("hist_max", "emb_top_k", "max_age", "lost_reid_after"):
+        c[k] = int(c[k])
+    return c
+
+
+def _c_conf(c):
+    s = _lib.tracker_conf()
+    for name, _ in _lib.tracker_conf._fields_:
+        setattr(s, name, c[name])
+    return s
+
+
+class MultiStreamTracker:
+    """S independent trackers stepped by the same kernel launches.
+
+    Detections are passed as dense host arrays padded to ``max_dets`` per stream:
+    ``n_det[S]`` (-1 = stream idle, 0 = empty frame), ``boxes[S,max_dets,4]`` float64 xyxy,
+    ``confs[S,max_dets]`` float64, ``embs[S,max_dets,128]`` float32, ``frame_ids[S]``.
+    """
+
+    def __init__(self, n_streams: int, conf: Optional[Dict[str, Any]] = None, max_tracks: int = 256,
+                 max_dets: int = 128, device=None):
+        if not torch.cuda.is_available():
+            raise _lib.B200Error("no CUDA device: this package has no CPU path")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.conf = resolve_conf(SHIPPED_CONF if conf is None else conf)
+        self.S, self.max_tracks, self.max_dets = int(n_streams), int(max_tracks), int(max_dets)
+        self._h = ctypes.c_void_p()
+        cc = _c_conf(self.conf)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().b200_tracker_create(ctypes.byref(self._h), self.S, self.max_tracks, self.max_dets,
+                                                      ctypes.byref(cc)))
+        self.stride = _lib.lib().b200_tracker_result_stride(self._h)
+        self._res = np.zeros((self.S, self.stride), dtype=np.int32)
+        self.n_live = np.zeros(self.S, dtype=np.int64)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            _lib.lib().b200_tracker_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reset(self):
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().b200_tracker_reset(self._h, _lib.stream_ptr(self.device)))
+        self.n_live[:] = 0
+
+    # -- one frame-step for every stream, host arrays in, host result table out -------------------
+    def step(self, n_det, boxes, confs, embs, frame_ids) -> np.ndarray:
+        n_det = np.ascontiguousarray(n_det, dtype=np.int32).reshape(self.S)
+        frame_ids = np.ascontiguousarray(frame_ids, dtype=np.int32).reshape(self.S)
+        boxes = np.ascontiguousarray(boxes, dtype=np.float64).reshape(self.S, self.max_dets, 4)
+        confs = np.ascontiguousarray(confs, dtype=np.float64).reshape(self.S, self.max_dets)
+        embs = np.ascontiguousarray(embs, dtype=np.float32).reshape(self.S, self.max_dets, 128)
+        if (self.n_live + np.maximum(n_det, 0) > self.max_tracks).any():
+            raise _lib.B200Error("tracker capacity: live tracks + detections could exceed max_tracks=%d; "
+                                 "construct the tracker with a larger max_tracks" % self.max_tracks)
+        p = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+        with torch.cuda.device(self.device):
+            rc = _lib.lib().b200_tracker_step_host(self._h, p(n_det), p(boxes), p(confs), p(embs), p(frame_ids),
+                                                   p(self._res), _lib.stream_ptr(self.device))
+        _lib.check(rc)
+        self.n_live[:] = self._res[:, R_NLIVE]
+        bad = np.nonzero(self._res[:, R_STATUS])[0]
+        if len(bad):
+            st = int(self._res[bad[0], R_STATUS])
+            if st == _lib.ENUMERIC:
+                raise ValueError("matrix contains invalid numeric entries (stream %d)" % bad[0])
+            if st == _lib.EINFEASIBLE:
+                raise ValueError("cost matrix is infeasible (stream %d)" % bad[0])
+            raise _lib.B200Error("tracker step failed on stream %d with status %d" % (bad[0], st))
+        return self._res
+
+    # -- device-resident inputs, asynchronous on the current stream (no read-back) ------------------
+    def step_device(self, n_det: torch.Tensor, boxes: torch.Tensor, confs: torch.Tensor, embs: torch.Tensor,
+                    frame_ids: torch.Tensor, result: Optional[torch.Tensor] = None) -> torch.Tensor:
+        for t, dt in ((n_det, torch.int32), (boxes, torch.float64), (confs, torch.float64), (embs, torch.float32),
+                      (frame_ids, torch.int32)):
+            _lib.require_cuda(t, "input")
+            if t.dtype != dt or not t.is_contiguous():
+                raise TypeError("step_device: wrong dtype or non-contiguous input")
+        if result is None:
+            result = torch.empty((self.S, self.stride), dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = _lib.lib().b200_tracker_step(self._h, _lib.ptr(n_det), _lib.ptr(boxes), _lib.ptr(confs), _lib.ptr(embs),
+                                              _lib.ptr(frame_ids), _lib.ptr(result), _lib.stream_ptr(self.device))
+        _lib.check(rc)
+        return result
+
+    def decode(self, row: np.ndarray):
+        """Result-table row -> (matches_tid, unmatched_track_ids, unmatched_dets) as Tracking.update returns."""
+        MD, MT = self.max_dets, self.max_tracks
+        nm, nut, nud = int(row[R_NMATCH]), int(row[R_NUT]), int(row[R_NUD])
+        m = row[R_HDR:R_HDR + 2 * nm].reshape(nm, 2)
+        ut = row[R_HDR + 2 * MD:R_HDR + 2 * MD + nut]
+        ud = row[R_HDR + 2 * MD + MT:R_HDR + 2 * MD + MT + nud]
+        return [(int(a), int(b)) for a, b in m], [int(v) for v in ut], [int(v) for v in ud]
+
+    def export(self, stream: int = 0) -> Dict[str, np.ndarray]:
+        """Copies one stream's live tracks (ascending track id) to host arrays."""
+        MT, H = self.max_tracks, self.conf["hist_max"]
+        out = dict(ids=np.zeros(MT, np.int32), x=np.zeros((MT, 8)), P=np.zeros((MT, 8, 8)), stage=np.zeros(MT, np.uint8),
+                   ema=np.zeros((MT, 128), np.float32), bank=np.zeros((MT, H, 128), np.float32),
+                   bank_len=np.zeros(MT, np.int32), miss=np.zeros(MT, np.int32), age=np.zeros(MT, np.int32),
+                   last_bbox=np.zeros((MT, 4)), last_conf=np.zeros(MT), last_cost=np.zeros(MT))
+        nxt = ctypes.c_int32(0)
+        p = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+        with torch.cuda.device(self.device):
+            n = _lib.lib().b200_tracker_export(
+                self._h, int(stream), p(out["ids"]), p(out["x"]), p(out["P"]), p(out["stage"]), p(out["ema"]),
+                p(out["bank"]), p(out["bank_len"]), p(out["miss"]), p(out["age"]), p(out["last_bbox"]),
+                p(out["last_conf"]), p(out["last_cost"]), ctypes.byref(nxt), _lib.stream_ptr(self.device))
+        if n < 0:
+            _lib.check(n)
+        out = {k: v[:n] for k, v in out.items()}
+        out["next_id"] = int(nxt.value)
+        return out
+
+
+class TrackView:
+    """Read-only host snapshot of one track (TrackState + TrackMemory, mainTracking.py:15-42)."""
+
+    def __init__(self, snap, i):
+        self.track_id = int(snap["ids"][i])
+        self.miss_count = int(snap["miss"][i])
+        self.age = int(snap["age"][i])
+        self.state = "ACTIVE" if self.miss_count == 0 else "LOST"
+        st = int(snap["stage"][i])
+        self.x = snap["x"][i].reshape(8, 1) if st >= 2 else snap["x"][i].reshape(8, 1).astype(np.float32)
+        self.P = snap["P"][i] if st >= 1 else snap["P"][i].astype(np.float32)
+        self.encoder_feat = snap["ema"][i]
+        n = int(snap["bank_len"][i])
+        self.feat_historical = [snap["bank"][i, t] for t in range(n)]
+        self.last_bbox = tuple(float(v) for v in snap["last_bbox"][i])
+        self.last_conf = float(snap["last_conf"][i])
+        c = float(snap["last_cost"][i])
+        self.last_match_cost = None if np.isnan(c) else c
+
+
+class Tracking:
+    """Drop-in for the reference's ``Tracking`` (model/mainTracking.py:45).
+
+    ``Tracking()`` reads ``model/conf/conf.yaml`` relative to the working directory exactly like the
+    reference (:47); pass ``conf=`` (a tracker block) to skip the file.  ``max_tracks`` / ``max_dets``
+    size the device-side state (the reference is unbounded).
+    """
+
+    def __init__(self, conf_path: str = "model/conf/conf.yaml", *, conf: Optional[Dict[str, Any]] = None,
+                 max_tracks: int = 512, max_dets: int = 256, device=None):
+        if conf is None:
+            full = load_conf(conf_path)
+            if "tracker" not in full:
+                raise KeyError("Missing 'tracker' section in YAML config.")
+            conf = full["tracker"]
+        self._ms = MultiStreamTracker(1, conf, max_tracks, max_dets, device)
+        c = self._ms.conf
+        for k, v in c.items():                       # same attribute names as the reference (:55-96)
+            setattr(self, "tau" if k == "app_tau" else k, v)
+        MD = self._ms.max_dets
+        self._boxes = np.zeros((1, MD, 4), np.float64)
+        self._confs = np.zeros((1, MD), np.float64)
+        self._embs = np.zeros((1, MD, 128), np.float32)
+        self._snap = None
+
+    @property
+    def device(self):
+        return self._ms.device
+
+    # -- the call the pipeline makes (tracking.py:326) ---------------------------------------------
+    def update(self, obj: Dict):
+        det_embs = obj.get("embs", []) or []
+        det_boxes = obj.get("bboxes", []) or []
+        det_confs = obj.get("confs", []) or []
+        input_hw = obj.get("input_hw", None)
+        frame_id = obj.get("frame_id", None)
+        if input_hw is None:
+            raise ValueError("obj['input_hw'] is required")
+        if frame_id is None:
+            raise ValueError("obj['frame_id'] is required")
+        if not (len(det_embs) == len(det_boxes) == len(det_confs)):
+            raise ValueError("Length mismatch: embs/bboxes/confs must have same length")
+        N = len(det_boxes)
+        if N:
+            e = np.stack([np.asarray(v, dtype=np.float32).reshape(-1) for v in det_embs], axis=0)
+            if e.shape[1] != 128:
+                raise ValueError(f"det_embs must be 128D, got {e.shape}")
+            return self.update_arrays(np.asarray(det_boxes, dtype=np.float64), np.asarray(det_confs, dtype=np.float64),
+                                      e, int(frame_id))
+        return self.update_arrays(np.zeros((0, 4)), np.zeros((0,)), np.zeros((0, 128), np.float32), int(frame_id))
+
+    def update_arrays(self, boxes: np.ndarray, confs: np.ndarray, embs: np.ndarray, frame_id: int):
+        """Array form of ``update``: boxes [N,4] float64 xyxy, confs [N], embs [N,128] float32."""
+        N = boxes.shape[0]
+        if N > self._ms.max_dets:
+            raise ValueError("%d detections exceed max_dets=%d" % (N, self._ms.max_dets))
+        self._boxes[0, :N] = boxes
+        self._confs[0, :N] = confs
+        self._embs[0, :N] = embs
+        res = self._ms.step([N], self._boxes, self._confs, self._embs, [frame_id])
+        self._snap = None
+        return self._ms.decode(res[0])
+
+    # -- state inspection ---------------------------------------------------------------------------
+    def snapshot(self) -> Dict[str, np.ndarray]:
+        if self._snap is None:
+            self._snap = self._ms.export(0)
+        return self._snap
+
+    @property
+    def tracks(self) -> Dict[int, TrackView]:
+        s = self.snapshot()
+        return {int(s["ids"][i]): TrackView(s, i) for i in range(len(s["ids"]))}
+
+    @property
+    def next_id(self) -> int:
+        return self.snapshot()["next_id"]
+
+    def _rows(self, row_to_tid):
+        s = self.snapshot()
+        pos = {int(t): i for i, t in enumerate(s["ids"])}
+        return s, [pos[int(t)] for t in row_to_tid]
+
+    # -- operator-level queries over the device state (read-only) -----------------------------------
+    @torch.no_grad()
+    def build_C_app_topk(self, *, row_to_tid: List[int], det_embs: List[np.ndarray], device=None, topk: int = 5,
+                         use_topk_mean: bool = True, fallback_to_ema: bool = True) -> torch.Tensor:
+        """mainTracking.py:141-211."""
+        M, N = len(row_to_tid), len(det_embs)
+        if M == 0 or N == 0:
+            return torch.zeros((M, N), device=self.device)
+        s, rows = self._rows(row_to_tid)
+        det = torch.from_numpy(np.stack([np.asarray(e, dtype=np.float32).reshape(-1) for e in det_embs])).to(self.device)
+        bank = torch.from_numpy(s["bank"][rows]).to(self.device)
+        lens = torch.from_numpy(s["bank_len"][rows]).to(self.device)
+        fb = torch.from_numpy(s["ema"][rows]).to(self.device) if fallback_to_ema else None
+        return cost_ops.app_cost_topk(bank, lens, det, topk=topk, use_topk_mean=use_topk_mean, fallback=fb)
+
+    @torch.no_grad()
+    def cal_cost(self, *, row_to_tid, det_embs, det_boxes, det_confs, input_hw, device=None, assign=None):
+        """mainTracking.py:213-303."""
+        s, rows = self._rows(row_to_tid)
+        for e in det_embs:
+            if np.asarray(e).reshape(-1).shape[0] != 128:
+                raise ValueError("det_embs must be 128D")
+        C_app = self.build_C_app_topk(row_to_tid=row_to_tid, det_embs=det_embs, topk=self.emb_top_k)
+        return cost_ops.cal_cost(C_app=C_app, boxes_prev=s["last_bbox"][rows].tolist(), boxes_cur=det_boxes,
+                                 input_hw=input_hw, conf_prev=s["last_conf"][rows].tolist(), conf_cur=det_confs,
+                                 w_app=self.w_app, w_bbox=self.w_bbox, w_conf=self.w_conf, alpha=self.alpha,
+                                 beta=self.beta, assign=assign, unmatch_cost=self.unmatch_cost)
+
+    def apply_kalman_gating(self, C_total_np: np.ndarray, row_to_tid: List[int], det_boxes, *, maha_thr: float = 13.28,
+                            INF: float = 1e9) -> np.ndarray:
+        """mainTracking.py:306-338: gates ``C_total_np`` in place and returns it."""
+        M, N = C_total_np.shape
+        if M == 0 or N == 0:
+            return C_total_np
+        s, rows = self._rows(row_to_tid)
+        bk = kalman_ops.BatchedKalman.__new__(kalman_ops.BatchedKalman)
+        bk.device, bk.M = self.device, M
+        bk.x = torch.from_numpy(s["x"][rows]).to(self.device)
+        bk.P = torch.from_numpy(s["P"][rows]).to(self.device)
+        bk.stage = torch.from_numpy(s["stage"][rows]).to(self.device)
+        bk.r = torch.ones(4, dtype=torch.float32, device=self.device)
+        d2 = bk.maha(det_boxes).cpu().numpy()
+        C_total_np[d2 > float(maha_thr)] = float(INF)
+        return C_total_np

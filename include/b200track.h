@@ -86,9 +86,11 @@ int b200_kalman_init(const double* boxes_xyxy, int M, double* x, double* P, uint
 int b200_kalman_predict(double* x, double* P, const uint8_t* stage, int M, const float* q_diag,
                         double* pred_boxes_xyxy /* [M,4] or NULL: KalmanFilter.py:19-33 */,
                         void* stream);                               /* mainTracking.py:340-345 */
-/* det_of_track[M]: index into boxes_xyxy[N,4] (float64) or -1 = no update for that track. */
+/* det_of_track[M]: index into meas[N,4] (float64) or -1 = no update for that track.  meas rows
+ * are xyxy boxes (meas_is_z == 0; converted by bbox_xyxy_to_z, KalmanFilter.py:5-16) or already
+ * (cx, cy, a, h) measurements (meas_is_z != 0; rounded to float32 like the reference's z). */
 int b200_kalman_update(double* x, double* P, uint8_t* stage, int M, const int32_t* det_of_track,
-                       const double* boxes_xyxy, const float* r_diag, void* stream);
+                       const double* meas, int meas_is_z, const float* r_diag, void* stream);
                                                                      /* mainTracking.py:400 */
 /* d2[M,ldd] float64 = squared Mahalanobis distance of every (track, box) pair
  * (KalmanFilter.py:105-116); if C != NULL, C[i,j] = inf_value where d2 > maha_thr

@@ -1,0 +1,179 @@
+"""GPU parity of the fused, GPU-resident tracker (Tracking.update) against the golden traces of
+the live reference and against the oracle tracker on larger synthetic scenes."""
+import numpy as np
+import pytest
+
+from conftest import assert_close, load_golden
+from oracle import tracker_ref
+
+pytestmark = pytest.mark.gpu
+
+import alufe_b200  # noqa: E402,F401
+from alufe_b200 import Tracking, MultiStreamTracker, SHIPPED_CONF, synth  # noqa: E402
+from alufe_b200 import _lib  # noqa: E402
+
+
+def _compare_state(trk, want_ids, want, what):
+    """want: dict with x, P, ema, bank (list per track), miss, age, last_bbox."""
+    s = trk.snapshot()
+    assert s["ids"].tolist() == list(want_ids), what
+    assert_close(s["x"], want["x"], rtol=1e-5, atol=1e-6, what=what + " x")
+    assert_close(s["P"], want["P"], rtol=1e-5, atol=1e-5, what=what + " P")
+    assert_close(s["ema"], want["ema"], rtol=1e-5, atol=1e-6, what=what + " ema")
+    assert s["miss"].tolist() == list(want["miss"]), what
+    assert s["age"].tolist() == list(want["age"]), what
+    assert_close(s["last_bbox"], want["last_bbox"], rtol=1e-5, atol=1e-5, what=what + " last_bbox")
+    assert s["bank_len"].tolist() == [len(b) for b in want["bank"]], what
+    for r, b in enumerate(want["bank"]):
+        if len(b):
+            assert_close(s["bank"][r, :len(b)], np.stack(b), rtol=1e-5, atol=1e-6, what=what + " bank")
+
+
+@pytest.mark.parametrize("name", ["c1_steady", "churn"])
+def test_tracker_vs_golden_reference_trace(name):
+    g = load_golden("tracker_" + name)
+    cfg = dict(SHIPPED_CONF)
+    for k in g.files:
+        if k.startswith("cfg_"):
+            cfg[k[4:]] = int(g[k]) if k[4:] in ("lost_reid_after", "max_age", "hist_max") else float(g[k])
+    trk = Tracking(conf=cfg, max_tracks=64, max_dets=32)
+    for f in range(int(g["n_frames"])):
+        p = "f%03d_" % f
+        obj = {"embs": [e for e in g[p + "embs"]], "bboxes": g[p + "boxes"].tolist(), "confs": g[p + "confs"].tolist(),
+               "input_hw": (int(g["H"]), int(g["W"])), "frame_id": f}
+        m, ut, ud = trk.update(obj)
+        assert np.array_equal(np.array(m, dtype=np.int64).reshape(-1, 2), g[p + "matches"]), p
+        assert ut == g[p + "unmatched_tracks"].tolist(), p
+        assert ud == g[p + "unmatched_dets"].tolist(), p
+        if p + "st_ids" in g:
+            n = g[p + "st_bank_len"]
+            want = dict(x=g[p + "st_x"], P=g[p + "st_P"], ema=g[p + "st_ema"], miss=g[p + "st_miss"].tolist(),
+                        age=g[p + "st_age"].tolist(), last_bbox=g[p + "st_last_bbox"],
+                        bank=[list(g[p + "st_bank"][r, :n[r]]) for r in range(len(n))])
+            _compare_state(trk, g[p + "st_ids"].tolist(), want, p)
+            assert trk.next_id == int(g[p + "st_next_id"])
+            s = trk.snapshot()
+            assert (s["stage"] == g[p + "st_x_is64"].astype(int) + g[p + "st_P_is64"].astype(int)).all()
+
+
+def _oracle_state(ref):
+    ids = sorted(ref.tracks)
+    T = [ref.tracks[i] for i in ids]
+    return ids, dict(x=np.array([t.kf.x.reshape(-1) for t in T], dtype=np.float64).reshape(-1, 8),
+                     P=np.array([t.kf.P for t in T], dtype=np.float64).reshape(-1, 8, 8),
+                     ema=np.array([t.ema for t in T], dtype=np.float32).reshape(-1, 128),
+                     miss=[t.miss_count for t in T], age=[t.age for t in T],
+                     last_bbox=np.array([t.last_bbox for t in T], dtype=np.float64).reshape(-1, 4),
+                     bank=[t.bank for t in T])
+
+
+@pytest.mark.parametrize("case", [
+    dict(n=64, H=1280, W=1280, frames=45, scene={}, conf={}),                                   # BASELINE config 2
+    dict(n=40, H=1280, W=1280, frames=70, scene=dict(drop=0.3, churn=0.15, churn_every=9),
+         conf=dict(lost_reid_after=4, max_age=12, hist_max=8), empty=(20, 21, 50)),
+    dict(n=128, H=1088, W=1920, frames=12, scene=dict(drop=0.1), conf={}),                      # config 5 stream
+    dict(n=24, H=640, W=640, frames=40, scene=dict(drop=0.5, churn=0.3, churn_every=5),
+         conf=dict(lost_reid_after=2, max_age=6, hist_max=3, emb_top_k=2, conf_update_min=0.7)),
+])
+def test_tracker_vs_oracle(case):
+    cfg = dict(SHIPPED_CONF, **case["conf"])
+    ref = tracker_ref.TrackerRef(cfg)
+    trk = Tracking(conf=cfg, max_tracks=768, max_dets=192)
+    scene = synth.Scene(7, case["n"], case["H"], case["W"], **case["scene"])
+    saw_reid = 0
+    for f in range(case["frames"]):
+        obj = scene.step()
+        if f in case.get("empty", ()):
+            obj["embs"], obj["bboxes"], obj["confs"] = [], [], []
+        trace = {}
+        want = ref.update(obj, trace=trace)
+        saw_reid += int("C_reid" in trace)
+        got = trk.update(obj)
+        assert got[0] == want[0] and got[1] == want[1] and got[2] == want[2], "frame %d" % f
+        if f % 6 == 5 or f == case["frames"] - 1:
+            ids, st = _oracle_state(ref)
+            _compare_state(trk, ids, st, "frame %d" % f)
+            assert trk.next_id == ref.next_id
+    if case["conf"].get("lost_reid_after", 50) < 10:
+        assert saw_reid > 0
+
+
+def test_tracker_queries_and_errors():
+    cfg = dict(SHIPPED_CONF)
+    ref = tracker_ref.TrackerRef(cfg)
+    trk = Tracking(conf=cfg, max_tracks=64, max_dets=32)
+    scene = synth.Scene(3, 12, 640, 640)
+    for _ in range(8):
+        obj = scene.step()
+        ref.update(obj)
+        trk.update(obj)
+    obj = scene.step()
+    ids = sorted(ref.tracks)
+    want = ref.stage1_cost(ids, obj["embs"], obj["bboxes"], obj["confs"], obj["input_hw"])
+    ref.predict_all()   # reference computes costs after predict; emulate on the oracle copy only for C_app
+    got = trk.cal_cost(row_to_tid=ids, det_embs=obj["embs"], det_boxes=obj["bboxes"], det_confs=obj["confs"],
+                       input_hw=obj["input_hw"])
+    for k in ("C_total", "C_app", "C_bbox", "C_conf"):
+        assert_close(got[k].cpu().numpy(), want[k], rtol=1e-5, atol=2e-6, what=k)
+    tv = trk.tracks[ids[0]]
+    assert tv.track_id == ids[0] and tv.encoder_feat.shape == (128,) and len(tv.feat_historical) == 8
+    C = np.zeros((len(ids), len(obj["bboxes"])), np.float32)
+    out = trk.apply_kalman_gating(C, ids, obj["bboxes"], maha_thr=9.49)
+    assert out is C and (C == 1e9).any() and (C == 0).any()
+    with pytest.raises(ValueError):
+        trk.update({"embs": [], "bboxes": [], "confs": [], "frame_id": 1})
+    with pytest.raises(ValueError):
+        trk.update({"embs": [], "bboxes": [], "confs": [], "input_hw": (1, 1)})
+    with pytest.raises(ValueError):
+        trk.update({"embs": [np.zeros(128)], "bboxes": [], "confs": [], "input_hw": (1, 1), "frame_id": 1})
+    with pytest.raises(ValueError):
+        trk.update({"embs": [np.zeros(64, np.float32)], "bboxes": [[0, 0, 1, 1]], "confs": [0.9], "input_hw": (1, 1),
+                    "frame_id": 1})
+    with pytest.raises(KeyError):
+        import os, tempfile, yaml
+        d = tempfile.mkdtemp()
+        with open(os.path.join(d, "c.yaml"), "w") as fh:
+            yaml.safe_dump({"model": {}}, fh)
+        Tracking(os.path.join(d, "c.yaml"))
+    small = Tracking(conf=cfg, max_tracks=16, max_dets=16)
+    sc = synth.Scene(0, 12, 640, 640)
+    small.update(sc.step())
+    with pytest.raises(_lib.B200Error):
+        small.update(synth.Scene(1, 12, 640, 640).step())     # 12 live + 12 new could exceed 16
+
+
+def test_multistream_equals_independent_trackers():
+    cfg = dict(SHIPPED_CONF, lost_reid_after=5, max_age=15)
+    S, MD = 5, 48
+    ms = MultiStreamTracker(S, cfg, max_tracks=128, max_dets=MD)
+    singles = [tracker_ref.TrackerRef(cfg) for _ in range(S)]
+    scenes = [synth.Scene(10 + s, 10 + 6 * s, 1088, 1920, drop=0.2, churn=0.2, churn_every=8) for s in range(S)]
+    for f in range(40):
+        n_det = np.zeros(S, np.int32)
+        boxes = np.zeros((S, MD, 4))
+        confs = np.zeros((S, MD))
+        embs = np.zeros((S, MD, 128), np.float32)
+        want = []
+        for s in range(S):
+            if (f + s) % 7 == 3:                     # this stream has no frame this step
+                n_det[s] = -1
+                want.append(None)
+                continue
+            obj = scenes[s].step()
+            if (f + s) % 11 == 5:
+                obj["embs"], obj["bboxes"], obj["confs"] = [], [], []
+            n = len(obj["bboxes"])
+            n_det[s] = n
+            if n:
+                boxes[s, :n] = obj["bboxes"]
+                confs[s, :n] = obj["confs"]
+                embs[s, :n] = np.stack(obj["embs"])
+            want.append(singles[s].update(obj))
+        res = ms.step(n_det, boxes, confs, embs, np.full(S, f))
+        for s in range(S):
+            got = ms.decode(res[s])
+            if want[s] is None:
+                assert got == ([], [], [])
+            else:
+                assert got[0] == want[s][0] and got[1] == want[s][1] and got[2] == want[s][2], (f, s)
+            assert int(res[s, 3]) == len(singles[s].tracks) and int(res[s, 4]) == singles[s].next_id
