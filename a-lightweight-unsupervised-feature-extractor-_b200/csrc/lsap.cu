@@ -33,17 +33,10 @@ __global__ void lsap_kernel(const float* __restrict__ C, const float* __restrict
     const int R = tall ? N : M, Cc = tall ? M : N;
     const float* orig = C + (size_t)b * batch_stride;
     const float* cost = tall ? Ct + (size_t)b * M * N : orig;
-    int ld = tall ? M : ldc;
+    const int ld = tall ? M : ldc;
     lsap::Work w = lsap::carve(smem_raw, R, Cc);
-    if (in_smem) {
-        float* sc = reinterpret_cast<float*>(smem_raw + lsap::work_bytes(R, Cc));
-        for (int i = 0; i < R; ++i)
-            for (int j = tid; j < Cc; j += nt) sc[(size_t)i * Cc + j] = cost[(size_t)i * ld + j];
-        cost = sc;
-        ld = Cc;
-        __syncthreads();
-    }
-    const int rc = lsap::solve(cost, R, Cc, ld, w, tid, nt);
+    float* stage = in_smem ? reinterpret_cast<float*>(smem_raw + lsap::work_bytes(R, Cc)) : nullptr;
+    const int rc = lsap::solve_block(cost, R, Cc, ld, w, stage);
     if (tid == 0) status[b] = rc;
     int32_t* out_c = col_of_row + (size_t)b * M;
     uint8_t* out_m = matched + (size_t)b * M;
@@ -93,7 +86,7 @@ extern "C" int b200_lsap_f32(const float* C, int batch, int64_t batch_stride, in
     const size_t mat = (size_t)R * Cc * sizeof(float);
     const int in_smem = (wb + mat <= kSmemMatrixBudget) ? 1 : 0;
     const size_t smem = wb + (in_smem ? mat : 0);
-    const int nt = Cc <= 128 ? 32 : (Cc <= 512 ? 128 : 256);
+    const int nt = 256;
     static bool configured = false;
     if (!configured) {
         B200_CUDA(cudaFuncSetAttribute(lsap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));

@@ -97,17 +97,19 @@ __device__ __forceinline__ Cand warp_best(Cand c) {
 // Solves the R x Cc problem (R <= Cc) whose row i is cost[i * ld + 0..Cc).  `tid` in [0, nt),
 // nt a multiple of 32 (<= kMaxThreads); all nt threads must call.  On return w.c4r / w.r4c hold
 // the assignment.  Returns B200_OK, B200_ENUMERIC or B200_EINFEASIBLE (same on every thread).
-__device__ inline int solve(const float* cost, int R, int Cc, int ld, const Work& w, int tid, int nt) {
+__device__ inline int solve(const float* cost, int R, int Cc, int ld, const Work& w, int tid, int nt,
+                         bool checked = false) {
     const double kInf = __longlong_as_double(0x7ff0000000000000LL);
     // NaN / -inf check (scipy: "matrix contains invalid numeric entries").
     if (tid == 0) *w.flag = 0;
     group_sync(nt);
     int bad = 0;
-    for (int i = 0; i < R; ++i)
-        for (int j = tid; j < Cc; j += nt) {
-            const float c = cost[(size_t)i * ld + j];
-            if (c != c || c == -__int_as_float(0x7f800000)) bad = 1;
-        }
+    if (!checked)
+        for (int i = 0; i < R; ++i)
+            for (int j = tid; j < Cc; j += nt) {
+                const float c = cost[(size_t)i * ld + j];
+                if (c != c || c == -__int_as_float(0x7f800000)) bad = 1;
+            }
     if (bad) *w.flag = 1;
     for (int i = tid; i < R; i += nt) { w.u[i] = 0.0; w.c4r[i] = -1; }
     for (int j = tid; j < Cc; j += nt) { w.v[j] = 0.0; w.r4c[j] = -1; w.pred[j] = -1; }
@@ -194,6 +196,168 @@ __device__ inline int solve(const float* cost, int R, int Cc, int ld, const Work
         group_sync(nt);
     }
     return B200_OK;
+}
+
+
+// ---- single-warp solver: all per-column state in registers -------------------------------------
+// Same algorithm and tie rule as solve(), for Cc <= 32 * CPL columns.  Lane l owns columns
+// l, l+32, ...; for each it keeps dist, v, pred, r4c and the column's POSITION in scipy's
+// "remaining" list (-1 once scanned), so the swap-removal of a scanned column is a register update
+// (the column sitting at the last position moves to the freed position) and no list lives in
+// memory.  The argmin of a Dijkstra step is three warp-wide integer min reductions (redux.sync):
+// the distance mapped to an order-preserving 64-bit key (high word, then low word), then -- only
+// when several lanes tie -- a key encoding scipy's tie rule.  u and col4row live in shared memory.
+// No block barriers: the calling warp runs alone.  The caller has rejected NaN / -inf entries.
+// On return c4r_s[R] / r4c_s[Cc] (shared memory) hold the assignment.
+__device__ __forceinline__ unsigned long long dist_key(double d) {
+    const long long b = __double_as_longlong(d + 0.0);          // +0.0 folds -0.0 into +0.0
+    return (unsigned long long)(b ^ ((b >> 63) | (long long)0x8000000000000000LL));
+}
+__device__ __forceinline__ double key_dist(unsigned long long k) {
+    const long long b = (k >> 63) ? (long long)(k ^ 0x8000000000000000ULL) : (long long)~k;
+    return __longlong_as_double(b);
+}
+// scipy's tie rule among equal distances as a min-key: an unassigned column beats an assigned one;
+// among unassigned the LAST list position wins, among assigned the FIRST.
+__device__ __forceinline__ unsigned tie_key(int it, bool un) { return un ? (0xFFFFu - (unsigned)it) : (0x10000u | (unsigned)it); }
+
+template <int CPL>
+__device__ inline int solve_warp(const float* cost, int R, int Cc, int ld, double* u_s, int* c4r_s, int* r4c_s) {
+    const unsigned kFull = 0xffffffffu;
+    const double kInf = __longlong_as_double(0x7ff0000000000000LL);
+    const int lane = threadIdx.x & 31;
+    double v[CPL], dist[CPL];
+    int pred[CPL], r4c[CPL], pos[CPL];
+#pragma unroll
+    for (int q = 0; q < CPL; ++q) { v[q] = 0.0; r4c[q] = -1; pred[q] = -1; }
+    for (int i = lane; i < R; i += 32) { u_s[i] = 0.0; c4r_s[i] = -1; }
+    __syncwarp();
+    for (int cur = 0; cur < R; ++cur) {
+#pragma unroll
+        for (int q = 0; q < CPL; ++q) {
+            const int j = lane + 32 * q;
+            pos[q] = j < Cc ? Cc - 1 - j : -1;          // remaining[it] = Cc - 1 - it
+            dist[q] = kInf;
+        }
+        unsigned scanned = 0;                            // bit q: own column q scanned in this search
+        int i = cur, n_todo = Cc, sink = -1;
+        double minv = 0.0;
+        while (sink < 0) {
+            const double ui = u_s[i];
+            const float* crow = cost + (size_t)i * ld;
+            unsigned long long bk = ~0ull;
+            unsigned bt = 0xffffffffu;
+            int bq = 0;
+#pragma unroll
+            for (int q = 0; q < CPL; ++q) {
+                if (pos[q] >= 0) {
+                    const double r = ((minv + (double)crow[lane + 32 * q]) - ui) - v[q];
+                    if (r < dist[q]) { dist[q] = r; pred[q] = i; }
+                    const unsigned long long k = dist_key(dist[q]);
+                    const unsigned t = tie_key(pos[q], r4c[q] < 0);
+                    if (k < bk || (k == bk && t < bt)) { bk = k; bt = t; bq = q; }
+                }
+            }
+            const unsigned hi = (unsigned)(bk >> 32), lo = (unsigned)bk;
+            const unsigned mh = __reduce_min_sync(kFull, hi);
+            const unsigned ml = __reduce_min_sync(kFull, hi == mh ? lo : 0xffffffffu);
+            bool cand = hi == mh && lo == ml && bt != 0xffffffffu;
+            unsigned who = __ballot_sync(kFull, cand);
+            if (__popc(who) > 1) {
+                const unsigned mt = __reduce_min_sync(kFull, cand ? bt : 0xffffffffu);
+                cand = cand && bt == mt;
+                who = __ballot_sync(kFull, cand);
+            }
+            minv = key_dist(((unsigned long long)mh << 32) | ml);
+            if (who == 0 || minv == kInf) return B200_EINFEASIBLE;
+            const int wl = __ffs(who) - 1;
+            int packed = 0, rj = 0;
+            if (lane == wl) {
+#pragma unroll
+                for (int q = 0; q < CPL; ++q)
+                    if (q == bq) { rj = r4c[q]; packed = (q << 16) | pos[q]; pos[q] = -1; scanned |= 1u << q; }
+            }
+            packed = __shfl_sync(kFull, packed, wl);
+            rj = __shfl_sync(kFull, rj, wl);
+            const int j = wl + 32 * (packed >> 16), freed = packed & 0xffff;
+            --n_todo;                                    // swap-removal: the last list entry fills the gap
+#pragma unroll
+            for (int q = 0; q < CPL; ++q)
+                if (pos[q] == n_todo) pos[q] = freed;
+            if (rj < 0) sink = j; else i = rj;
+        }
+        // dual update: u[cur] += minv; for every scanned column j with a row: u[r4c[j]] += minv - dist[j];
+        // v[j] -= minv - dist[j]  (the sink column has dist == minv, so it does not move)
+        if (lane == 0) u_s[cur] += minv;
+#pragma unroll
+        for (int q = 0; q < CPL; ++q)
+            if (scanned & (1u << q)) {
+                const double delta = minv - dist[q];
+                if (r4c[q] >= 0) u_s[r4c[q]] += delta;
+                v[q] -= delta;
+            }
+        // augment along the predecessor chain; only lane 0 touches col4row
+        int j = sink;
+        for (;;) {
+            int pi = 0;
+#pragma unroll
+            for (int q = 0; q < CPL; ++q)
+                if (q == (j >> 5)) pi = pred[q];
+            pi = __shfl_sync(kFull, pi, j & 31);
+            if (lane == (j & 31)) {
+#pragma unroll
+                for (int q = 0; q < CPL; ++q)
+                    if (q == (j >> 5)) r4c[q] = pi;
+            }
+            int prev = 0;
+            if (lane == 0) { prev = c4r_s[pi]; c4r_s[pi] = j; }
+            j = __shfl_sync(kFull, prev, 0);
+            if (pi == cur) break;
+        }
+        __syncwarp();                                    // u_s updates visible before the next search
+    }
+#pragma unroll
+    for (int q = 0; q < CPL; ++q)
+        if (lane + 32 * q < Cc) r4c_s[lane + 32 * q] = r4c[q];
+    __syncwarp();
+    return B200_OK;
+}
+
+// Block-level driver shared by the operator kernel and the tracker: validates the matrix (all
+// threads, flattened so loads overlap), optionally stages it in shared memory, then runs the
+// single-warp solver (Cc <= 256) or the multi-warp one.  Every thread of the CTA must call; the
+// status is returned on every thread and w.c4r / w.r4c hold the assignment.
+__device__ inline int solve_block(const float* cost, int R, int Cc, int ld, const Work& w, float* stage_or_null) {
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    int bad = 0;
+    const int total = R * Cc;
+#pragma unroll 4
+    for (int idx = tid; idx < total; idx += nthr) {
+        const int i = idx / Cc, j = idx - i * Cc;
+        const float c = cost[(size_t)i * ld + j];
+        if (c != c || c == -__int_as_float(0x7f800000)) bad = 1;
+        if (stage_or_null) stage_or_null[idx] = c;
+    }
+    bad = __syncthreads_or(bad);
+    if (bad) return B200_ENUMERIC;
+    if (stage_or_null) { cost = stage_or_null; ld = Cc; }
+    __shared__ int s_status;
+    if (Cc <= 256) {
+        if (tid < 32) {
+            const int rc = Cc <= 64    ? solve_warp<2>(cost, R, Cc, ld, w.u, w.c4r, w.r4c)
+                           : Cc <= 128 ? solve_warp<4>(cost, R, Cc, ld, w.u, w.c4r, w.r4c)
+                                       : solve_warp<8>(cost, R, Cc, ld, w.u, w.c4r, w.r4c);
+            if (tid == 0) s_status = rc;
+        }
+    } else {
+        const int nt = nthr < kMaxThreads ? (nthr & ~31) : kMaxThreads;
+        if (tid < nt) {
+            const int rc = solve(cost, R, Cc, ld, w, tid, nt, true);
+            if (tid == 0) s_status = rc;
+        }
+    }
+    __syncthreads();
+    return s_status;
 }
 
 }  // namespace lsap

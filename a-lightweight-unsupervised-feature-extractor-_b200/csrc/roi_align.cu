@@ -172,7 +172,7 @@ __device__ __forceinline__ void separable_accumulate(float (&acc)[PH][PW], const
 }
 
 #ifndef B200_ROI_MIN_CTAS
-#define B200_ROI_MIN_CTAS 1
+#define B200_ROI_MIN_CTAS 6
 #endif
 
 template <int PH, int PW, bool NHWC>
@@ -241,11 +241,13 @@ roi_align_tile_kernel(const float* __restrict__ feat, int B, int C, int H, int W
             float* sV = sMain;
             if (NHWC) {
                 const float* base = feat + (((size_t)g.b * H + ymin) * W + xmin) * C + c0 + lane;
-                if (lane < cn)
-                    for (int cell = 0; cell < ncell; ++cell) {
-                        const int r = cell / FX, x = cell - r * FX;
-                        cp_async4(sV + cell * 32 + lane, base + ((size_t)r * W + x) * C);
+                if (lane < cn) {
+                    float* dst = sV + lane;
+                    for (int r = 0; r < FY; ++r) {
+                        const float* src = base + (size_t)r * W * C;
+                        for (int x = 0; x < FX; ++x, dst += 32, src += C) cp_async4(dst, src);
                     }
+                }
                 cp_async_wait_all();
             } else if (ncell) {
                 const float* plane0 = feat + ((size_t)g.b * C + c0) * H * W;
@@ -257,6 +259,8 @@ roi_align_tile_kernel(const float* __restrict__ feat, int B, int C, int H, int W
                 const int per_it = 32 / nqp, sub = lane & (nqp - 1), slot = lane / nqp;
                 const int items = cn * FY;                           // item = r * cn + c (channel fastest)
                 const int xq = (q0 + sub) * G;
+                int rn = 0, cnx = slot;                              // (row, channel) of this lane's next item
+                while (cnx >= cn) { cnx -= cn; ++rn; }
                 for (int base = 0; base < items; base += 4 * per_it) {
                     float4 v[4];
                     int rr[4], cc[4];
@@ -265,12 +269,14 @@ roi_align_tile_kernel(const float* __restrict__ feat, int B, int C, int H, int W
                         const int item = base + u * per_it + slot;
                         rr[u] = -1;
                         if (item < items && sub < nq) {
-                            rr[u] = item / cn;
-                            cc[u] = item - rr[u] * cn;
+                            rr[u] = rn;
+                            cc[u] = cnx;
                             const float* p = plane0 + ((size_t)cc[u] * H + ymin + rr[u]) * W + xq;
                             if (vec) v[u] = __ldg(reinterpret_cast<const float4*>(p));
                             else v[u].x = __ldg(p);
                         }
+                        cnx += per_it;                               // advance without integer division
+                        while (cnx >= cn) { cnx -= cn; ++rn; }
                     }
 #pragma unroll
                     for (int u = 0; u < 4; ++u)

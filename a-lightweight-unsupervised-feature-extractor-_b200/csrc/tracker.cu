@@ -23,6 +23,13 @@
 namespace b200 {
 namespace trk {
 
+#ifdef B200_TRK_TIMING          // debug builds only: SM-clock stamps at phase boundaries of stream 0
+__device__ long long g_timing[32];
+#define TRK_STAMP(k) do { __syncthreads(); if (threadIdx.x == 0 && blockIdx.x == 0) g_timing[k] = clock64(); } while (0)
+#else
+#define TRK_STAMP(k) do { } while (0)
+#endif
+
 constexpr int kThreads = 256;
 constexpr int kHdr = 8;                 // ints per stream in hdr / cnt
 enum { H_NLIVE = 0, H_NEXT = 1, H_NFREE = 2 };
@@ -41,6 +48,8 @@ struct Dev {
     float *det_unit, *det_z, *det_boxf, *det_conff, *prev_boxf, *prev_conff, *C1, *C1T, *C2, *C2T;
     double* gate_SI;
     int *rows_main, *rows_reid, *cnt, *ud1, *det_used, *m_row, *m_det, *m_app, *tmp;
+    int2 *work1, *work2;             // (stream, row * 64 + detection tile) items of the two cost launches
+    int* wcount;                     // [2] number of items queued for this step
     // configuration
     cost::PairWeights pw;
     double maha_thr, cost_max, conf_update_min, cost_update_max, reid_only_cost_max, init_conf_min;
@@ -118,6 +127,17 @@ __device__ inline void purge(const Dev& d, int s, int nl, int* scratch) {
     __syncthreads();
 }
 
+// Queues one work item per (row, 64-detection tile) of this stream for the persistent cost kernel.
+__device__ inline void enqueue_cost_work(int2* work, int* counter, int s, int M, int N, int* scratch) {
+    const int tiles = (N + cost::kTileN - 1) / cost::kTileN, total = M * tiles;
+    if (total <= 0) return;                       // uniform across the CTA
+    __syncthreads();
+    if (threadIdx.x == 0) scratch[0] = atomicAdd(counter, total);
+    __syncthreads();
+    const int base = scratch[0];
+    for (int i = threadIdx.x; i < total; i += blockDim.x) work[base + i] = make_int2(s, (i / tiles) * 64 + i % tiles);
+}
+
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) begin_kernel(Dev d) {
     __shared__ int scratch[kThreads / 32];
@@ -128,6 +148,26 @@ __global__ void __launch_bounds__(kThreads) begin_kernel(Dev d) {
     const size_t sb = (size_t)s * d.MT, db = (size_t)s * d.MD;
     const int n = d.n_det[s], nl = hdr[H_NLIVE];
     int* order = d.order + sb;
+    if (blockIdx.y == 1) {                         // second CTA of the stream: detection prep only
+        if (n <= 0) return;
+    // ---- detections: unit embeddings (:167-168), z (KalmanFilter.py:5-16), float32 boxes/confs ----
+        for (int j = tid >> 5; j < n; j += blockDim.x >> 5) {
+            const float4 v = reinterpret_cast<const float4*>(d.embs + (db + j) * cost::kD)[tid & 31];
+            reinterpret_cast<float4*>(d.det_unit + (db + j) * cost::kD)[tid & 31] = cost::unit_row(v);
+        }
+        for (int j = tid; j < n; j += blockDim.x) {
+            double b[4];
+            float z[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { b[k] = d.boxes[(db + j) * 4 + k]; d.det_boxf[(db + j) * 4 + k] = (float)b[k]; }
+            kf::box_to_z(b, z);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) d.det_z[(db + j) * 4 + k] = z[k];
+            d.det_conff[db + j] = (float)d.confs[db + j];
+            d.det_used[db + j] = 0;
+        }
+        return;
+    }
     if (n < 0) {                                   // stream idle this step
         if (tid == 0) {
             cnt[C_MODE] = MODE_SKIP;
@@ -154,35 +194,26 @@ __global__ void __launch_bounds__(kThreads) begin_kernel(Dev d) {
         }
         return;
     }
-    // ---- detections: unit embeddings (:167-168), z (KalmanFilter.py:5-16), float32 boxes/confs ----
-    for (int j = tid >> 5; j < n; j += blockDim.x >> 5) {
-        const float4 v = reinterpret_cast<const float4*>(d.embs + (db + j) * cost::kD)[tid & 31];
-        reinterpret_cast<float4*>(d.det_unit + (db + j) * cost::kD)[tid & 31] = cost::unit_row(v);
-    }
-    for (int j = tid; j < n; j += blockDim.x) {
-        double b[4];
-        float z[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { b[k] = d.boxes[(db + j) * 4 + k]; d.det_boxf[(db + j) * 4 + k] = (float)b[k]; }
-        kf::box_to_z(b, z);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) d.det_z[(db + j) * 4 + k] = z[k];
-        d.det_conff[db + j] = (float)d.confs[db + j];
-        d.det_used[db + j] = 0;
-    }
-    // ---- predict_all (:340-345) ----------------------------------------------------------------
+    // ---- predict_all (:340-345) + per-track inputs of the stage-1 cost (by slot): predicted box and
+    // confidence as float32, inverse innovation covariance for the gate -------------------------------
     const float q[8] = {1.f, 1.f, 1.f, 1.f, 100.f, 100.f, 100.f, 100.f};    // KalmanFilter.py:91-95
+    const float rdiag[4] = {1.f, 1.f, 1.f, 1.f};                           // KalmanFilter.py:98-99
     for (int p = tid; p < nl; p += blockDim.x) {
         const size_t slot = sb + order[p];
         double x[8], P[64], b[4];
         load_kf(d, slot, x, P);
-        kf::predict(x, P, d.kf_stage[slot], q);
+        const int st = d.kf_stage[slot];
+        kf::predict(x, P, st, q);
         store_kf(d, slot, x, P);
         kf::x_to_box(x, b);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) d.last_bbox[slot * 4 + k] = b[k];
+        for (int k = 0; k < 4; ++k) { d.last_bbox[slot * 4 + k] = b[k]; d.prev_boxf[slot * 4 + k] = (float)b[k]; }
+        d.prev_conff[slot] = (float)d.last_conf[slot];
+        kf::Gate g;
+        kf::gate_prepare(x, P, st, rdiag, &g);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) d.gate_SI[slot * 16 + k] = g.SI[k];
     }
-    __syncthreads();
     // ---- rows_main / rows_reid in ascending track-id order (:478-487) -----------------------------
     int* rm = d.rows_main + sb;
     int* rr = d.rows_reid + sb;
@@ -190,27 +221,11 @@ __global__ void __launch_bounds__(kThreads) begin_kernel(Dev d) {
                                  [&](int pos, int i) { rm[pos] = order[i]; }, scratch);
     const int M2 = block_compact(nl, [&](int i) { return d.miss[sb + order[i]] > d.lost_reid_after; },
                                  [&](int pos, int i) { rr[pos] = order[i]; }, scratch);
-    // ---- per-row inputs of the stage-1 cost: predicted boxes as float32, gate inverse --------------
-    const float rdiag[4] = {1.f, 1.f, 1.f, 1.f};                           // KalmanFilter.py:98-99
-    for (int r = tid; r < M1; r += blockDim.x) {
-        const size_t slot = sb + rm[r];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) d.prev_boxf[(sb + r) * 4 + k] = (float)d.last_bbox[slot * 4 + k];
-        d.prev_conff[sb + r] = (float)d.last_conf[slot];
-        double P4[64];
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int b = 0; b < 4; ++b) P4[a * 8 + b] = d.kf_P[slot * 64 + a * 8 + b];
-        kf::Gate g;
-        kf::gate_prepare(d.kf_x + slot * 8, P4, d.kf_stage[slot], rdiag, &g);
-#pragma unroll
-        for (int k = 0; k < 16; ++k) d.gate_SI[(sb + r) * 16 + k] = g.SI[k];
-    }
     if (tid == 0) {
         cnt[C_M1] = M1; cnt[C_M2] = M2; cnt[C_NU] = 0; cnt[C_MODE] = MODE_NORMAL;
         cnt[C_NMATCH] = 0; cnt[C_NUT] = 0; cnt[C_STATUS] = 0;
     }
+    enqueue_cost_work(d.work1, d.wcount + 0, s, M1, 1, scratch);      // one item per row (all detections)
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -218,57 +233,171 @@ __global__ void __launch_bounds__(kThreads) begin_kernel(Dev d) {
 template <int STAGE>
 __global__ void __launch_bounds__(cost::kThreads) cost_kernel(Dev d) {
     extern __shared__ __align__(16) float smem[];
-    const int s = blockIdx.z, r = blockIdx.y, j0 = blockIdx.x * cost::kTileN;
-    const int* cnt = d.cnt + s * kHdr;
-    if (cnt[C_MODE] != MODE_NORMAL) return;
-    const int M = STAGE == 1 ? cnt[C_M1] : cnt[C_M2];
-    const int N = STAGE == 1 ? d.n_det[s] : cnt[C_NU];
-    if (r >= M || j0 >= N) return;
-    const size_t sb = (size_t)s * d.MT, db = (size_t)s * d.MD;
-    const size_t slot = sb + (STAGE == 1 ? d.rows_main : d.rows_reid)[sb + r];
-    int T = d.bank_len[slot];
-    const float* rows = d.bank + slot * d.HIST * cost::kD;
-    if (T <= 0) { rows = d.ema + slot * cost::kD; T = 1; }        // :180-182 fallback to the EMA
-    // stage 2 gathers the leftover detections through ud1
     __shared__ int s_idx[cost::kTileN];
-    if (threadIdx.x < cost::kTileN) {
-        const int j = j0 + threadIdx.x;
-        s_idx[threadIdx.x] = j < N ? (STAGE == 1 ? j : d.ud1[db + j]) : 0;
-    }
-    __syncthreads();
-    // app_cost_tile reads det rows [j0, j0+kTileN) of a [N][128] matrix; give it a gathered view.
-    const int tc = cost::bank_cap(T);
-    float* sBank = smem;
-    float* sDet = sBank + tc * cost::kD;
-    float* sSim = sDet + cost::kTileN * cost::kDetStride;
+    const int total = d.wcount[STAGE - 1];
+    const int2* work = STAGE == 1 ? d.work1 : d.work2;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    for (int t = warp; t < tc; t += cost::kThreads / 32) {
-        float4 v = make_float4(0, 0, 0, 0);
-        if (t < T) v = cost::unit_row(reinterpret_cast<const float4*>(rows + (size_t)t * cost::kD)[lane]);
-        reinterpret_cast<float4*>(sBank + t * cost::kD)[lane] = v;
+    for (int wi = blockIdx.x; wi < total; wi += gridDim.x) {        // persistent CTAs, uniform trip count
+        const int2 item = work[wi];
+        const int s = item.x, r = item.y >> 6, j0 = (item.y & 63) * cost::kTileN;
+        const int* cnt = d.cnt + s * kHdr;
+        const int N = STAGE == 1 ? d.n_det[s] : cnt[C_NU];
+        const size_t sb = (size_t)s * d.MT, db = (size_t)s * d.MD;
+        const size_t slot = sb + (STAGE == 1 ? d.rows_main : d.rows_reid)[sb + r];
+        int T = d.bank_len[slot];
+        const float* rows = d.bank + slot * d.HIST * cost::kD;
+        if (T <= 0) { rows = d.ema + slot * cost::kD; T = 1; }        // :180-182 fallback to the EMA
+        if (tid < cost::kTileN) {                                      // stage 2 gathers leftover detections
+            const int j = j0 + tid;
+            s_idx[tid] = j < N ? (STAGE == 1 ? j : d.ud1[db + j]) : 0;
+        }
+        __syncthreads();
+        const int tc = cost::bank_cap(T);
+        float* sBank = smem;
+        float* sDet = sBank + tc * cost::kD;
+        float* sSim = sDet + cost::kTileN * cost::kDetStride;
+        for (int t = warp; t < tc; t += cost::kThreads / 32) {
+            float4 v = make_float4(0, 0, 0, 0);
+            if (t < T) v = cost::unit_row(reinterpret_cast<const float4*>(rows + (size_t)t * cost::kD)[lane]);
+            reinterpret_cast<float4*>(sBank + t * cost::kD)[lane] = v;
+        }
+        for (int j = warp; j < cost::kTileN; j += cost::kThreads / 32) {
+            float4 v = make_float4(0, 0, 0, 0);
+            if (j0 + j < N) v = reinterpret_cast<const float4*>(d.det_unit + (db + s_idx[j]) * cost::kD)[lane];
+            reinterpret_cast<float4*>(sDet + j * cost::kDetStride)[lane] = v;
+        }
+        __syncthreads();
+        const float c_app = cost::sims_and_topk(sBank, sDet, sSim, tc, T, d.topk, true);   // ends with a barrier
+        const int j = j0 + tid;
+        if (tid >= cost::kTileN || j >= N) continue;
+        if (STAGE == 2) {
+            d.C2[(sb + r) * d.MD + j] = c_app;
+            d.C2T[(db + j) * d.MT + r] = c_app;
+            continue;
+        }
+        const cost::PairCost pc = cost::pair_cost(d.prev_boxf + slot * 4, d.det_boxf + (db + j) * 4,
+                                                  d.prev_conff[slot], d.det_conff[db + j], d.pw, c_app);
+        float total_c = pc.total;
+        const double d2 = kf::gate_d2(d.gate_SI + slot * 16, d.kf_x + slot * 8, d.kf_stage[slot],
+                                      d.det_z + (db + j) * 4);
+        if (d2 > d.maha_thr) total_c = 1e9f;                                // :335-336
+        d.C1[(sb + r) * d.MD + j] = total_c;
+        d.C1T[(db + j) * d.MT + r] = total_c;
     }
-    for (int j = warp; j < cost::kTileN; j += cost::kThreads / 32) {
-        float4 v = make_float4(0, 0, 0, 0);
-        if (j0 + j < N) v = reinterpret_cast<const float4*>(d.det_unit + (db + s_idx[j]) * cost::kD)[lane];
-        reinterpret_cast<float4*>(sDet + j * cost::kDetStride)[lane] = v;
+}
+
+// ---- stage-1 cost, gate first -----------------------------------------------------------------------
+// apply_kalman_gating (:306-338) overwrites every pair with d2 > maha_thr by 1e9 AFTER the reference has
+// computed its full cost (:496-511).  The result does not depend on the order, and in steady state ~98 %
+// of the pairs are gated, so this kernel evaluates the gate for all pairs first and
+// runs the bank contraction + top-k only for the pairs that survive.  One warp owns one track row:
+//   lane = detection (chunks of 32): box/conf terms and d2; ballot -> surviving detections;
+//   per survivor: lane = bank row t, a 128-long fp32 dot product against the detection (bank rows staged
+//   re-normalised in shared memory with a padded stride, so the 16 B loads of 32 rows are conflict free),
+//   then k rounds of warp-max for the top-k mean.
+constexpr int kCost1Warps = 4;
+constexpr int kBankStride = cost::kD + 4;
+
+__host__ __device__ inline size_t cost1_smem_bytes(int T) {
+    return sizeof(float) * (size_t)kCost1Warps * cost::bank_cap(T) * kBankStride;
+}
+
+__device__ __forceinline__ unsigned fkey(float f) {                 // order-preserving float -> uint
+    const unsigned b = __float_as_uint(f);
+    return b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u);
+}
+
+__global__ void __launch_bounds__(kCost1Warps * 32) cost1_sparse_kernel(Dev d) {
+    extern __shared__ __align__(16) float smem[];
+    const int total = d.wcount[0];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tcap = cost::bank_cap(d.HIST);
+    float* sBank = smem + (size_t)warp * tcap * kBankStride;
+    for (int wi = blockIdx.x * kCost1Warps + warp; wi < total; wi += gridDim.x * kCost1Warps) {
+        const int2 item = d.work1[wi];
+        const int s = item.x, r = item.y >> 6;
+        const int N = d.n_det[s];
+        const size_t sb = (size_t)s * d.MT, db = (size_t)s * d.MD;
+        const size_t slot = sb + d.rows_main[sb + r];
+        int T = d.bank_len[slot];
+        const float* rows = d.bank + slot * d.HIST * cost::kD;
+        if (T <= 0) { rows = d.ema + slot * cost::kD; T = 1; }        // :180-182 fallback to the EMA
+        const int kk = min(d.topk, T);
+        // per-row gate inputs
+        double SI[16], xs[4];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) SI[k] = d.gate_SI[slot * 16 + k];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) xs[k] = d.kf_x[slot * 8 + k];
+        const int stage = d.kf_stage[slot];
+        float pb[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) pb[k] = d.prev_boxf[slot * 4 + k];
+        const float pconf = d.prev_conff[slot];
+        bool staged = false;
+        for (int j0 = 0; j0 < N; j0 += 32) {
+            const int j = j0 + lane;
+            bool alive = false;
+            if (j < N) alive = !(kf::gate_d2(SI, xs, stage, d.det_z + (db + j) * 4) > d.maha_thr);   // :335
+            unsigned todo = __ballot_sync(0xffffffffu, alive);
+            float c_app = 0.0f;
+            if (todo && !staged) {                                 // stage the re-normalised bank once per row
+                for (int t = 0; t < T; ++t) {
+                    const float4 v = cost::unit_row(reinterpret_cast<const float4*>(rows + (size_t)t * cost::kD)[lane]);
+                    reinterpret_cast<float4*>(sBank + t * kBankStride)[lane] = v;
+                }
+                __syncwarp();
+                staged = true;
+            }
+            while (todo) {
+                const int jl = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const float4* det = reinterpret_cast<const float4*>(d.det_unit + (db + j0 + jl) * cost::kD);
+                float s0 = -__int_as_float(0x7f800000), s1 = s0;   // sims of bank rows lane and lane + 32
+                if (lane < T) {
+                    const float4* b = reinterpret_cast<const float4*>(sBank + lane * kBankStride);
+                    float a = 0.0f;
+#pragma unroll 8
+                    for (int k = 0; k < cost::kD / 4; ++k) {
+                        const float4 x = b[k], y = __ldg(det + k);
+                        a = fmaf(x.x, y.x, a); a = fmaf(x.y, y.y, a); a = fmaf(x.z, y.z, a); a = fmaf(x.w, y.w, a);
+                    }
+                    s0 = a;
+                }
+                if (lane + 32 < T) {
+                    const float4* b = reinterpret_cast<const float4*>(sBank + (lane + 32) * kBankStride);
+                    float a = 0.0f;
+#pragma unroll 8
+                    for (int k = 0; k < cost::kD / 4; ++k) {
+                        const float4 x = b[k], y = __ldg(det + k);
+                        a = fmaf(x.x, y.x, a); a = fmaf(x.y, y.y, a); a = fmaf(x.z, y.z, a); a = fmaf(x.w, y.w, a);
+                    }
+                    s1 = a;
+                }
+                float sum = 0.0f;                                   // top-k mean, largest first (:196-202)
+                for (int q = 0; q < kk; ++q) {
+                    const float mine = fmaxf(s0, s1);
+                    const unsigned m = __reduce_max_sync(0xffffffffu, fkey(mine));
+                    const unsigned who = __ballot_sync(0xffffffffu, fkey(mine) == m);
+                    if (lane == __ffs(who) - 1) {
+                        if (s0 >= s1) s0 = -__int_as_float(0x7f800000); else s1 = -__int_as_float(0x7f800000);
+                    }
+                    const unsigned bits = m ^ ((m >> 31) ? 0x80000000u : 0xffffffffu);
+                    sum = __fadd_rn(sum, __uint_as_float(bits));
+                }
+                const float ca = __fsub_rn(1.0f, __fdiv_rn(sum, (float)kk));
+                if (lane == jl) c_app = ca;
+            }
+            if (j < N) {
+                float total_c = 1e9f;
+                if (alive)
+                    total_c = cost::pair_cost(pb, d.det_boxf + (db + j) * 4, pconf, d.det_conff[db + j], d.pw, c_app).total;
+                d.C1[(sb + r) * d.MD + j] = total_c;
+                d.C1T[(db + j) * d.MT + r] = total_c;
+            }
+        }
+        __syncwarp();
     }
-    __syncthreads();
-    const float c_app = cost::sims_and_topk(sBank, sDet, sSim, tc, T, d.topk, true);
-    const int j = j0 + tid;
-    if (tid >= cost::kTileN || j >= N) return;
-    if (STAGE == 2) {
-        d.C2[(sb + r) * d.MD + j] = c_app;
-        d.C2T[(db + j) * d.MT + r] = c_app;
-        return;
-    }
-    const cost::PairCost pc = cost::pair_cost(d.prev_boxf + (sb + r) * 4, d.det_boxf + (db + j) * 4,
-                                              d.prev_conff[sb + r], d.det_conff[db + j], d.pw, c_app);
-    float total = pc.total;
-    const double d2 = kf::gate_d2(d.gate_SI + (sb + r) * 16, d.kf_x + slot * 8, d.kf_stage[slot],
-                                  d.det_z + (db + j) * 4);
-    if (d2 > d.maha_thr) total = 1e9f;                                  // :335-336
-    d.C1[(sb + r) * d.MD + j] = total;
-    d.C1T[(db + j) * d.MT + r] = total;
 }
 
 // update_matched (:375-448) for `nm` (row, det) pairs listed in m_row / m_det (det = global index).
@@ -303,28 +432,44 @@ __device__ inline void update_matched(const Dev& d, int s, int nm, const int* ro
         d.m_app[sb + qd] = app;
     }
     __syncthreads();
-    // EMA + bank push (:429-448), one warp per match
-    const int lane = threadIdx.x & 31;
-    for (int qd = threadIdx.x >> 5; qd < nm; qd += blockDim.x >> 5) {
-        if (!d.m_app[sb + qd]) continue;
-        const size_t slot = sb + rows[d.m_row[sb + qd]];
-        const float4 e = reinterpret_cast<const float4*>(d.det_unit + (db + d.m_det[sb + qd]) * cost::kD)[lane];
-        float4* pe = reinterpret_cast<float4*>(d.ema + slot * cost::kD) + lane;
-        const float4 o = *pe;
-        float4 f;
-        f.x = __fadd_rn(__fmul_rn(d.ema_a, o.x), __fmul_rn(d.ema_b, e.x));
-        f.y = __fadd_rn(__fmul_rn(d.ema_a, o.y), __fmul_rn(d.ema_b, e.y));
-        f.z = __fadd_rn(__fmul_rn(d.ema_a, o.z), __fmul_rn(d.ema_b, e.z));
-        f.w = __fadd_rn(__fmul_rn(d.ema_a, o.w), __fmul_rn(d.ema_b, e.w));
-        *pe = cost::unit_row(f);
-        int len = d.bank_len[slot], head = d.bank_head[slot], pos;
-        if (len < d.HIST) { pos = (head + len) % d.HIST; ++len; }
-        else { pos = head; head = (head + 1) % d.HIST; }
-        reinterpret_cast<float4*>(d.bank + (slot * d.HIST + pos) * cost::kD)[lane] = e;
-        __syncwarp();
-        if (lane == 0) { d.bank_len[slot] = len; d.bank_head[slot] = head; }
+    TRK_STAMP(3);
+    // EMA + bank push (:429-448): a warp takes four matches at a time and issues all their loads first
+    const int lane = threadIdx.x & 31, nwarp = blockDim.x >> 5, warp = threadIdx.x >> 5;
+    for (int q0 = warp * 4; q0 < nm; q0 += nwarp * 4) {
+        float4 e[4], o[4];
+        size_t slots[4];
+        int len[4], head[4];
+        bool on[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int qd = q0 + u;
+            on[u] = qd < nm && d.m_app[sb + (qd < nm ? qd : 0)];
+            if (on[u]) {
+                slots[u] = sb + rows[d.m_row[sb + qd]];
+                e[u] = reinterpret_cast<const float4*>(d.det_unit + (db + d.m_det[sb + qd]) * cost::kD)[lane];
+                o[u] = reinterpret_cast<const float4*>(d.ema + slots[u] * cost::kD)[lane];
+                len[u] = d.bank_len[slots[u]];
+                head[u] = d.bank_head[slots[u]];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (!on[u]) continue;
+            float4 f;
+            f.x = __fadd_rn(__fmul_rn(d.ema_a, o[u].x), __fmul_rn(d.ema_b, e[u].x));
+            f.y = __fadd_rn(__fmul_rn(d.ema_a, o[u].y), __fmul_rn(d.ema_b, e[u].y));
+            f.z = __fadd_rn(__fmul_rn(d.ema_a, o[u].z), __fmul_rn(d.ema_b, e[u].z));
+            f.w = __fadd_rn(__fmul_rn(d.ema_a, o[u].w), __fmul_rn(d.ema_b, e[u].w));
+            reinterpret_cast<float4*>(d.ema + slots[u] * cost::kD)[lane] = cost::unit_row(f);
+            int pos;
+            if (len[u] < d.HIST) { pos = head[u] + len[u]; if (pos >= d.HIST) pos -= d.HIST; ++len[u]; }
+            else { pos = head[u]; head[u] = head[u] + 1 == d.HIST ? 0 : head[u] + 1; }
+            reinterpret_cast<float4*>(d.bank + (slots[u] * d.HIST + pos) * cost::kD)[lane] = e[u];
+            if (lane == 0) { d.bank_len[slots[u]] = len[u]; d.bank_head[slots[u]] = head[u]; }
+        }
     }
     __syncthreads();
+    TRK_STAMP(4);
 }
 
 // hungarian_assign (hung.py:5-45) for this stream's matrix; fills m_row/m_det, marks misses.
@@ -336,6 +481,8 @@ __global__ void __launch_bounds__(kThreads) assign_kernel(Dev d, int smem_matrix
     __shared__ int s_rc;
     const int s = blockIdx.x, tid = threadIdx.x;
     int* cnt = d.cnt + s * kHdr;
+    // both cost launches of this step are done: clear their queues for the next step
+    if (STAGE == 2 && s == 0 && tid == 0) { d.wcount[0] = 0; d.wcount[1] = 0; }
     if (cnt[C_MODE] != MODE_NORMAL) return;
     int* hdr = d.hdr + s * kHdr;
     int* res = d.result + (size_t)s * d.res_stride;
@@ -351,27 +498,20 @@ __global__ void __launch_bounds__(kThreads) assign_kernel(Dev d, int smem_matrix
     int* out_ut = res_ut(d, res);
     int* m_col = d.tmp + sb;                        // column (local det index) of each match
     int n_match = 0, n_ut = 0, n_left = N;
+    if (STAGE == 1) TRK_STAMP(0);
 
     if (M > 0 && N > 0) {
         const bool tall = M > N;
         const int R = tall ? N : M, Cc = tall ? M : N;
         const float* costp = tall ? CT : C;
-        int ld = tall ? d.MT : d.MD;
+        const int ld = tall ? d.MT : d.MD;
         const lsap::Work w = lsap::carve(smem_raw, R, Cc);
-        if ((size_t)R * Cc <= (size_t)smem_matrix_floats) {
-            float* sc = reinterpret_cast<float*>(smem_raw + lsap::work_bytes(R, Cc));
-            for (int i = 0; i < R; ++i)
-                for (int j = tid; j < Cc; j += blockDim.x) sc[(size_t)i * Cc + j] = costp[(size_t)i * ld + j];
-            costp = sc;
-            ld = Cc;
-        }
+        float* stage = (size_t)R * Cc <= (size_t)smem_matrix_floats
+                           ? reinterpret_cast<float*>(smem_raw + lsap::work_bytes(R, Cc)) : nullptr;
+        const int rc = lsap::solve_block(costp, R, Cc, ld, w, stage);
+        if (tid == 0) s_rc = rc;
         __syncthreads();
-        const int nt = Cc <= 128 ? 32 : (Cc <= 512 ? 128 : kThreads);
-        if (tid < nt) {
-            const int rc = lsap::solve(costp, R, Cc, ld, w, tid, nt);
-            if (tid == 0) s_rc = rc;
-        }
-        __syncthreads();
+        if (STAGE == 1) TRK_STAMP(1);
         if (s_rc != B200_OK) {                      // NaN / infeasible: scipy would raise
             if (tid == 0) cnt[C_STATUS] = s_rc;
         } else {
@@ -395,6 +535,7 @@ __global__ void __launch_bounds__(kThreads) assign_kernel(Dev d, int smem_matrix
                 out_ut[ut0 + pos] = d.tid[slot];
             }, scratch);
             __syncthreads();
+            if (STAGE == 1) TRK_STAMP(2);
             update_matched(d, s, n_match, rows, C, d.MD, m_col,
                            STAGE == 1 ? d.cost_update_max : d.reid_only_cost_max, STAGE == 1 ? d.maha_thr : 1e18);
         }
@@ -413,6 +554,8 @@ __global__ void __launch_bounds__(kThreads) assign_kernel(Dev d, int smem_matrix
         n_left = block_compact(N, [&](int j) { return d.det_used[db + j] == 0; },
                                [&](int pos, int j) { d.ud1[db + pos] = j; }, scratch);
         if (tid == 0) { cnt[C_NU] = n_left; cnt[C_NMATCH] = n_match; cnt[C_NUT] = n_ut; }
+        enqueue_cost_work(d.work2, d.wcount + 1, s, n_left > 0 ? cnt[C_M2] : 0, n_left, scratch);
+        TRK_STAMP(5);
         return;
     }
 
@@ -509,6 +652,7 @@ __global__ void reset_kernel(Dev d) {
         d.hdr[s * kHdr + H_NLIVE] = 0;
         d.hdr[s * kHdr + H_NEXT] = 0;
         d.hdr[s * kHdr + H_NFREE] = d.MT;
+        if (s == 0) { d.wcount[0] = 0; d.wcount[1] = 0; }
     }
 }
 
@@ -524,7 +668,7 @@ struct b200_tracker {
     size_t in_bytes = 0, res_bytes = 0;
     int* in_ndet = nullptr; int* in_frame = nullptr; double* in_boxes = nullptr; double* in_confs = nullptr;
     float* in_embs = nullptr; int* dev_result = nullptr;
-    int rows_ub = 0;                // upper bound on live tracks of any stream (sizes the cost grids)
+    int cost_grid = 0, cost1_grid = 0;   // persistent CTAs of the cost kernels (resident CTAs per SM x SMs)
     size_t assign_smem = 0;
     int smem_matrix_floats = 0;
 };
@@ -547,7 +691,7 @@ extern "C" int b200_tracker_create(b200_tracker** out, int n_streams, int max_tr
                                    const b200_tracker_conf* conf) {
     B200_REQUIRE(out && conf, "tracker_create: null pointer");
     B200_REQUIRE(n_streams >= 1 && n_streams <= 65535, "tracker_create: n_streams %d out of range", n_streams);
-    B200_REQUIRE(max_tracks >= 1 && max_tracks <= 4096 && max_dets >= 1 && max_dets <= 4096,
+    B200_REQUIRE(max_tracks >= 1 && max_tracks <= 4096 && max_dets >= 1 && max_dets <= 4096 && n_streams * (long long)max_tracks < (1 << 25),
                  "tracker_create: capacities out of range (tracks %d, dets %d)", max_tracks, max_dets);
     B200_REQUIRE(conf->hist_max >= 1 && conf->hist_max <= cost::kMaxBank, "tracker_create: hist_max %d outside [1,%d]",
                  conf->hist_max, cost::kMaxBank);
@@ -574,6 +718,8 @@ extern "C" int b200_tracker_create(b200_tracker** out, int n_streams, int max_tr
     TAKE(rows_main, int, S * MT); TAKE(rows_reid, int, S * MT); TAKE(cnt, int, S * trk::kHdr);
     TAKE(ud1, int, S * MD); TAKE(det_used, int, S * MD); TAKE(m_row, int, S * MT); TAKE(m_det, int, S * MT);
     TAKE(m_app, int, S * MT); TAKE(tmp, int, S * MT);
+    const size_t tiles_max = (MD + cost::kTileN - 1) / cost::kTileN;
+    TAKE(work1, int2, S * MT * tiles_max); TAKE(work2, int2, S * MT * tiles_max); TAKE(wcount, int, 2);
     // inputs (one contiguous block so step_host needs a single H2D copy) and the result table
     const size_t o_in = c.take<double>(0);
     TAKE(in_ndet, int, S); TAKE(in_frame, int, S); TAKE(in_boxes, double, S * MD * 4); TAKE(in_confs, double, S * MD);
@@ -595,7 +741,7 @@ extern "C" int b200_tracker_create(b200_tracker** out, int n_streams, int max_tr
     PTR(det_unit, float); PTR(det_z, float); PTR(det_boxf, float); PTR(det_conff, float); PTR(prev_boxf, float);
     PTR(prev_conff, float); PTR(C1, float); PTR(C1T, float); PTR(C2, float); PTR(C2T, float); PTR(gate_SI, double);
     PTR(rows_main, int); PTR(rows_reid, int); PTR(cnt, int); PTR(ud1, int); PTR(det_used, int); PTR(m_row, int);
-    PTR(m_det, int); PTR(m_app, int); PTR(tmp, int);
+    PTR(m_det, int); PTR(m_app, int); PTR(tmp, int); PTR(work1, int2); PTR(work2, int2); PTR(wcount, int);
 #undef PTR
     t->in_ndet = reinterpret_cast<int*>(base + o_in_ndet);
     t->in_frame = reinterpret_cast<int*>(base + o_in_frame);
@@ -642,7 +788,20 @@ extern "C" int b200_tracker_create(b200_tracker** out, int n_streams, int max_tr
         return fail(B200_ECUDA, "tracker_create: %s", cudaGetErrorString(e));
     }
     g_launches.fetch_add(1);
-    t->rows_ub = 0;
+    {
+        int per_sm = 1, sms = kSMs, devid = 0;
+        cudaGetDevice(&devid);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, devid);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trk::cost_kernel<1>, cost::kThreads,
+                                                      cost::smem_bytes(d.HIST));
+        t->cost_grid = sms * (per_sm > 0 ? per_sm : 1);
+        cudaFuncSetAttribute(trk::cost1_sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)trk::cost1_smem_bytes(d.HIST));
+        per_sm = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trk::cost1_sparse_kernel, trk::kCost1Warps * 32,
+                                                      trk::cost1_smem_bytes(d.HIST));
+        t->cost1_grid = sms * (per_sm > 0 ? per_sm : 1);
+    }
     *out = t;
     return B200_OK;
 }
@@ -657,7 +816,6 @@ extern "C" void b200_tracker_destroy(b200_tracker* t) {
 extern "C" int b200_tracker_reset(b200_tracker* t, void* stream) {
     B200_REQUIRE(t, "tracker_reset: null handle");
     trk::reset_kernel<<<t->d.S, 128, 0, as_stream(stream)>>>(t->d);
-    t->rows_ub = 0;
     return check_launch("reset_kernel");
 }
 
@@ -669,25 +827,19 @@ extern "C" int b200_tracker_step(b200_tracker* t, const int32_t* n_det, const do
     cudaStream_t st = as_stream(stream);
     trk::Dev d = t->d;
     d.n_det = n_det; d.boxes = boxes; d.confs = confs; d.embs = embs; d.frame_id = frame_id; d.result = result;
-    const int tiles = (d.MD + cost::kTileN - 1) / cost::kTileN;
     const size_t csm = cost::smem_bytes(d.HIST);
-    trk::begin_kernel<<<d.S, trk::kThreads, 0, st>>>(d);
+    const int cost_grid = t->cost_grid;
+    trk::begin_kernel<<<dim3(d.S, 2), trk::kThreads, 0, st>>>(d);
     int rc = check_launch("trk begin_kernel");
     if (rc) return rc;
-    if (t->rows_ub > 0) {
-        trk::cost_kernel<1><<<dim3(tiles, t->rows_ub, d.S), cost::kThreads, csm, st>>>(d);
-        if ((rc = check_launch("trk cost_kernel<1>"))) return rc;
-    }
+    trk::cost1_sparse_kernel<<<t->cost1_grid, trk::kCost1Warps * 32, trk::cost1_smem_bytes(d.HIST), st>>>(d);
+    if ((rc = check_launch("trk cost1_sparse_kernel"))) return rc;
     trk::assign_kernel<1><<<d.S, trk::kThreads, t->assign_smem, st>>>(d, t->smem_matrix_floats);
     if ((rc = check_launch("trk assign_kernel<1>"))) return rc;
-    if (t->rows_ub > 0) {
-        trk::cost_kernel<2><<<dim3(tiles, t->rows_ub, d.S), cost::kThreads, csm, st>>>(d);
-        if ((rc = check_launch("trk cost_kernel<2>"))) return rc;
-    }
+    trk::cost_kernel<2><<<cost_grid, cost::kThreads, csm, st>>>(d);
+    if ((rc = check_launch("trk cost_kernel<2>"))) return rc;
     trk::assign_kernel<2><<<d.S, trk::kThreads, t->assign_smem, st>>>(d, t->smem_matrix_floats);
     if ((rc = check_launch("trk assign_kernel<2>"))) return rc;
-    // without a read-back the live-track bound can only grow by the detections of this step
-    t->rows_ub = t->rows_ub + d.MD < d.MT ? t->rows_ub + d.MD : d.MT;
     return B200_OK;
 }
 
@@ -724,12 +876,6 @@ extern "C" int b200_tracker_step_host(b200_tracker* t, const int32_t* n_det_host
     B200_CUDA(cudaMemcpyAsync(h_res, t->dev_result, t->res_bytes, cudaMemcpyDeviceToHost, st));
     B200_CUDA(cudaStreamSynchronize(st));
     memcpy(result_host, h_res, t->res_bytes);
-    int ub = 0;
-    for (int s = 0; s < d.S; ++s) {
-        const int nl = result_host[(size_t)s * d.res_stride + trk::R_NLIVE];
-        ub = nl > ub ? nl : ub;
-    }
-    t->rows_ub = ub;                                    // exact after a read-back
     return B200_OK;
 }
 
@@ -772,3 +918,9 @@ extern "C" int b200_tracker_export(b200_tracker* t, int stream_idx, int32_t* ids
     B200_CUDA(cudaFreeAsync(buf, st));
     return (int)n;
 }
+
+#ifdef B200_TRK_TIMING
+extern "C" int b200_debug_timing(long long* out32) {
+    return cudaMemcpyFromSymbol(out32, b200::trk::g_timing, sizeof(long long) * 32) == cudaSuccess ? 0 : -2;
+}
+#endif

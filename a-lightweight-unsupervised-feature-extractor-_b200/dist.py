@@ -1,0 +1,54 @@
+"""Multi-GPU plumbing: independent video streams are partitioned across ranks (one process per
+GPU); the only traffic is a gather of the small per-stream result tables.
+
+The association step itself never crosses GPUs -- a stream's state lives on exactly one device --
+so there is no data-path collective; ``ResultGatherer`` exists because a consumer (the display /
+sink process of tracking.py:329) wants every stream's matches in one place.
+"""
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+
+
+def stream_owner(stream: int, world: int) -> int:
+    """Static placement: stream s lives on rank s mod world."""
+    return stream % world
+
+
+def local_streams(n_streams: int, rank: int, world: int) -> List[int]:
+    return [s for s in range(n_streams) if stream_owner(s, world) == rank]
+
+
+class ResultGatherer:
+    """All-gathers per-stream result tables (int32 [n_local, stride]) into global stream order."""
+
+    def __init__(self, n_streams: int, stride: int, device, group: Optional[dist.ProcessGroup] = None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.n_streams, self.stride = n_streams, stride
+        self.local = local_streams(n_streams, self.rank, self.world)
+        self.per_rank = (n_streams + self.world - 1) // self.world
+        self._send = torch.zeros((self.per_rank, stride), dtype=torch.int32, device=device)
+        self._recv = torch.zeros((self.world, self.per_rank, stride), dtype=torch.int32, device=device)
+        # global stream s sits at [s % world, s // world] of the gathered buffer
+        idx = torch.tensor([(s % self.world) * self.per_rank + s // self.world for s in range(n_streams)],
+                           dtype=torch.long, device=device)
+        self._index = idx
+
+    def gather(self, local_results: torch.Tensor, async_op: bool = False):
+        """Returns Tensor[n_streams, stride] (or (work, finish) when async_op)."""
+        n = len(self.local)
+        if local_results.shape != (n, self.stride):
+            raise ValueError("expected local results of shape %s" % ((n, self.stride),))
+        self._send[:n].copy_(local_results)
+        if self.world == 1:
+            out = self._send[:n].clone()
+            return (None, lambda: out) if async_op else out
+        work = dist.all_gather_into_tensor(self._recv.view(-1), self._send.view(-1), group=self.group,
+                                           async_op=async_op)
+        finish = lambda: self._recv.view(-1, self.stride).index_select(0, self._index)  # noqa: E731
+        if async_op:
+            return work, finish
+        return finish()
