@@ -19,3 +19,4 @@ int fail(int code, const char* fmt, ...) {
 extern "C" int b200_version(void) { return 100; }
 extern "C" const char* b200_last_error(void) { return b200::g_err; }
 extern "C" int64_t b200_launch_count(void) { return b200::g_launches.load(); }
+

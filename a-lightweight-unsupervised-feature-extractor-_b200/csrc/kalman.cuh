@@ -275,5 +275,98 @@ __device__ __forceinline__ double gate_d2(const double* SI, const double* xs, in
     return d;
 }
 
+// Cooperative form of update_t: eight consecutive lanes of a warp share one track, lane i owning row i of
+// P and of K.  Every entry is computed with the same operations in the same order as update_t (so the two
+// forms agree bit for bit); what changes is who computes it, the code size (one row instead of 64 unrolled
+// entries) and the register footprint.  sP (64 doubles) and sK (32 doubles) are this group's scratch in
+// shared memory; `mask` is the set of lanes of the warp executing the call (all groups in it take the same
+// template instantiation).  Returns the squared Mahalanobis distance of z to the UPDATED state when
+// want_d2 (mainTracking.py:424), else 0.
+template <typename TX, typename TP>
+__device__ __forceinline__ double update_rows_t(double* gx, double* gP, const float* z, const float* r, double* sP,
+                                                double* sK, int i, unsigned mask, int new_stage, bool want_d2) {
+    using TXN = typename Promote<TX, TP>::type;
+    double Pr[8];
+    {
+        const double2* p2 = reinterpret_cast<const double2*>(gP + i * 8);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { const double2 v = p2[k]; Pr[2 * k] = v.x; Pr[2 * k + 1] = v.y; }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sP[i * 8 + j] = Pr[j];
+    double xg[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) xg[k] = gx[k];
+    const double xi = gx[i];
+    __syncwarp(mask);
+    TP S[16], SI[16], Kr[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) S[a * 4 + b] = (TP)sP[a * 8 + b] + (a == b ? (TP)r[a] : (TP)0);
+    inv4<TP>(S, SI);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        TP acc = (TP)Pr[0] * SI[j];
+#pragma unroll
+        for (int k = 1; k < 4; ++k) acc = fma((TP)Pr[k], SI[k * 4 + j], acc);
+        Kr[j] = acc;
+    }
+    TX y[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) y[k] = (TX)z[k] - (TX)xg[k];
+    TXN sx = (TXN)Kr[0] * (TXN)y[0];
+#pragma unroll
+    for (int k = 1; k < 4; ++k) sx = fma((TXN)Kr[k], (TXN)y[k], sx);
+    const double xn = (double)((TXN)(TX)xi + sx);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) sK[i * 4 + j] = (double)Kr[j];
+    __syncwarp(mask);                       // P rows and K rows of the whole track are visible; x has been read
+    gx[i] = xn;
+    // A = (I-KH) P, row i
+    double ik[4], A[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) ik[k] = (i == k) ? 1.0 - (double)Kr[k] : -(double)Kr[k];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        double a = ik[0] * sP[j];
+#pragma unroll
+        for (int k = 1; k < 4; ++k) a = fma(ik[k], sP[k * 8 + j], a);
+        A[j] = i >= 4 ? a + Pr[j] : a;
+    }
+    // B = A (I-KH)^T + (K R) K^T, row i
+    double Pn[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        double ikj[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) ikj[k] = (j == k) ? 1.0 - sK[j * 4 + k] : -sK[j * 4 + k];
+        const double b = fma(A[3], ikj[3], fma(A[2], ikj[2], fma(A[1], ikj[1], A[0] * ikj[0])));
+        TP dd = (Kr[0] * (TP)r[0]) * (TP)sK[j * 4];
+#pragma unroll
+        for (int k = 1; k < 4; ++k) dd = fma(Kr[k] * (TP)r[k], (TP)sK[j * 4 + k], dd);
+        Pn[j] = (j < 4 ? b : b + A[j]) + (double)dd;
+    }
+    {
+        double2* p2 = reinterpret_cast<double2*>(gP + i * 8);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) p2[k] = make_double2(Pn[2 * k], Pn[2 * k + 1]);
+    }
+    if (!want_d2) return 0.0;
+    __syncwarp(mask);                       // everyone is done reading the old P rows
+    if (i < 4) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) sP[i * 8 + j] = Pn[j];
+        sK[i] = xn;
+    }
+    __syncwarp(mask);
+    Gate g;
+    double x4[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) x4[k] = sK[k];
+    gate_prepare(x4, sP, new_stage, r, &g);
+    return gate_d2(g.SI, g.xs, new_stage, z);
+}
+
 }  // namespace kf
 }  // namespace b200

@@ -8,9 +8,10 @@
 // sampling weights depend on the ROI only, not on the channel, so each warp
 //   1. turns the ROI's PH*gh + PW*gw sample positions into two small dense weight
 //      tables Wy[FY][PH], Wx[FX][PW] over the ROI's footprint (FY x FX map cells);
-//   2. stages the footprint of its 32 channels into shared memory as V[cell][channel]
-//      (NHWC: coalesced 128 B cp.async per cell; NCHW: 16 B vector loads along x,
-//      transposed on the way in);
+//   2. stages the footprint of its 32 channels into shared memory as V[cell][channel] with
+//      cp.async (NHWC: one coalesced 128 B request per cell; NCHW: lanes run along x inside
+//      a row segment so a request touches the fewest lines, transposed by the destination
+//      address), issued before step 1's arithmetic so the round trip overlaps it;
 //   3. accumulates out[ph][pw] = sum_x Wx[x][pw] * (sum_y Wy[y][ph] * V[y][x]) in
 //      registers (PH*PW accumulators per lane, every map value read exactly once);
 //   4. writes its [32][PH*PW] result tile -- contiguous in the NCHW output -- to shared
@@ -25,7 +26,12 @@
 namespace b200 {
 namespace {
 
-constexpr int kWarpsPerCta = 2;
+int g_roi_ctas_per_sm = 0;        // 0: one CTA per two tiles; > 0: persistent grid of that many CTAs per SM
+
+#ifndef B200_ROI_WARPS
+#define B200_ROI_WARPS 2
+#endif
+constexpr int kWarpsPerCta = B200_ROI_WARPS;
 constexpr int kFootCap = 8;     // max footprint rows / cols on the staged path (<= 64 cells x 32 ch = 8 KB)
 constexpr int kCellCap = kFootCap * kFootCap;
 
@@ -113,13 +119,16 @@ __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.wait_all;\n" ::: "memory");
 }
 
-// One bulk async copy shared -> global issued by a single lane (TMA engine, SASS UBLKCP).
-__device__ __forceinline__ void bulk_store(float* gdst, const float* ssrc, unsigned bytes) {
+// One bulk async copy shared -> global issued by a single lane (TMA engine, SASS UBLKCP).  The
+// source tile may be overwritten only after bulk_store_wait_read() on the issuing lane.
+__device__ __forceinline__ void bulk_store_issue(float* gdst, const float* ssrc, unsigned bytes) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(ssrc);
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gdst), "r"(s),
                  "r"(bytes)
                  : "memory");
     asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+}
+__device__ __forceinline__ void bulk_store_wait_read() {
     asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
 }
 
@@ -176,7 +185,7 @@ __device__ __forceinline__ void separable_accumulate(float (&acc)[PH][PW], const
 #endif
 
 template <int PH, int PW, bool NHWC>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, B200_ROI_MIN_CTAS)
+__global__ void __launch_bounds__(kWarpsPerCta * 32, (B200_ROI_MIN_CTAS * 2 + kWarpsPerCta - 1) / kWarpsPerCta)
 roi_align_tile_kernel(const float* __restrict__ feat, int B, int C, int H, int W,
                       const float* __restrict__ rois, long long K, float scale, int sr, int aligned,
                       float* __restrict__ out, int ctiles) {
@@ -185,11 +194,15 @@ roi_align_tile_kernel(const float* __restrict__ feat, int B, int C, int H, int W
     static_assert(PH <= 16 && PW <= 16, "one lane per output row/column");
     extern __shared__ __align__(16) float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long wi = (long long)blockIdx.x * kWarpsPerCta + warp;
-    if (wi >= K * ctiles) return;            // warps are independent: no block-wide barriers below
+    // Warps are independent (no block-wide barriers) and persistent: warp w of the grid takes tiles
+    // w, w + #warps, ...  The bulk store of one tile is only waited for after the next tile's geometry.
+    const int span_slot = (int)((reinterpret_cast<uintptr_t>(rois) / (size_t)(K * 20)) & 7);   // debug: step index mod 8
+    B200_SPAN_BEGIN(span_slot);
     float* sMain = smem + (size_t)warp * L::kFloatsPerWarp;   // V staging / big tables, later the output tile
     float* sTab = sMain + L::kMainFloats;
-
+    const long long total = K * ctiles, wstride = (long long)gridDim.x * kWarpsPerCta;
+    bool pending = false;                    // lane 0: a bulk store may still be reading sMain
+    for (long long wi = (long long)blockIdx.x * kWarpsPerCta + warp; wi < total; wi += wstride) {
     const long long k = wi / ctiles;
     const int c0 = (int)(wi % ctiles) * 32;
     const int cn = min(32, C - c0);
@@ -199,6 +212,11 @@ roi_align_tile_kernel(const float* __restrict__ feat, int B, int C, int H, int W
     axis_footprint(g.sh, g.bh, PH, g.gh, H, &ymin, &FY);
     axis_footprint(g.sw, g.bw, PW, g.gw, W, &xmin, &FX);
     if (g.b < 0 || g.b >= B || FY == 0 || FX == 0) FY = FX = 0;      // nothing sampled: zeros
+    if (pending) {                            // previous tile's output has left shared memory
+        if (lane == 0) bulk_store_wait_read();
+        pending = false;
+    }
+    __syncwarp();
     const bool staged = FY <= kFootCap && FX <= kFootCap;
     // Larger footprints keep their (bigger) weight tables in the output-tile area and read V
     // straight from global memory; only absurdly large ones take the per-bin path.
@@ -211,6 +229,33 @@ roi_align_tile_kernel(const float* __restrict__ feat, int B, int C, int H, int W
         for (int b = 0; b < PW; ++b) acc[a][b] = 0.0f;
 
     if (staged || direct) {
+        float* sV = sMain;
+        // ---- stage V[cell][channel], fully asynchronous, BEFORE the weight tables are built so the
+        // global-memory round trip overlaps that work.  Cell (r, x) of channel c lands at
+        // (r*FX + x)*32 + ((c + skew(x)) & 31): the skew makes both the channel-fastest reads of the
+        // accumulation loop and the x-fastest NCHW writes bank-conflict free. -------------------------
+        int nxp = 1;
+        while (nxp < FX) nxp <<= 1;                                  // lanes per row segment: 1, 2, 4, 8
+        const int cper = 32 / (nxp > 32 ? 32 : nxp), xmask = nxp - 1;
+        if (staged && FY) {
+            if (NHWC) {
+                const float* base = feat + (((size_t)g.b * H + ymin) * W + xmin) * C + c0 + lane;
+                if (lane < cn)
+                    for (int r = 0; r < FY; ++r) {
+                        const float* src = base + (size_t)r * W * C;
+                        for (int x = 0; x < FX; ++x, src += C)
+                            cp_async4(sV + (r * FX + x) * 32 + ((lane + (x & xmask) * cper) & 31), src);
+                    }
+            } else {
+                const int xi = lane & xmask, cs = lane / nxp;        // lane = (channel sub-index, x)
+                const float* base = feat + (((size_t)g.b * C + c0) * H + ymin) * W + xmin + xi;
+                if (xi < FX)
+                    for (int r = 0; r < FY; ++r)
+                        for (int c = cs; c < cn; c += cper)
+                            cp_async4(sV + (r * FX + xi) * 32 + ((c + xi * cper) & 31),
+                                      base + ((size_t)c * H + r) * W);
+            }
+        }
         // ---- dense separable weight tables over the footprint (lanes 0-15: y, 16-31: x) ------
         float* sWy = staged ? sTab : sMain;
         float* sWx = sWy + (staged ? kFootCap : FY) * PHP;
@@ -236,63 +281,11 @@ roi_align_tile_kernel(const float* __restrict__ feat, int B, int C, int H, int W
                 }
         }
         if (staged) {
-            // ---- stage V[cell][channel] -----------------------------------------------------
-            const int ncell = FY * FX;
-            float* sV = sMain;
-            if (NHWC) {
-                const float* base = feat + (((size_t)g.b * H + ymin) * W + xmin) * C + c0 + lane;
-                if (lane < cn) {
-                    float* dst = sV + lane;
-                    for (int r = 0; r < FY; ++r) {
-                        const float* src = base + (size_t)r * W * C;
-                        for (int x = 0; x < FX; ++x, dst += 32, src += C) cp_async4(dst, src);
-                    }
-                }
-                cp_async_wait_all();
-            } else if (ncell) {
-                const float* plane0 = feat + ((size_t)g.b * C + c0) * H * W;
-                const bool vec = (W & 3) == 0 && ((reinterpret_cast<uintptr_t>(feat) & 15) == 0);
-                const int G = vec ? 4 : 1;
-                const int q0 = xmin / G, nq = (xmin + FX - 1) / G - q0 + 1;   // chunks per footprint row
-                int nqp = 1;
-                while (nqp < nq) nqp <<= 1;                         // lanes per row segment (<= 8)
-                const int per_it = 32 / nqp, sub = lane & (nqp - 1), slot = lane / nqp;
-                const int items = cn * FY;                           // item = r * cn + c (channel fastest)
-                const int xq = (q0 + sub) * G;
-                int rn = 0, cnx = slot;                              // (row, channel) of this lane's next item
-                while (cnx >= cn) { cnx -= cn; ++rn; }
-                for (int base = 0; base < items; base += 4 * per_it) {
-                    float4 v[4];
-                    int rr[4], cc[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {                    // all loads of the batch first
-                        const int item = base + u * per_it + slot;
-                        rr[u] = -1;
-                        if (item < items && sub < nq) {
-                            rr[u] = rn;
-                            cc[u] = cnx;
-                            const float* p = plane0 + ((size_t)cc[u] * H + ymin + rr[u]) * W + xq;
-                            if (vec) v[u] = __ldg(reinterpret_cast<const float4*>(p));
-                            else v[u].x = __ldg(p);
-                        }
-                        cnx += per_it;                               // advance without integer division
-                        while (cnx >= cn) { cnx -= cn; ++rn; }
-                    }
-#pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                        if (rr[u] >= 0) {
-                            const float e4[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const int x = xq + e - xmin;
-                                if (e < G && x >= 0 && x < FX) sV[(rr[u] * FX + x) * 32 + cc[u]] = e4[e];
-                            }
-                        }
-                }
-            }
+            cp_async_wait_all();
             __syncwarp();
-            separable_accumulate<PH, PW>(acc, sWy, sWx, FY, FX,
-                                         [&](int r, int x) { return sV[(r * FX + x) * 32 + lane]; });
+            separable_accumulate<PH, PW>(acc, sWy, sWx, FY, FX, [&](int r, int x) {
+                return sV[(r * FX + x) * 32 + ((lane + (x & xmask) * cper) & 31)];
+            });
         } else {
             __syncwarp();
             const int cl = lane < cn ? lane : 0;                     // idle lanes re-read channel 0
@@ -358,12 +351,16 @@ roi_align_tile_kernel(const float* __restrict__ feat, int B, int C, int H, int W
     if (bulk) {
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
         __syncwarp();
-        if (lane == 0) bulk_store(gdst, sMain, bytes);
-        __syncwarp();
+        if (lane == 0) bulk_store_issue(gdst, sMain, bytes);
+        pending = true;
     } else {
         __syncwarp();
         for (int i = lane; i < cn * NB; i += 32) gdst[i] = sMain[i];
+        __syncwarp();
     }
+    }   // persistent tile loop
+    if (pending && lane == 0) bulk_store_wait_read();     // shared memory must outlive the last copy
+    B200_SPAN_END(span_slot);
 }
 
 // Any output size / any parameters: one thread per output element, direct sampling.
@@ -413,7 +410,17 @@ int launch_tile(const float* feat, int B, int C, int H, int W, const float* rois
     }
     const int ctiles = (C + 31) / 32;
     const long long warps = K * ctiles;
-    const long long blocks = (warps + kWarpsPerCta - 1) / kWarpsPerCta;
+    long long blocks = (warps + kWarpsPerCta - 1) / kWarpsPerCta;
+    if (g_roi_ctas_per_sm > 0) {             // persistent grid: a fixed number of CTAs per SM loop over the tiles
+        static int sms = 0;
+        if (!sms) {
+            int dev = 0;
+            B200_CUDA(cudaGetDevice(&dev));
+            B200_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        }
+        const long long cap = (long long)sms * g_roi_ctas_per_sm;
+        if (blocks > cap) blocks = cap;
+    }
     if (blocks > 0x7fffffffLL) return fail(B200_EINVAL, "roi_align: too many ROI tiles (%lld)", blocks);
     kern<<<(unsigned)blocks, kWarpsPerCta * 32, L::kBytesPerCta, st>>>(feat, B, C, H, W, rois, K, scale, sr,
                                                                      aligned, out, ctiles);
@@ -422,6 +429,11 @@ int launch_tile(const float* feat, int B, int C, int H, int W, const float* rois
 
 }  // namespace
 }  // namespace b200
+
+extern "C" int b200_roi_align_set_ctas_per_sm(int ctas_per_sm) {
+    b200::g_roi_ctas_per_sm = ctas_per_sm > 0 ? ctas_per_sm : 0;
+    return B200_OK;
+}
 
 extern "C" int b200_roi_align_fwd_f32(const float* feat, int layout, int B, int C, int H, int W,
                                       const float* rois, int64_t K, int PH, int PW, float spatial_scale,
@@ -455,3 +467,5 @@ extern "C" int b200_roi_align_fwd_f32(const float* feat, int layout, int B, int 
                                                                 spatial_scale, sampling_ratio, aligned, out);
     return check_launch("roi_align_generic_kernel");
 }
+
+B200_SPAN_GETTER(b200_debug_spans_roi)

@@ -23,6 +23,12 @@
 namespace b200 {
 namespace trk {
 
+struct Span {                     // RAII global-timer span of one kernel (debug builds only)
+    int k;
+    __device__ explicit Span(int kk) : k(kk) { B200_SPAN_BEGIN(k); }
+    __device__ ~Span() { B200_SPAN_END(k); }
+};
+
 #ifdef B200_TRK_TIMING          // debug builds only: SM-clock stamps at phase boundaries of stream 0
 __device__ long long g_timing[32];
 #define TRK_STAMP(k) do { __syncthreads(); if (threadIdx.x == 0 && blockIdx.x == 0) g_timing[k] = clock64(); } while (0)
@@ -140,6 +146,7 @@ __device__ inline void enqueue_cost_work(int2* work, int* counter, int s, int M,
 
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) begin_kernel(Dev d) {
+    Span span((d.frame_id[0] & 7) * 5 + 0);
     __shared__ int scratch[kThreads / 32];
     const int s = blockIdx.x, tid = threadIdx.x;
     int* hdr = d.hdr + s * kHdr;
@@ -232,6 +239,7 @@ __global__ void __launch_bounds__(kThreads) begin_kernel(Dev d) {
 // STAGE 1: rows_main x all detections, full cost + gate.  STAGE 2: rows_reid x leftover dets, C_app.
 template <int STAGE>
 __global__ void __launch_bounds__(cost::kThreads) cost_kernel(Dev d) {
+    Span span((d.frame_id[0] & 7) * 5 + 3);
     extern __shared__ __align__(16) float smem[];
     __shared__ int s_idx[cost::kTileN];
     const int total = d.wcount[STAGE - 1];
@@ -291,16 +299,12 @@ __global__ void __launch_bounds__(cost::kThreads) cost_kernel(Dev d) {
 // computed its full cost (:496-511).  The result does not depend on the order, and in steady state ~98 %
 // of the pairs are gated, so this kernel evaluates the gate for all pairs first and
 // runs the bank contraction + top-k only for the pairs that survive.  One warp owns one track row:
-//   lane = detection (chunks of 32): box/conf terms and d2; ballot -> surviving detections;
-//   per survivor: lane = bank row t, a 128-long fp32 dot product against the detection (bank rows staged
-//   re-normalised in shared memory with a padded stride, so the 16 B loads of 32 rows are conflict free),
-//   then k rounds of warp-max for the top-k mean.
+//   lane = detection (chunks of 32): d2 and, for survivors, the box/conf terms; ballot -> survivors;
+//   per survivor: lanes split the 128 dimensions (one coalesced 512 B read per bank row, eight rows in
+//   flight), a shuffle reduction gives <bank_t, det>, lane t keeps the similarity of row t, then k rounds
+//   of warp-max give the top-k mean.  No shared memory and few registers, so every row of a 64-stream
+//   group is resident at once and the kernel can share SMs with ROI Align.
 constexpr int kCost1Warps = 4;
-constexpr int kBankStride = cost::kD + 4;
-
-__host__ __device__ inline size_t cost1_smem_bytes(int T) {
-    return sizeof(float) * (size_t)kCost1Warps * cost::bank_cap(T) * kBankStride;
-}
 
 __device__ __forceinline__ unsigned fkey(float f) {                 // order-preserving float -> uint
     const unsigned b = __float_as_uint(f);
@@ -308,11 +312,10 @@ __device__ __forceinline__ unsigned fkey(float f) {                 // order-pre
 }
 
 __global__ void __launch_bounds__(kCost1Warps * 32) cost1_sparse_kernel(Dev d) {
-    extern __shared__ __align__(16) float smem[];
+    Span span((d.frame_id[0] & 7) * 5 + 1);
     const int total = d.wcount[0];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tcap = cost::bank_cap(d.HIST);
-    float* sBank = smem + (size_t)warp * tcap * kBankStride;
+    const float kNegInf = -__int_as_float(0x7f800000);
     for (int wi = blockIdx.x * kCost1Warps + warp; wi < total; wi += gridDim.x * kCost1Warps) {
         const int2 item = d.work1[wi];
         const int s = item.x, r = item.y >> 6;
@@ -323,8 +326,7 @@ __global__ void __launch_bounds__(kCost1Warps * 32) cost1_sparse_kernel(Dev d) {
         const float* rows = d.bank + slot * d.HIST * cost::kD;
         if (T <= 0) { rows = d.ema + slot * cost::kD; T = 1; }        // :180-182 fallback to the EMA
         const int kk = min(d.topk, T);
-        // per-row gate inputs
-        double SI[16], xs[4];
+        double SI[16], xs[4];                                         // per-row gate inputs
 #pragma unroll
         for (int k = 0; k < 16; ++k) SI[k] = d.gate_SI[slot * 16 + k];
 #pragma unroll
@@ -334,53 +336,51 @@ __global__ void __launch_bounds__(kCost1Warps * 32) cost1_sparse_kernel(Dev d) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) pb[k] = d.prev_boxf[slot * 4 + k];
         const float pconf = d.prev_conff[slot];
-        bool staged = false;
+        float inv0 = 0.0f, inv1 = 0.0f;           // 1 / (|bank_t| + 1e-12) of rows lane and lane + 32 (:188-189)
+        bool have_norm = false;
         for (int j0 = 0; j0 < N; j0 += 32) {
             const int j = j0 + lane;
             bool alive = false;
             if (j < N) alive = !(kf::gate_d2(SI, xs, stage, d.det_z + (db + j) * 4) > d.maha_thr);   // :335
             unsigned todo = __ballot_sync(0xffffffffu, alive);
             float c_app = 0.0f;
-            if (todo && !staged) {                                 // stage the re-normalised bank once per row
-                for (int t = 0; t < T; ++t) {
-                    const float4 v = cost::unit_row(reinterpret_cast<const float4*>(rows + (size_t)t * cost::kD)[lane]);
-                    reinterpret_cast<float4*>(sBank + t * kBankStride)[lane] = v;
-                }
-                __syncwarp();
-                staged = true;
-            }
             while (todo) {
                 const int jl = __ffs(todo) - 1;
                 todo &= todo - 1;
-                const float4* det = reinterpret_cast<const float4*>(d.det_unit + (db + j0 + jl) * cost::kD);
-                float s0 = -__int_as_float(0x7f800000), s1 = s0;   // sims of bank rows lane and lane + 32
-                if (lane < T) {
-                    const float4* b = reinterpret_cast<const float4*>(sBank + lane * kBankStride);
-                    float a = 0.0f;
-#pragma unroll 8
-                    for (int k = 0; k < cost::kD / 4; ++k) {
-                        const float4 x = b[k], y = __ldg(det + k);
-                        a = fmaf(x.x, y.x, a); a = fmaf(x.y, y.y, a); a = fmaf(x.z, y.z, a); a = fmaf(x.w, y.w, a);
+                const float4 dv = reinterpret_cast<const float4*>(d.det_unit + (db + j0 + jl) * cost::kD)[lane];
+                float s0 = kNegInf, s1 = kNegInf;                    // similarities of bank rows lane, lane + 32
+                for (int t0 = 0; t0 < T; t0 += 8) {
+                    float4 bv[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        if (t0 + u < T) bv[u] = reinterpret_cast<const float4*>(rows + (size_t)(t0 + u) * cost::kD)[lane];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int t = t0 + u;
+                        if (t >= T) break;                          // uniform
+                        float p = bv[u].x * dv.x;
+                        p = fmaf(bv[u].y, dv.y, p); p = fmaf(bv[u].z, dv.z, p); p = fmaf(bv[u].w, dv.w, p);
+                        p = warp_sum(p);
+                        if (!have_norm) {
+                            float q = bv[u].x * bv[u].x;
+                            q = fmaf(bv[u].y, bv[u].y, q); q = fmaf(bv[u].z, bv[u].z, q); q = fmaf(bv[u].w, bv[u].w, q);
+                            q = warp_sum(q);
+                            const float iv = __fdiv_rn(1.0f, __fadd_rn(sqrtf(q), 1e-12f));
+                            if (lane == (t & 31)) { if (t < 32) inv0 = iv; else inv1 = iv; }
+                        }
+                        if (lane == (t & 31)) { if (t < 32) s0 = p; else s1 = p; }
                     }
-                    s0 = a;
                 }
-                if (lane + 32 < T) {
-                    const float4* b = reinterpret_cast<const float4*>(sBank + (lane + 32) * kBankStride);
-                    float a = 0.0f;
-#pragma unroll 8
-                    for (int k = 0; k < cost::kD / 4; ++k) {
-                        const float4 x = b[k], y = __ldg(det + k);
-                        a = fmaf(x.x, y.x, a); a = fmaf(x.y, y.y, a); a = fmaf(x.z, y.z, a); a = fmaf(x.w, y.w, a);
-                    }
-                    s1 = a;
-                }
+                have_norm = true;
+                if (lane < T) s0 *= inv0;
+                if (lane + 32 < T) s1 *= inv1;
                 float sum = 0.0f;                                   // top-k mean, largest first (:196-202)
                 for (int q = 0; q < kk; ++q) {
                     const float mine = fmaxf(s0, s1);
                     const unsigned m = __reduce_max_sync(0xffffffffu, fkey(mine));
                     const unsigned who = __ballot_sync(0xffffffffu, fkey(mine) == m);
                     if (lane == __ffs(who) - 1) {
-                        if (s0 >= s1) s0 = -__int_as_float(0x7f800000); else s1 = -__int_as_float(0x7f800000);
+                        if (s0 >= s1) s0 = kNegInf; else s1 = kNegInf;
                     }
                     const unsigned bits = m ^ ((m >> 31) ? 0x80000000u : 0xffffffffu);
                     sum = __fadd_rn(sum, __uint_as_float(bits));
@@ -396,40 +396,168 @@ __global__ void __launch_bounds__(kCost1Warps * 32) cost1_sparse_kernel(Dev d) {
                 d.C1T[(db + j) * d.MT + r] = total_c;
             }
         }
-        __syncwarp();
+    }
+}
+
+// Sum over lanes of 32 per-lane partials at once: after the call lane t holds the full sum of
+// partial[t] in p[0].  31 shuffles instead of 32 x 5 (each stage sends the half the partner lane owns).
+__device__ __forceinline__ void transpose_reduce32(float (&p)[32]) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const bool up = lane & o;
+#pragma unroll
+        for (int i = 0; i < o; ++i) {
+            const float keep = up ? p[i + o] : p[i], send = up ? p[i] : p[i + o];
+            p[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+    }
+}
+
+// Stage-1 cost for hist_max <= 32 (the shipped 30): same algorithm as cost1_sparse_kernel, but the row's
+// whole bank is read once into registers (one global round trip, reused by every surviving detection) and
+// the 32 dot products of a detection are reduced together (transpose_reduce32).
+__global__ void __launch_bounds__(kCost1Warps * 32, 2) cost1_sparse32_kernel(Dev d) {
+    Span span((d.frame_id[0] & 7) * 5 + 1);
+    const int total = d.wcount[0];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float kNegInf = -__int_as_float(0x7f800000);
+    for (int wi = blockIdx.x * kCost1Warps + warp; wi < total; wi += gridDim.x * kCost1Warps) {
+        const int2 item = d.work1[wi];
+        const int s = item.x, r = item.y >> 6;
+        const int N = d.n_det[s];
+        const size_t sb = (size_t)s * d.MT, db = (size_t)s * d.MD;
+        const size_t slot = sb + d.rows_main[sb + r];
+        int T = d.bank_len[slot];
+        const float* rows = d.bank + slot * d.HIST * cost::kD;
+        if (T <= 0) { rows = d.ema + slot * cost::kD; T = 1; }        // :180-182 fallback to the EMA
+        const int kk = min(d.topk, T);
+        double SI[16], xs[4];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) SI[k] = d.gate_SI[slot * 16 + k];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) xs[k] = d.kf_x[slot * 8 + k];
+        const int stage = d.kf_stage[slot];
+        float pb[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) pb[k] = d.prev_boxf[slot * 4 + k];
+        const float pconf = d.prev_conff[slot];
+        float4 bv[32];
+        float inv = 0.0f;                          // 1 / (|bank_lane| + 1e-12), :188-189
+        bool have_bank = false;
+        for (int j0 = 0; j0 < N; j0 += 32) {
+            const int j = j0 + lane;
+            bool alive = false;
+            if (j < N) alive = !(kf::gate_d2(SI, xs, stage, d.det_z + (db + j) * 4) > d.maha_thr);   // :335
+            unsigned todo = __ballot_sync(0xffffffffu, alive);
+            float c_app = 0.0f;
+            if (todo && !have_bank) {
+                float q[32];
+#pragma unroll
+                for (int t = 0; t < 32; ++t)
+                    bv[t] = t < T ? reinterpret_cast<const float4*>(rows + (size_t)t * cost::kD)[lane] : make_float4(0, 0, 0, 0);
+#pragma unroll
+                for (int t = 0; t < 32; ++t) {
+                    float a = bv[t].x * bv[t].x;
+                    a = fmaf(bv[t].y, bv[t].y, a); a = fmaf(bv[t].z, bv[t].z, a); a = fmaf(bv[t].w, bv[t].w, a);
+                    q[t] = a;
+                }
+                transpose_reduce32(q);
+                inv = __fdiv_rn(1.0f, __fadd_rn(sqrtf(q[0]), 1e-12f));
+                have_bank = true;
+            }
+            while (todo) {
+                const int jl = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const float4 dv = reinterpret_cast<const float4*>(d.det_unit + (db + j0 + jl) * cost::kD)[lane];
+                float p[32];
+#pragma unroll
+                for (int t = 0; t < 32; ++t) {
+                    float a = bv[t].x * dv.x;
+                    a = fmaf(bv[t].y, dv.y, a); a = fmaf(bv[t].z, dv.z, a); a = fmaf(bv[t].w, dv.w, a);
+                    p[t] = a;
+                }
+                transpose_reduce32(p);
+                float sim = lane < T ? p[0] * inv : kNegInf;        // <bank_lane, det> of unit vectors
+                float sum = 0.0f;                                   // top-k mean, largest first (:196-202)
+                for (int q = 0; q < kk; ++q) {
+                    const unsigned m = __reduce_max_sync(0xffffffffu, fkey(sim));
+                    const unsigned who = __ballot_sync(0xffffffffu, fkey(sim) == m);
+                    if (lane == __ffs(who) - 1) sim = kNegInf;
+                    const unsigned bits = m ^ ((m >> 31) ? 0x80000000u : 0xffffffffu);
+                    sum = __fadd_rn(sum, __uint_as_float(bits));
+                }
+                const float ca = __fsub_rn(1.0f, __fdiv_rn(sum, (float)kk));
+                if (lane == jl) c_app = ca;
+            }
+            if (j < N) {
+                float total_c = 1e9f;
+                if (alive)
+                    total_c = cost::pair_cost(pb, d.det_boxf + (db + j) * 4, pconf, d.det_conff[db + j], d.pw, c_app).total;
+                d.C1[(sb + r) * d.MD + j] = total_c;
+                d.C1T[(db + j) * d.MT + r] = total_c;
+            }
+        }
     }
 }
 
 // update_matched (:375-448) for `nm` (row, det) pairs listed in m_row / m_det (det = global index).
 __device__ inline void update_matched(const Dev& d, int s, int nm, const int* rows, const float* C, int ldc,
-                                      const int* m_col, double cost_update_max, double maha_thr) {
+                                      const int* m_col, double cost_update_max, double maha_thr, double* kf_scratch) {
     const size_t sb = (size_t)s * d.MT, db = (size_t)s * d.MD;
     const int frame = d.frame_id[s];
     const float rdiag[4] = {1.f, 1.f, 1.f, 1.f};
-    for (int qd = threadIdx.x; qd < nm; qd += blockDim.x) {
-        const int r = d.m_row[sb + qd], j = d.m_det[sb + qd];
-        const size_t slot = sb + rows[r];
-        double x[8], P[64];
-        load_kf(d, slot, x, P);
-        const int st = kf::update(x, P, d.kf_stage[slot], d.det_z + (db + j) * 4, rdiag);
-        d.kf_stage[slot] = (uint8_t)st;
-        store_kf(d, slot, x, P);
-        const double conf = d.confs[db + j];
+    // Kalman update (:400) + bookkeeping (:403-426): eight lanes per match (one per row of P), see
+    // kf::update_rows_t; a 256-thread CTA works on 32 matches at a time.
+    {
+        const int sub = threadIdx.x & 7, group = threadIdx.x >> 3, ngroups = blockDim.x >> 3;
+        double* sP = kf_scratch + (size_t)group * 96;
+        double* sK = sP + 64;
+        for (int q0 = 0; q0 < nm; q0 += ngroups) {
+            const int qd = q0 + group;
+            const bool on = qd < nm;
+            int r = 0, j = 0, st = -1;
+            size_t slot = 0;
+            if (on) {
+                r = d.m_row[sb + qd];
+                j = d.m_det[sb + qd];
+                slot = sb + rows[r];
+                st = d.kf_stage[slot];
+            }
+            const float* z = d.det_z + (db + j) * 4;
+            const double conf = on ? d.confs[db + j] : 0.0;
+            const double c = on ? (double)C[(size_t)r * ldc + m_col[qd]] : 0.0;
+            int app = on && !(conf < d.conf_update_min) && !(c > cost_update_max);      // :418-421
+            // :424-426 posterior gate.  Whether d2 is evaluated must be uniform over every group that shares a
+            // __syncwarp mask inside update_rows_t, so it only depends on the (CTA-uniform) threshold.
+            const bool want = maha_thr < 1e17;
+            const int nst = st < 2 ? st + 1 : 2;
+            double d2 = 0.0;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) d.last_bbox[slot * 4 + k] = d.boxes[(db + j) * 4 + k];
-        d.last_conf[slot] = conf;
-        d.last_frame[slot] = frame;
-        d.age[slot] += 1;
-        d.miss[slot] = 0;
-        const double c = (double)C[(size_t)r * ldc + m_col[qd]];
-        d.last_cost[slot] = c;
-        int app = !(conf < d.conf_update_min) && !(c > cost_update_max);          // :418-421
-        if (app && maha_thr < 1e17) {                                            // :424-426 posterior gate
-            kf::Gate g;
-            kf::gate_prepare(x, P, st, rdiag, &g);
-            if (kf::gate_d2(g.SI, g.xs, st, d.det_z + (db + j) * 4) > maha_thr) app = 0;
+            for (int v = 0; v < 3; ++v) {                         // one pass per arithmetic variant (stage)
+                const unsigned mask = __ballot_sync(0xffffffffu, on && st == v);
+                if (on && st == v) {
+                    double* gx = d.kf_x + slot * 8;
+                    double* gP = d.kf_P + slot * 64;
+                    if (v == 0) d2 = kf::update_rows_t<float, float>(gx, gP, z, rdiag, sP, sK, sub, mask, nst, want);
+                    else if (v == 1) d2 = kf::update_rows_t<float, double>(gx, gP, z, rdiag, sP, sK, sub, mask, nst, want);
+                    else d2 = kf::update_rows_t<double, double>(gx, gP, z, rdiag, sP, sK, sub, mask, nst, want);
+                }
+            }
+            if (on && sub == 0) {
+                if (app && want && d2 > maha_thr) app = 0;
+                d.kf_stage[slot] = (uint8_t)nst;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) d.last_bbox[slot * 4 + k] = d.boxes[(db + j) * 4 + k];
+                d.last_conf[slot] = conf;
+                d.last_frame[slot] = frame;
+                d.age[slot] += 1;
+                d.miss[slot] = 0;
+                d.last_cost[slot] = c;
+                d.m_app[sb + qd] = app;
+            }
+            __syncwarp();
         }
-        d.m_app[sb + qd] = app;
     }
     __syncthreads();
     TRK_STAMP(3);
@@ -476,6 +604,7 @@ __device__ inline void update_matched(const Dev& d, int s, int nm, const int* ro
 // Returns the number of matches; *n_unmatched_rows is the count appended to the unmatched list.
 template <int STAGE>
 __global__ void __launch_bounds__(kThreads) assign_kernel(Dev d, int smem_matrix_floats) {
+    Span span((d.frame_id[0] & 7) * 5 + (STAGE == 1 ? 2 : 4));
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int scratch[kThreads / 32];
     __shared__ int s_rc;
@@ -537,7 +666,8 @@ __global__ void __launch_bounds__(kThreads) assign_kernel(Dev d, int smem_matrix
             __syncthreads();
             if (STAGE == 1) TRK_STAMP(2);
             update_matched(d, s, n_match, rows, C, d.MD, m_col,
-                           STAGE == 1 ? d.cost_update_max : d.reid_only_cost_max, STAGE == 1 ? d.maha_thr : 1e18);
+                           STAGE == 1 ? d.cost_update_max : d.reid_only_cost_max, STAGE == 1 ? d.maha_thr : 1e18,
+                           reinterpret_cast<double*>(smem_raw));          // the LSAP workspace is free again
         }
     } else if (M > 0) {                             // no detections left for these rows: all missed
         for (int r = tid; r < M; r += blockDim.x) {
@@ -668,6 +798,7 @@ struct b200_tracker {
     size_t in_bytes = 0, res_bytes = 0;
     int* in_ndet = nullptr; int* in_frame = nullptr; double* in_boxes = nullptr; double* in_confs = nullptr;
     float* in_embs = nullptr; int* dev_result = nullptr;
+    int ctl_threads = 256;              // CTA width of the per-stream control kernels (begin / assign)
     int cost_grid = 0, cost1_grid = 0;   // persistent CTAs of the cost kernels (resident CTAs per SM x SMs)
     size_t assign_smem = 0;
     int smem_matrix_floats = 0;
@@ -775,8 +906,13 @@ extern "C" int b200_tracker_create(b200_tracker** out, int n_streams, int max_tr
     }
     size_t mat = (size_t)Rm * Cm * sizeof(float);
     if (wb + mat > budget) mat = budget - wb;
+    // Small problems (the tracking shapes) keep the shared-memory footprint of the assignment kernels modest
+    // so that they can share an SM with resident ROI Align CTAs.
+    if (max_tracks <= 256 && max_dets <= 256 && mat > 32 * 1024) mat = 32 * 1024;
     t->smem_matrix_floats = (int)(mat / sizeof(float));
     t->assign_smem = wb + mat;
+    const size_t kf_scratch = (size_t)(trk::kThreads / 8) * 96 * sizeof(double);    // update_rows_t scratch
+    if (t->assign_smem < kf_scratch) t->assign_smem = kf_scratch;
     cudaFuncSetAttribute(trk::assign_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t->assign_smem);
     cudaFuncSetAttribute(trk::assign_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t->assign_smem);
     cudaFuncSetAttribute(trk::cost_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cost::smem_bytes(cost::kMaxBank));
@@ -795,11 +931,11 @@ extern "C" int b200_tracker_create(b200_tracker** out, int n_streams, int max_tr
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trk::cost_kernel<1>, cost::kThreads,
                                                       cost::smem_bytes(d.HIST));
         t->cost_grid = sms * (per_sm > 0 ? per_sm : 1);
-        cudaFuncSetAttribute(trk::cost1_sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)trk::cost1_smem_bytes(d.HIST));
         per_sm = 1;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trk::cost1_sparse_kernel, trk::kCost1Warps * 32,
-                                                      trk::cost1_smem_bytes(d.HIST));
+        if (d.HIST <= 32)
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trk::cost1_sparse32_kernel, trk::kCost1Warps * 32, 0);
+        else
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trk::cost1_sparse_kernel, trk::kCost1Warps * 32, 0);
         t->cost1_grid = sms * (per_sm > 0 ? per_sm : 1);
     }
     *out = t;
@@ -829,16 +965,17 @@ extern "C" int b200_tracker_step(b200_tracker* t, const int32_t* n_det, const do
     d.n_det = n_det; d.boxes = boxes; d.confs = confs; d.embs = embs; d.frame_id = frame_id; d.result = result;
     const size_t csm = cost::smem_bytes(d.HIST);
     const int cost_grid = t->cost_grid;
-    trk::begin_kernel<<<dim3(d.S, 2), trk::kThreads, 0, st>>>(d);
+    trk::begin_kernel<<<dim3(d.S, 2), t->ctl_threads, 0, st>>>(d);
     int rc = check_launch("trk begin_kernel");
     if (rc) return rc;
-    trk::cost1_sparse_kernel<<<t->cost1_grid, trk::kCost1Warps * 32, trk::cost1_smem_bytes(d.HIST), st>>>(d);
+    if (d.HIST <= 32) trk::cost1_sparse32_kernel<<<t->cost1_grid, trk::kCost1Warps * 32, 0, st>>>(d);
+    else trk::cost1_sparse_kernel<<<t->cost1_grid, trk::kCost1Warps * 32, 0, st>>>(d);
     if ((rc = check_launch("trk cost1_sparse_kernel"))) return rc;
-    trk::assign_kernel<1><<<d.S, trk::kThreads, t->assign_smem, st>>>(d, t->smem_matrix_floats);
+    trk::assign_kernel<1><<<d.S, t->ctl_threads, t->assign_smem, st>>>(d, t->smem_matrix_floats);
     if ((rc = check_launch("trk assign_kernel<1>"))) return rc;
     trk::cost_kernel<2><<<cost_grid, cost::kThreads, csm, st>>>(d);
     if ((rc = check_launch("trk cost_kernel<2>"))) return rc;
-    trk::assign_kernel<2><<<d.S, trk::kThreads, t->assign_smem, st>>>(d, t->smem_matrix_floats);
+    trk::assign_kernel<2><<<d.S, t->ctl_threads, t->assign_smem, st>>>(d, t->smem_matrix_floats);
     if ((rc = check_launch("trk assign_kernel<2>"))) return rc;
     return B200_OK;
 }
@@ -924,3 +1061,5 @@ extern "C" int b200_debug_timing(long long* out32) {
     return cudaMemcpyFromSymbol(out32, b200::trk::g_timing, sizeof(long long) * 32) == cudaSuccess ? 0 : -2;
 }
 #endif
+
+B200_SPAN_GETTER(b200_debug_spans_trk)
