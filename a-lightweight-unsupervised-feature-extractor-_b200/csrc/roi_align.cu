@@ -26,8 +26,6 @@
 namespace b200 {
 namespace {
 
-int g_roi_ctas_per_sm = 0;        // 0: one CTA per two tiles; > 0: persistent grid of that many CTAs per SM
-
 #ifndef B200_ROI_WARPS
 #define B200_ROI_WARPS 2
 #endif
@@ -194,15 +192,13 @@ roi_align_tile_kernel(const float* __restrict__ feat, int B, int C, int H, int W
     static_assert(PH <= 16 && PW <= 16, "one lane per output row/column");
     extern __shared__ __align__(16) float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // Warps are independent (no block-wide barriers) and persistent: warp w of the grid takes tiles
-    // w, w + #warps, ...  The bulk store of one tile is only waited for after the next tile's geometry.
+    // Warps are independent: no block-wide barriers anywhere below.
+    const long long wi = (long long)blockIdx.x * kWarpsPerCta + warp;
+    if (wi >= K * ctiles) return;
     const int span_slot = (int)((reinterpret_cast<uintptr_t>(rois) / (size_t)(K * 20)) & 7);   // debug: step index mod 8
     B200_SPAN_BEGIN(span_slot);
     float* sMain = smem + (size_t)warp * L::kFloatsPerWarp;   // V staging / big tables, later the output tile
     float* sTab = sMain + L::kMainFloats;
-    const long long total = K * ctiles, wstride = (long long)gridDim.x * kWarpsPerCta;
-    bool pending = false;                    // lane 0: a bulk store may still be reading sMain
-    for (long long wi = (long long)blockIdx.x * kWarpsPerCta + warp; wi < total; wi += wstride) {
     const long long k = wi / ctiles;
     const int c0 = (int)(wi % ctiles) * 32;
     const int cn = min(32, C - c0);
@@ -212,11 +208,6 @@ roi_align_tile_kernel(const float* __restrict__ feat, int B, int C, int H, int W
     axis_footprint(g.sh, g.bh, PH, g.gh, H, &ymin, &FY);
     axis_footprint(g.sw, g.bw, PW, g.gw, W, &xmin, &FX);
     if (g.b < 0 || g.b >= B || FY == 0 || FX == 0) FY = FX = 0;      // nothing sampled: zeros
-    if (pending) {                            // previous tile's output has left shared memory
-        if (lane == 0) bulk_store_wait_read();
-        pending = false;
-    }
-    __syncwarp();
     const bool staged = FY <= kFootCap && FX <= kFootCap;
     // Larger footprints keep their (bigger) weight tables in the output-tile area and read V
     // straight from global memory; only absurdly large ones take the per-bin path.
@@ -351,15 +342,14 @@ roi_align_tile_kernel(const float* __restrict__ feat, int B, int C, int H, int W
     if (bulk) {
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
         __syncwarp();
-        if (lane == 0) bulk_store_issue(gdst, sMain, bytes);
-        pending = true;
+        if (lane == 0) {
+            bulk_store_issue(gdst, sMain, bytes);
+            bulk_store_wait_read();           // shared memory must outlive the copy's read
+        }
     } else {
         __syncwarp();
         for (int i = lane; i < cn * NB; i += 32) gdst[i] = sMain[i];
-        __syncwarp();
     }
-    }   // persistent tile loop
-    if (pending && lane == 0) bulk_store_wait_read();     // shared memory must outlive the last copy
     B200_SPAN_END(span_slot);
 }
 
@@ -410,17 +400,7 @@ int launch_tile(const float* feat, int B, int C, int H, int W, const float* rois
     }
     const int ctiles = (C + 31) / 32;
     const long long warps = K * ctiles;
-    long long blocks = (warps + kWarpsPerCta - 1) / kWarpsPerCta;
-    if (g_roi_ctas_per_sm > 0) {             // persistent grid: a fixed number of CTAs per SM loop over the tiles
-        static int sms = 0;
-        if (!sms) {
-            int dev = 0;
-            B200_CUDA(cudaGetDevice(&dev));
-            B200_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        }
-        const long long cap = (long long)sms * g_roi_ctas_per_sm;
-        if (blocks > cap) blocks = cap;
-    }
+    const long long blocks = (warps + kWarpsPerCta - 1) / kWarpsPerCta;
     if (blocks > 0x7fffffffLL) return fail(B200_EINVAL, "roi_align: too many ROI tiles (%lld)", blocks);
     kern<<<(unsigned)blocks, kWarpsPerCta * 32, L::kBytesPerCta, st>>>(feat, B, C, H, W, rois, K, scale, sr,
                                                                      aligned, out, ctiles);
@@ -429,11 +409,6 @@ int launch_tile(const float* feat, int B, int C, int H, int W, const float* rois
 
 }  // namespace
 }  // namespace b200
-
-extern "C" int b200_roi_align_set_ctas_per_sm(int ctas_per_sm) {
-    b200::g_roi_ctas_per_sm = ctas_per_sm > 0 ? ctas_per_sm : 0;
-    return B200_OK;
-}
 
 extern "C" int b200_roi_align_fwd_f32(const float* feat, int layout, int B, int C, int H, int W,
                                       const float* rois, int64_t K, int PH, int PW, float spatial_scale,

@@ -157,6 +157,25 @@ def cpu_group_fps(warm, max_frames, budget_s, workers=None):
                       % (workers, os.cpu_count() or 0, n_tot, warm, out[0][4], ms_roi, ms_upd)}
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Libraries (NCCL) may print to stdout; the driver wants exactly one JSON line there.  Everything
+    else is sent to stderr and emit() writes the line to the real stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path (oracle port; the
     reference is pure Python and its arithmetic lives in torchvision / filterpy / scipy), on all
@@ -177,7 +196,7 @@ def run_reference(args):
         "cpu_baseline": cpu,
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 class StreamGroup:
@@ -284,7 +303,9 @@ def main():
     ap.add_argument("--streams", type=int, default=64, help="config-2 streams per GPU stepped together")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the single-stream side measurement")
     args = ap.parse_args()
+    quiet_stdout()
     if args.impl == "reference":
         return run_reference(args)
     if args.warmup < 3:
@@ -391,7 +412,7 @@ def main():
 
     extra = {}
     # ---- single-stream latency mode (one frame in flight; the shape the reference runs) --------------
-    if rank == 0:
+    if rank == 0 and not args.no_extra:
         try:
             K1 = 400
             g1 = StreamGroup(1, W + K1, 7000 + rank, dev)
@@ -439,7 +460,7 @@ def main():
             "cpu_baseline": cpu,
             "extra": extra,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -52,11 +52,6 @@ int64_t     b200_launch_count(void);
 int b200_roi_align_fwd_f32(const float* feat, int layout, int B, int C, int H, int W,
                            const float* rois, int64_t K, int PH, int PW, float spatial_scale,
                            int sampling_ratio, int aligned, float* out, void* stream);
-/* Launch tuning (process-wide): ctas_per_sm > 0 runs ROI Align as a persistent grid of that many
- * 64-thread CTAs per SM instead of one CTA per two tiles.  6 fills every SM; 5 leaves one CTA slot
- * (~11k registers, ~80 KB shared memory) per SM free so that small latency-bound kernels on another
- * stream (the association chain) can always be placed while ROI Align is running.  0 = default. */
-int b200_roi_align_set_ctas_per_sm(int ctas_per_sm);
 
 /* ---- appearance cost -----------------------------------------------------------
  * Replaces Tracking.build_C_app_topk (model/mainTracking.py:141-211).

@@ -72,5 +72,7 @@ if __name__ == "__main__":
                 case("c3", 256, 40, 40, 1280, 1280, 16, nhwc=nhwc, tv=tv, iters=10)
             if "c5" in which:
                 case("c5x64", 64, 34, 60, 1088, 1920, 128, nhwc=nhwc, tv=tv, iters=10)
+            if "g64" in which:      # the bench.py stream group: 64 maps x 64 boxes per launch
+                case("g64", 64, 40, 40, 1280, 1280, 64, nhwc=nhwc, tv=tv, iters=10)
             if "c2_7" in which:
                 case("c2_7x7", 1, 40, 40, 1280, 1280, 64, ps=(7, 7), nhwc=nhwc, tv=tv)
