@@ -113,6 +113,9 @@ __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ void cp_async4_s(unsigned smem_addr, const void* gsrc) {     // shared-space address
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(smem_addr), "l"(gsrc) : "memory");
+}
 __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.wait_all;\n" ::: "memory");
 }
@@ -199,8 +202,9 @@ roi_align_tile_kernel(const float* __restrict__ feat, int B, int C, int H, int W
     B200_SPAN_BEGIN(span_slot);
     float* sMain = smem + (size_t)warp * L::kFloatsPerWarp;   // V staging / big tables, later the output tile
     float* sTab = sMain + L::kMainFloats;
-    const long long k = wi / ctiles;
-    const int c0 = (int)(wi % ctiles) * 32;
+    const unsigned wi32 = (unsigned)wi;       // the launcher keeps the tile count below 2^31
+    const long long k = wi32 / (unsigned)ctiles;
+    const int c0 = (int)(wi32 % (unsigned)ctiles) * 32;
     const int cn = min(32, C - c0);
     const Geom g = roi_geometry(rois + 5 * k, scale, sr, aligned, PH, PW);
 
@@ -229,22 +233,30 @@ roi_align_tile_kernel(const float* __restrict__ feat, int B, int C, int H, int W
         while (nxp < FX) nxp <<= 1;                                  // lanes per row segment: 1, 2, 4, 8
         const int cper = 32 / (nxp > 32 ? 32 : nxp), xmask = nxp - 1;
         if (staged && FY) {
+            // running pointers / shared addresses: one 64-bit add and one 32-bit add per request
+            const unsigned sv = (unsigned)__cvta_generic_to_shared(sV);
             if (NHWC) {
-                const float* base = feat + (((size_t)g.b * H + ymin) * W + xmin) * C + c0 + lane;
+                const float* row = feat + (((size_t)g.b * H + ymin) * W + xmin) * C + c0 + lane;
+                unsigned dst = sv;
                 if (lane < cn)
-                    for (int r = 0; r < FY; ++r) {
-                        const float* src = base + (size_t)r * W * C;
-                        for (int x = 0; x < FX; ++x, src += C)
-                            cp_async4(sV + (r * FX + x) * 32 + ((lane + (x & xmask) * cper) & 31), src);
+                    for (int r = 0; r < FY; ++r, row += (size_t)W * C) {
+                        const float* src = row;
+                        for (int x = 0; x < FX; ++x, src += C, dst += 128)
+                            cp_async4_s(dst + 4u * ((lane + (x & xmask) * cper) & 31), src);
                     }
             } else {
                 const int xi = lane & xmask, cs = lane / nxp;        // lane = (channel sub-index, x)
-                const float* base = feat + (((size_t)g.b * C + c0) * H + ymin) * W + xmin + xi;
+                const size_t plane = (size_t)H * W, cstep = plane * cper;
+                const float* row = feat + (((size_t)g.b * C + c0 + cs) * H + ymin) * W + xmin + xi;
+                unsigned dst = sv + 128u * xi;
+                const int skew0 = cs + xi * cper;
                 if (xi < FX)
-                    for (int r = 0; r < FY; ++r)
-                        for (int c = cs; c < cn; c += cper)
-                            cp_async4(sV + (r * FX + xi) * 32 + ((c + xi * cper) & 31),
-                                      base + ((size_t)c * H + r) * W);
+                    for (int r = 0; r < FY; ++r, row += W, dst += 128u * FX) {
+                        const float* src = row;
+                        int sk = skew0;
+                        for (int c = cs; c < cn; c += cper, src += cstep, sk += cper)
+                            cp_async4_s(dst + 4u * (sk & 31), src);
+                    }
             }
         }
         // ---- dense separable weight tables over the footprint (lanes 0-15: y, 16-31: x) ------

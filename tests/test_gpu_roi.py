@@ -133,3 +133,17 @@ def test_roi_full_size_properties():
     sub_rois[:, 0] = np.searchsorted(maps, sub_rois[:, 0].astype(int))
     want = native.roi_align(sub_feat, sub_rois, (10, 10), 40 / 1280.0, 2, True)
     assert_close(ya[torch.from_numpy(pick).cuda()].cpu().numpy(), want, what="c3 subset")
+
+
+@pytest.mark.parametrize("nhwc", [False, True])
+def test_roi_huge_footprints_take_the_exact_fallbacks(nhwc):
+    """Whole-map boxes on a 150x140 map: the weight tables no longer fit next to the output tile, so the
+    kernel's per-bin path runs; medium boxes on the same map use the unstaged separable path."""
+    rng = np.random.default_rng(11)
+    feat = rng.standard_normal((1, 40, 150, 140), dtype=np.float32)
+    boxes = np.array([[0, 0, 140, 150], [3.5, 2.25, 138.0, 149.0], [10, 20, 60, 90], [100, 5, 139, 40],
+                      [50, 50, 58, 57], [-20, -30, 200, 220]], dtype=np.float64)
+    rois = np.concatenate([np.zeros((len(boxes), 1)), boxes], 1).astype(np.float32)
+    for ps, sr in [((10, 10), 2), ((7, 7), 2), ((10, 10), -1)]:
+        want = native.roi_align(feat, rois, ps, 1.0, sr, True)
+        assert_close(_run(feat, rois, ps, 1.0, sr, True, nhwc), want, rtol=1e-5, atol=2e-6, what="huge %s %s" % (ps, sr))

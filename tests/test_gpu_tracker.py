@@ -74,11 +74,16 @@ def _oracle_state(ref):
     dict(n=128, H=1088, W=1920, frames=12, scene=dict(drop=0.1), conf={}),                      # config 5 stream
     dict(n=24, H=640, W=640, frames=40, scene=dict(drop=0.5, churn=0.3, churn_every=5),
          conf=dict(lost_reid_after=2, max_age=6, hist_max=3, emb_top_k=2, conf_update_min=0.7)),
+    # banks deeper than 32 rows use the L2-resident variant of the stage-1 cost kernel
+    dict(n=20, H=640, W=640, frames=52, scene=dict(drop=0.15, churn=0.1, churn_every=11),
+         conf=dict(hist_max=44, emb_top_k=7, lost_reid_after=6, max_age=20)),
+    # a crowd: 256 detections per frame, births and misses every frame (BASELINE config 4 is 512)
+    dict(n=256, H=1280, W=1280, frames=5, scene=dict(drop=0.08), conf={}),
 ])
 def test_tracker_vs_oracle(case):
     cfg = dict(SHIPPED_CONF, **case["conf"])
     ref = tracker_ref.TrackerRef(cfg)
-    trk = Tracking(conf=cfg, max_tracks=768, max_dets=192)
+    trk = Tracking(conf=cfg, max_tracks=max(768, 3 * case["n"]), max_dets=max(192, case["n"]))
     scene = synth.Scene(7, case["n"], case["H"], case["W"], **case["scene"])
     saw_reid = 0
     for f in range(case["frames"]):
