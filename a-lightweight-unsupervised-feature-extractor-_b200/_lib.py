@@ -58,6 +58,7 @@ SIGNATURES = {
     "b200_tracker_step": (_I, [_P, _P, _P, _P, _P, _P, _P, _P]),
     "b200_tracker_step_host": (_I, [_P, _P, _P, _P, _P, _P, _P, _P]),
     "b200_tracker_export": (_I, [_P, _I] + [_P] * 14),
+    "b200_tracker_import": (_I, [_P, _I, _I] + [_P] * 12 + [_I, _P]),
 }
 
 

@@ -775,6 +775,19 @@ __global__ void export_kernel(Dev d, int s, int* ids, double* x, double* P, uint
     }
 }
 
+__global__ void import_finish_kernel(Dev d, int s, int n, int next_id) {
+    const size_t sb = (size_t)s * d.MT;
+    for (int i = threadIdx.x; i < d.MT; i += blockDim.x) {
+        if (i < n) { d.order[sb + i] = i; d.bank_head[sb + i] = 0; d.last_frame[sb + i] = 0; }
+        if (i < d.MT - n) d.free_list[sb + i] = d.MT - 1 - i;
+    }
+    if (threadIdx.x == 0) {
+        d.hdr[s * kHdr + H_NLIVE] = n;
+        d.hdr[s * kHdr + H_NEXT] = next_id;
+        d.hdr[s * kHdr + H_NFREE] = d.MT - n;
+    }
+}
+
 __global__ void reset_kernel(Dev d) {
     const int s = blockIdx.x;
     for (int i = threadIdx.x; i < d.MT; i += blockDim.x) d.free_list[(size_t)s * d.MT + i] = d.MT - 1 - i;
@@ -1061,5 +1074,33 @@ extern "C" int b200_debug_timing(long long* out32) {
     return cudaMemcpyFromSymbol(out32, b200::trk::g_timing, sizeof(long long) * 32) == cudaSuccess ? 0 : -2;
 }
 #endif
+
+extern "C" int b200_tracker_import(b200_tracker* t, int stream_idx, int n, const int32_t* ids, const double* x,
+                                   const double* P, const uint8_t* stage, const float* ema, const float* bank,
+                                   const int32_t* bank_len, const int32_t* miss, const int32_t* age,
+                                   const double* last_bbox, const double* last_conf, const double* last_cost,
+                                   int32_t next_id, void* stream) {
+    B200_REQUIRE(t, "tracker_import: null handle");
+    const trk::Dev& d = t->d;
+    B200_REQUIRE(stream_idx >= 0 && stream_idx < d.S, "tracker_import: stream %d out of range", stream_idx);
+    B200_REQUIRE(n >= 0 && n <= d.MT, "tracker_import: %d tracks exceed max_tracks %d", n, d.MT);
+    cudaStream_t st = as_stream(stream);
+    const size_t sb = (size_t)stream_idx * d.MT, H = d.HIST;
+    if (n > 0) {
+        B200_REQUIRE(ids && x && P && stage && ema && bank && bank_len && miss && age && last_bbox && last_conf && last_cost,
+                     "tracker_import: null array");
+#define PUSH(dst, src, T, per) B200_CUDA(cudaMemcpyAsync(dst + sb * (per), src, sizeof(T) * (per) * n, cudaMemcpyHostToDevice, st))
+        PUSH(d.tid, ids, int, 1); PUSH(d.kf_x, x, double, 8); PUSH(d.kf_P, P, double, 64); PUSH(d.kf_stage, stage, uint8_t, 1);
+        PUSH(d.ema, ema, float, 128); PUSH(d.bank, bank, float, H * 128); PUSH(d.bank_len, bank_len, int, 1);
+        PUSH(d.miss, miss, int, 1); PUSH(d.age, age, int, 1); PUSH(d.last_bbox, last_bbox, double, 4);
+        PUSH(d.last_conf, last_conf, double, 1); PUSH(d.last_cost, last_cost, double, 1);
+#undef PUSH
+    }
+    trk::import_finish_kernel<<<1, 256, 0, st>>>(d, stream_idx, n, next_id);
+    int rc = check_launch("trk import_finish_kernel");
+    if (rc) return rc;
+    B200_CUDA(cudaStreamSynchronize(st));          // the host arrays may be released after return
+    return B200_OK;
+}
 
 B200_SPAN_GETTER(b200_debug_spans_trk)

@@ -66,20 +66,46 @@ class MultiStreamTracker:
     """
 
     def __init__(self, n_streams: int, conf: Optional[Dict[str, Any]] = None, max_tracks: int = 256,
-                 max_dets: int = 128, device=None):
+                 max_dets: int = 128, device=None, auto_grow: bool = True):
         if not torch.cuda.is_available():
             raise _lib.B200Error("no CUDA device: this package has no CPU path")
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.conf = resolve_conf(SHIPPED_CONF if conf is None else conf)
-        self.S, self.max_tracks, self.max_dets = int(n_streams), int(max_tracks), int(max_dets)
+        self.S, self.auto_grow = int(n_streams), bool(auto_grow)
         self._h = ctypes.c_void_p()
+        self._create(int(max_tracks), int(max_dets))
+        self.n_live = np.zeros(self.S, dtype=np.int64)
+
+    def _create(self, max_tracks, max_dets):
+        h = ctypes.c_void_p()
         cc = _c_conf(self.conf)
         with torch.cuda.device(self.device):
-            _lib.check(_lib.lib().b200_tracker_create(ctypes.byref(self._h), self.S, self.max_tracks, self.max_dets,
-                                                      ctypes.byref(cc)))
-        self.stride = _lib.lib().b200_tracker_result_stride(self._h)
+            _lib.check(_lib.lib().b200_tracker_create(ctypes.byref(h), self.S, max_tracks, max_dets, ctypes.byref(cc)))
+        self._h, self.max_tracks, self.max_dets = h, max_tracks, max_dets
+        self.stride = _lib.lib().b200_tracker_result_stride(h)
         self._res = np.zeros((self.S, self.stride), dtype=np.int32)
-        self.n_live = np.zeros(self.S, dtype=np.int64)
+
+    def grow(self, max_tracks: Optional[int] = None, max_dets: Optional[int] = None):
+        """Migrates every stream's state into a handle with larger capacities (export -> create -> import)."""
+        snaps = [self.export(s) for s in range(self.S)]
+        old = self._h
+        self._create(max(self.max_tracks, int(max_tracks or 0)), max(self.max_dets, int(max_dets or 0)))
+        _lib.lib().b200_tracker_destroy(old)
+        for s, snap in enumerate(snaps):
+            self.import_state(s, snap)
+
+    def import_state(self, stream: int, snap: Dict[str, np.ndarray]):
+        """Inverse of ``export`` for one stream."""
+        n = len(snap["ids"])
+        c = lambda k, dt: np.ascontiguousarray(snap[k], dtype=dt)  # noqa: E731
+        arrs = [c("ids", np.int32), c("x", np.float64), c("P", np.float64), c("stage", np.uint8), c("ema", np.float32),
+                c("bank", np.float32), c("bank_len", np.int32), c("miss", np.int32), c("age", np.int32),
+                c("last_bbox", np.float64), c("last_conf", np.float64), c("last_cost", np.float64)]
+        with torch.cuda.device(self.device):
+            rc = _lib.lib().b200_tracker_import(self._h, int(stream), n, *[a.ctypes.data_as(ctypes.c_void_p) for a in arrs],
+                                                int(snap["next_id"]), _lib.stream_ptr(self.device))
+        _lib.check(rc)
+        self.n_live[stream] = n
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
@@ -104,9 +130,12 @@ class MultiStreamTracker:
         boxes = np.ascontiguousarray(boxes, dtype=np.float64).reshape(self.S, self.max_dets, 4)
         confs = np.ascontiguousarray(confs, dtype=np.float64).reshape(self.S, self.max_dets)
         embs = np.ascontiguousarray(embs, dtype=np.float32).reshape(self.S, self.max_dets, 128)
-        if (self.n_live + np.maximum(n_det, 0) > self.max_tracks).any():
-            raise _lib.B200Error("tracker capacity: live tracks + detections could exceed max_tracks=%d; "
-                                 "construct the tracker with a larger max_tracks" % self.max_tracks)
+        need = int((self.n_live + np.maximum(n_det, 0)).max())
+        if need > self.max_tracks:                     # the reference is unbounded: migrate to a larger handle
+            if not self.auto_grow:
+                raise _lib.B200Error("tracker capacity: live tracks + detections could exceed max_tracks=%d; "
+                                     "construct the tracker with a larger max_tracks" % self.max_tracks)
+            self.grow(max_tracks=max(need, 2 * self.max_tracks))
         p = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
         with torch.cuda.device(self.device):
             rc = _lib.lib().b200_tracker_step_host(self._h, p(n_det), p(boxes), p(confs), p(embs), p(frame_ids),
@@ -194,17 +223,18 @@ class Tracking:
 
     ``Tracking()`` reads ``model/conf/conf.yaml`` relative to the working directory exactly like the
     reference (:47); pass ``conf=`` (a tracker block) to skip the file.  ``max_tracks`` / ``max_dets``
-    size the device-side state (the reference is unbounded).
+    are initial capacities of the device-side state: like the reference the tracker is unbounded, a step
+    that would not fit migrates the state into a larger handle first (``auto_grow=False`` raises instead).
     """
 
     def __init__(self, conf_path: str = "model/conf/conf.yaml", *, conf: Optional[Dict[str, Any]] = None,
-                 max_tracks: int = 512, max_dets: int = 256, device=None):
+                 max_tracks: int = 512, max_dets: int = 256, device=None, auto_grow: bool = True):
         if conf is None:
             full = load_conf(conf_path)
             if "tracker" not in full:
                 raise KeyError("Missing 'tracker' section in YAML config.")
             conf = full["tracker"]
-        self._ms = MultiStreamTracker(1, conf, max_tracks, max_dets, device)
+        self._ms = MultiStreamTracker(1, conf, max_tracks, max_dets, device, auto_grow)
         c = self._ms.conf
         for k, v in c.items():                       # same attribute names as the reference (:55-96)
             setattr(self, "tau" if k == "app_tau" else k, v)
@@ -244,7 +274,12 @@ class Tracking:
         """Array form of ``update``: boxes [N,4] float64 xyxy, confs [N], embs [N,128] float32."""
         N = boxes.shape[0]
         if N > self._ms.max_dets:
-            raise ValueError("%d detections exceed max_dets=%d" % (N, self._ms.max_dets))
+            if not self._ms.auto_grow:
+                raise ValueError("%d detections exceed max_dets=%d" % (N, self._ms.max_dets))
+            self._ms.grow(max_dets=max(N, 2 * self._ms.max_dets))
+            MD = self._ms.max_dets
+            self._boxes, self._confs = np.zeros((1, MD, 4), np.float64), np.zeros((1, MD), np.float64)
+            self._embs = np.zeros((1, MD, 128), np.float32)
         self._boxes[0, :N] = boxes
         self._confs[0, :N] = confs
         self._embs[0, :N] = embs

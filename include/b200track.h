@@ -149,6 +149,15 @@ int  b200_tracker_export(b200_tracker* t, int stream_idx, int32_t* ids, double* 
                          int32_t* age, double* last_bbox, double* last_conf, double* last_cost,
                          int32_t* next_id, void* stream);
 
+/* Inverse of b200_tracker_export: replaces one stream's state by `n` tracks given in ascending track-id
+ * order (host arrays, same layouts as export).  Used to migrate state into a handle with larger
+ * capacities -- the reference's Tracking is unbounded -- and to restore a saved tracker. */
+int  b200_tracker_import(b200_tracker* t, int stream_idx, int n, const int32_t* ids, const double* x,
+                         const double* P, const uint8_t* stage, const float* ema, const float* bank,
+                         const int32_t* bank_len, const int32_t* miss, const int32_t* age,
+                         const double* last_bbox, const double* last_conf, const double* last_cost,
+                         int32_t next_id, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -140,11 +140,28 @@ def test_tracker_queries_and_errors():
         with open(os.path.join(d, "c.yaml"), "w") as fh:
             yaml.safe_dump({"model": {}}, fh)
         Tracking(os.path.join(d, "c.yaml"))
-    small = Tracking(conf=cfg, max_tracks=16, max_dets=16)
+    small = Tracking(conf=cfg, max_tracks=16, max_dets=16, auto_grow=False)
     sc = synth.Scene(0, 12, 640, 640)
     small.update(sc.step())
     with pytest.raises(_lib.B200Error):
         small.update(synth.Scene(1, 12, 640, 640).step())     # 12 live + 12 new could exceed 16
+
+
+def test_tracker_grows_like_the_unbounded_reference():
+    """Start far too small: every capacity is outgrown mid-sequence and the outputs still match the oracle."""
+    cfg = dict(SHIPPED_CONF, lost_reid_after=4, max_age=10)
+    ref = tracker_ref.TrackerRef(cfg)
+    trk = Tracking(conf=cfg, max_tracks=8, max_dets=4)
+    scene = synth.Scene(5, 30, 1280, 1280, drop=0.2, churn=0.2, churn_every=6)
+    for f in range(30):
+        obj = scene.step()
+        want = ref.update(obj)
+        got = trk.update(obj)
+        assert got[0] == want[0] and got[1] == want[1] and got[2] == want[2], "frame %d" % f
+    assert trk._ms.max_tracks >= len(ref.tracks) and trk._ms.max_dets >= 30
+    ids, st = _oracle_state(ref)
+    _compare_state(trk, ids, st, "after growth")
+    assert trk.next_id == ref.next_id
 
 
 def test_multistream_equals_independent_trackers():
