@@ -3,10 +3,10 @@
 //
 //   begin   (CTA / stream)  :467-487  empty-frame shortcut, predict_all, main/ReID row split,
 //                                     detection prep (unit embeddings, z, float32 boxes), gate prep
-//   cost<1> (grid)          :496-511  bank top-k appearance + box + conf terms + Mahalanobis gate,
-//                                     written once as C and C^T
+//   cost1   (grid)          :496-511  Mahalanobis gate first, then bank top-k appearance + box + conf terms
+//                                     for the surviving pairs, written once as C and C^T
 //   assign<1> (CTA / stream):514-538  LSAP + cost_max filter, update_matched, mark_missed
-//   cost<2> (grid)          :552-558  ReID-only appearance cost for long-lost rows x leftover dets
+//   cost2   (grid)          :552-558  ReID-only appearance cost for long-lost rows x leftover dets
 //   assign<2> (CTA / stream):560-610  LSAP, update_matched, mark_missed, births, purge, result table
 //
 // State never leaves the device.  Tracks live in fixed physical slots (banks are never moved);
@@ -236,28 +236,26 @@ __global__ void __launch_bounds__(kThreads) begin_kernel(Dev d) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// STAGE 1: rows_main x all detections, full cost + gate.  STAGE 2: rows_reid x leftover dets, C_app.
-template <int STAGE>
-__global__ void __launch_bounds__(cost::kThreads) cost_kernel(Dev d) {
+// ReID-only stage (:552-558): rows_reid x leftover detections, appearance cost only, dense tiles (bank and
+// 64 detection rows staged in shared memory, see assoc_cost.cuh).  Persistent CTAs over queued work items.
+__global__ void __launch_bounds__(cost::kThreads) cost2_kernel(Dev d) {
     Span span((d.frame_id[0] & 7) * 5 + 3);
     extern __shared__ __align__(16) float smem[];
     __shared__ int s_idx[cost::kTileN];
-    const int total = d.wcount[STAGE - 1];
-    const int2* work = STAGE == 1 ? d.work1 : d.work2;
+    const int total = d.wcount[1];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    for (int wi = blockIdx.x; wi < total; wi += gridDim.x) {        // persistent CTAs, uniform trip count
-        const int2 item = work[wi];
+    for (int wi = blockIdx.x; wi < total; wi += gridDim.x) {        // uniform trip count per CTA
+        const int2 item = d.work2[wi];
         const int s = item.x, r = item.y >> 6, j0 = (item.y & 63) * cost::kTileN;
-        const int* cnt = d.cnt + s * kHdr;
-        const int N = STAGE == 1 ? d.n_det[s] : cnt[C_NU];
+        const int N = d.cnt[s * kHdr + C_NU];
         const size_t sb = (size_t)s * d.MT, db = (size_t)s * d.MD;
-        const size_t slot = sb + (STAGE == 1 ? d.rows_main : d.rows_reid)[sb + r];
+        const size_t slot = sb + d.rows_reid[sb + r];
         int T = d.bank_len[slot];
         const float* rows = d.bank + slot * d.HIST * cost::kD;
         if (T <= 0) { rows = d.ema + slot * cost::kD; T = 1; }        // :180-182 fallback to the EMA
-        if (tid < cost::kTileN) {                                      // stage 2 gathers leftover detections
+        if (tid < cost::kTileN) {                                      // leftover detections are gathered through ud1
             const int j = j0 + tid;
-            s_idx[tid] = j < N ? (STAGE == 1 ? j : d.ud1[db + j]) : 0;
+            s_idx[tid] = j < N ? d.ud1[db + j] : 0;
         }
         __syncthreads();
         const int tc = cost::bank_cap(T);
@@ -277,20 +275,10 @@ __global__ void __launch_bounds__(cost::kThreads) cost_kernel(Dev d) {
         __syncthreads();
         const float c_app = cost::sims_and_topk(sBank, sDet, sSim, tc, T, d.topk, true);   // ends with a barrier
         const int j = j0 + tid;
-        if (tid >= cost::kTileN || j >= N) continue;
-        if (STAGE == 2) {
+        if (tid < cost::kTileN && j < N) {
             d.C2[(sb + r) * d.MD + j] = c_app;
             d.C2T[(db + j) * d.MT + r] = c_app;
-            continue;
         }
-        const cost::PairCost pc = cost::pair_cost(d.prev_boxf + slot * 4, d.det_boxf + (db + j) * 4,
-                                                  d.prev_conff[slot], d.det_conff[db + j], d.pw, c_app);
-        float total_c = pc.total;
-        const double d2 = kf::gate_d2(d.gate_SI + slot * 16, d.kf_x + slot * 8, d.kf_stage[slot],
-                                      d.det_z + (db + j) * 4);
-        if (d2 > d.maha_thr) total_c = 1e9f;                                // :335-336
-        d.C1[(sb + r) * d.MD + j] = total_c;
-        d.C1T[(db + j) * d.MT + r] = total_c;
     }
 }
 
@@ -928,8 +916,7 @@ extern "C" int b200_tracker_create(b200_tracker** out, int n_streams, int max_tr
     if (t->assign_smem < kf_scratch) t->assign_smem = kf_scratch;
     cudaFuncSetAttribute(trk::assign_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t->assign_smem);
     cudaFuncSetAttribute(trk::assign_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t->assign_smem);
-    cudaFuncSetAttribute(trk::cost_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cost::smem_bytes(cost::kMaxBank));
-    cudaFuncSetAttribute(trk::cost_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cost::smem_bytes(cost::kMaxBank));
+    cudaFuncSetAttribute(trk::cost2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cost::smem_bytes(cost::kMaxBank));
     trk::reset_kernel<<<n_streams, 128>>>(d);
     e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
@@ -941,7 +928,7 @@ extern "C" int b200_tracker_create(b200_tracker** out, int n_streams, int max_tr
         int per_sm = 1, sms = kSMs, devid = 0;
         cudaGetDevice(&devid);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, devid);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trk::cost_kernel<1>, cost::kThreads,
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trk::cost2_kernel, cost::kThreads,
                                                       cost::smem_bytes(d.HIST));
         t->cost_grid = sms * (per_sm > 0 ? per_sm : 1);
         per_sm = 1;
@@ -986,8 +973,8 @@ extern "C" int b200_tracker_step(b200_tracker* t, const int32_t* n_det, const do
     if ((rc = check_launch("trk cost1_sparse_kernel"))) return rc;
     trk::assign_kernel<1><<<d.S, t->ctl_threads, t->assign_smem, st>>>(d, t->smem_matrix_floats);
     if ((rc = check_launch("trk assign_kernel<1>"))) return rc;
-    trk::cost_kernel<2><<<cost_grid, cost::kThreads, csm, st>>>(d);
-    if ((rc = check_launch("trk cost_kernel<2>"))) return rc;
+    trk::cost2_kernel<<<cost_grid, cost::kThreads, csm, st>>>(d);
+    if ((rc = check_launch("trk cost2_kernel"))) return rc;
     trk::assign_kernel<2><<<d.S, t->ctl_threads, t->assign_smem, st>>>(d, t->smem_matrix_floats);
     if ((rc = check_launch("trk assign_kernel<2>"))) return rc;
     return B200_OK;
