@@ -199,3 +199,33 @@ def test_multistream_equals_independent_trackers():
             else:
                 assert got[0] == want[s][0] and got[1] == want[s][1] and got[2] == want[s][2], (f, s)
             assert int(res[s, 3]) == len(singles[s].tracks) and int(res[s, 4]) == singles[s].next_id
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_tracker_fuzz_vs_oracle(seed):
+    """Randomised differential test: random hyper-parameters (including degenerate ones: one-row banks,
+    top-1, immediate purge, ReID stage almost always on), random scene dynamics, empty and idle frames."""
+    rng = np.random.default_rng(1000 + seed)
+    cfg = dict(SHIPPED_CONF,
+               hist_max=int(rng.choice([1, 2, 5, 30, 33, 64])), emb_top_k=int(rng.choice([1, 3, 5, 9])),
+               max_age=int(rng.choice([0, 1, 5, 40])), lost_reid_after=int(rng.choice([0, 1, 3, 50])),
+               init_conf_min=float(rng.choice([0.0, 0.5, 0.7])), conf_update_min=float(rng.choice([0.0, 0.55, 0.8])),
+               cost_max=float(rng.choice([50.0, 1.0, 0.3])), cost_update_max=float(rng.choice([30.0, 0.5])),
+               maha_thr=float(rng.choice([9.49, 2.0, 1e6])), reid_only_cost_max=float(rng.choice([0.4, 0.05, 2.0])),
+               ema_alpha=float(rng.choice([0.9, 0.5, 0.0])), w_bbox=float(rng.choice([0.3, 0.0, 2.0])))
+    n = int(rng.integers(1, 40))
+    scene = synth.Scene(int(rng.integers(1 << 30)), n, 720, 1280, drop=float(rng.choice([0.0, 0.2, 0.6])),
+                        churn=float(rng.choice([0.0, 0.3])), churn_every=int(rng.integers(2, 9)),
+                        noise=float(rng.choice([0.05, 0.5])))
+    ref = tracker_ref.TrackerRef(cfg)
+    trk = Tracking(conf=cfg, max_tracks=16, max_dets=8)            # also exercises growth
+    for f in range(36):
+        obj = scene.step()
+        if rng.uniform() < 0.08:
+            obj["embs"], obj["bboxes"], obj["confs"] = [], [], []
+        want = ref.update(obj)
+        got = trk.update(obj)
+        assert got[0] == want[0] and got[1] == want[1] and got[2] == want[2], "seed %d frame %d cfg %s" % (seed, f, cfg)
+    ids, st = _oracle_state(ref)
+    _compare_state(trk, ids, st, "seed %d" % seed)
+    assert trk.next_id == ref.next_id
