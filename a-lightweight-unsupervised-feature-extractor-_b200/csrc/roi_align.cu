@@ -21,6 +21,8 @@
 // instantiation, take exact but slower paths.  Sample coordinates are evaluated with
 // the same operation order as torchvision and without FMA contraction so that cell
 // selection agrees with the CPU op.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace b200 {
@@ -32,6 +34,14 @@ namespace {
 constexpr int kWarpsPerCta = B200_ROI_WARPS;
 constexpr int kFootCap = 8;     // max footprint rows / cols on the staged path (<= 64 cells x 32 ch = 8 KB)
 constexpr int kCellCap = kFootCap * kFootCap;
+
+// Element type of the map and of the output: float, or __half storage with float arithmetic.
+template <typename T> __device__ __forceinline__ float ldf(const T* p);
+template <> __device__ __forceinline__ float ldf<float>(const float* p) { return __ldg(p); }
+template <> __device__ __forceinline__ float ldf<__half>(const __half* p) { return __half2float(__ldg(p)); }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ __half from_f<__half>(float v) { return __float2half_rn(v); }
 
 struct Geom {
     float sw, sh, bw, bh, count;
@@ -116,13 +126,16 @@ __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
 __device__ __forceinline__ void cp_async4_s(unsigned smem_addr, const void* gsrc) {     // shared-space address
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(smem_addr), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ void sts_f32(unsigned smem_addr, float v) {
+    asm volatile("st.shared.f32 [%0], %1;\n" ::"r"(smem_addr), "f"(v) : "memory");
+}
 __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.wait_all;\n" ::: "memory");
 }
 
 // One bulk async copy shared -> global issued by a single lane (TMA engine, SASS UBLKCP).  The
 // source tile may be overwritten only after bulk_store_wait_read() on the issuing lane.
-__device__ __forceinline__ void bulk_store_issue(float* gdst, const float* ssrc, unsigned bytes) {
+__device__ __forceinline__ void bulk_store_issue(void* gdst, const void* ssrc, unsigned bytes) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(ssrc);
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gdst), "r"(s),
                  "r"(bytes)
@@ -185,11 +198,12 @@ __device__ __forceinline__ void separable_accumulate(float (&acc)[PH][PW], const
 #define B200_ROI_MIN_CTAS 6
 #endif
 
-template <int PH, int PW, bool NHWC>
+template <int PH, int PW, bool NHWC, typename T>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, (B200_ROI_MIN_CTAS * 2 + kWarpsPerCta - 1) / kWarpsPerCta)
-roi_align_tile_kernel(const float* __restrict__ feat, int B, int C, int H, int W,
+roi_align_tile_kernel(const T* __restrict__ feat, int B, int C, int H, int W,
                       const float* __restrict__ rois, long long K, float scale, int sr, int aligned,
-                      float* __restrict__ out, int ctiles) {
+                      T* __restrict__ out, int ctiles) {
+    constexpr bool kF32 = sizeof(T) == 4;
     using L = TileSmem<PH, PW>;
     constexpr int PHP = L::kPHP, PWP = L::kPWP, NB = PH * PW;
     static_assert(PH <= 16 && PW <= 16, "one lane per output row/column");
@@ -236,26 +250,33 @@ roi_align_tile_kernel(const float* __restrict__ feat, int B, int C, int H, int W
             // running pointers / shared addresses: one 64-bit add and one 32-bit add per request
             const unsigned sv = (unsigned)__cvta_generic_to_shared(sV);
             if (NHWC) {
-                const float* row = feat + (((size_t)g.b * H + ymin) * W + xmin) * C + c0 + lane;
+                const T* row = feat + (((size_t)g.b * H + ymin) * W + xmin) * C + c0 + lane;
                 unsigned dst = sv;
                 if (lane < cn)
                     for (int r = 0; r < FY; ++r, row += (size_t)W * C) {
-                        const float* src = row;
-                        for (int x = 0; x < FX; ++x, src += C, dst += 128)
-                            cp_async4_s(dst + 4u * ((lane + (x & xmask) * cper) & 31), src);
+                        const T* src = row;
+#pragma unroll 4
+                        for (int x = 0; x < FX; ++x, src += C, dst += 128) {
+                            const unsigned a = dst + 4u * ((lane + (x & xmask) * cper) & 31);
+                            if (kF32) cp_async4_s(a, src);
+                            else sts_f32(a, ldf<T>(src));          // 16-bit storage: converting load
+                        }
                     }
             } else {
                 const int xi = lane & xmask, cs = lane / nxp;        // lane = (channel sub-index, x)
                 const size_t plane = (size_t)H * W, cstep = plane * cper;
-                const float* row = feat + (((size_t)g.b * C + c0 + cs) * H + ymin) * W + xmin + xi;
+                const T* row = feat + (((size_t)g.b * C + c0 + cs) * H + ymin) * W + xmin + xi;
                 unsigned dst = sv + 128u * xi;
                 const int skew0 = cs + xi * cper;
                 if (xi < FX)
                     for (int r = 0; r < FY; ++r, row += W, dst += 128u * FX) {
-                        const float* src = row;
+                        const T* src = row;
                         int sk = skew0;
-                        for (int c = cs; c < cn; c += cper, src += cstep, sk += cper)
-                            cp_async4_s(dst + 4u * (sk & 31), src);
+#pragma unroll 4
+                        for (int c = cs; c < cn; c += cper, src += cstep, sk += cper) {
+                            if (kF32) cp_async4_s(dst + 4u * (sk & 31), src);
+                            else sts_f32(dst + 4u * (sk & 31), ldf<T>(src));
+                        }
                     }
             }
         }
@@ -292,18 +313,18 @@ roi_align_tile_kernel(const float* __restrict__ feat, int B, int C, int H, int W
         } else {
             __syncwarp();
             const int cl = lane < cn ? lane : 0;                     // idle lanes re-read channel 0
-            const float* base = NHWC ? feat + (((size_t)g.b * H + ymin) * W + xmin) * C + c0 + cl
-                                     : feat + (((size_t)g.b * C + c0 + cl) * H + ymin) * W + xmin;
+            const T* base = NHWC ? feat + (((size_t)g.b * H + ymin) * W + xmin) * C + c0 + cl
+                                 : feat + (((size_t)g.b * C + c0 + cl) * H + ymin) * W + xmin;
             const size_t rs = NHWC ? (size_t)W * C : (size_t)W, xs = NHWC ? (size_t)C : 1;
             separable_accumulate<PH, PW>(acc, sWy, sWx, FY, FX,
-                                         [&](int r, int x) { return __ldg(base + r * rs + x * xs); });
+                                         [&](int r, int x) { return ldf<T>(base + r * rs + x * xs); });
         }
         __syncwarp();                          // every lane is done with V / the tables in sMain
     } else {
         // ---- exact last-resort path: per-bin direct 4-tap sampling ------------------------------
         const size_t ps = NHWC ? (size_t)C : 1;
-        const float* base = feat + (NHWC ? (size_t)g.b * H * W * C + c0 + lane
-                                         : ((size_t)g.b * C + c0 + lane) * H * W);
+        const T* base = feat + (NHWC ? (size_t)g.b * H * W * C + c0 + lane
+                                     : ((size_t)g.b * C + c0 + lane) * H * W);
 #pragma unroll 1
         for (int bin = 0; bin < NB; ++bin) {
             const int a = bin / PW, b = bin - a * PW;
@@ -313,10 +334,10 @@ roi_align_tile_kernel(const float* __restrict__ feat, int B, int C, int H, int W
                 for (int ix = 0; ix < g.gw; ++ix) {
                     const Tap tx = make_tap(sample_pos(g.sw, b, g.bw, ix, g.gw), W);
                     if (ty.valid && tx.valid && lane < cn) {
-                        const float v1 = __ldg(base + ((size_t)ty.lo * W + tx.lo) * ps);
-                        const float v2 = __ldg(base + ((size_t)ty.lo * W + tx.hi) * ps);
-                        const float v3 = __ldg(base + ((size_t)ty.hi * W + tx.lo) * ps);
-                        const float v4 = __ldg(base + ((size_t)ty.hi * W + tx.hi) * ps);
+                        const float v1 = ldf<T>(base + ((size_t)ty.lo * W + tx.lo) * ps);
+                        const float v2 = ldf<T>(base + ((size_t)ty.lo * W + tx.hi) * ps);
+                        const float v3 = ldf<T>(base + ((size_t)ty.hi * W + tx.lo) * ps);
+                        const float v4 = ldf<T>(base + ((size_t)ty.hi * W + tx.hi) * ps);
                         s += ty.wlo * tx.wlo * v1 + ty.wlo * tx.whi * v2 + ty.whi * tx.wlo * v3 +
                              ty.whi * tx.whi * v4;
                     }
@@ -335,21 +356,34 @@ roi_align_tile_kernel(const float* __restrict__ feat, int B, int C, int H, int W
     // ---- mean over samples (1/count is exact for the power-of-two counts of sampling_ratio 1, 2, 4;
     // otherwise within 1 ulp of the reference's division), output tile to shared memory ----------
     const float inv = __fdiv_rn(1.0f, g.count);
-    float* myrow = sMain + lane * NB;
-    if ((NB & 3) == 0) {
+    if (kF32) {
+        float* myrow = sMain + lane * NB;
+        if ((NB & 3) == 0) {
 #pragma unroll
-        for (int q = 0; q < NB / 4; ++q)
-            reinterpret_cast<float4*>(myrow)[q] =
-                make_float4(acc[(4 * q) / PW][(4 * q) % PW] * inv, acc[(4 * q + 1) / PW][(4 * q + 1) % PW] * inv,
-                            acc[(4 * q + 2) / PW][(4 * q + 2) % PW] * inv, acc[(4 * q + 3) / PW][(4 * q + 3) % PW] * inv);
-    } else {
+            for (int q = 0; q < NB / 4; ++q)
+                reinterpret_cast<float4*>(myrow)[q] =
+                    make_float4(acc[(4 * q) / PW][(4 * q) % PW] * inv, acc[(4 * q + 1) / PW][(4 * q + 1) % PW] * inv,
+                                acc[(4 * q + 2) / PW][(4 * q + 2) % PW] * inv, acc[(4 * q + 3) / PW][(4 * q + 3) % PW] * inv);
+        } else {
 #pragma unroll
-        for (int i = 0; i < NB; ++i) myrow[i] = acc[i / PW][i % PW] * inv;
+            for (int i = 0; i < NB; ++i) myrow[i] = acc[i / PW][i % PW] * inv;
+        }
+    } else {                                   // 16-bit output: round once, after the fp32 mean
+        __half* myrow = reinterpret_cast<__half*>(sMain) + lane * NB;
+        if ((NB & 1) == 0) {
+#pragma unroll
+            for (int q = 0; q < NB / 2; ++q)
+                reinterpret_cast<__half2*>(myrow)[q] = __floats2half2_rn(acc[(2 * q) / PW][(2 * q) % PW] * inv,
+                                                                         acc[(2 * q + 1) / PW][(2 * q + 1) % PW] * inv);
+        } else {
+#pragma unroll
+            for (int i = 0; i < NB; ++i) myrow[i] = __float2half_rn(acc[i / PW][i % PW] * inv);
+        }
     }
 
     // ---- one contiguous [cn][PH*PW] chunk of the NCHW output -----------------------------------
-    float* gdst = out + ((size_t)k * C + c0) * NB;
-    const unsigned bytes = (unsigned)cn * NB * 4u;
+    T* gdst = out + ((size_t)k * C + c0) * NB;
+    const unsigned bytes = (unsigned)cn * NB * (unsigned)sizeof(T);
     const bool bulk = ((reinterpret_cast<uintptr_t>(gdst) & 15) == 0) && (bytes & 15u) == 0;
     if (bulk) {
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
@@ -360,17 +394,18 @@ roi_align_tile_kernel(const float* __restrict__ feat, int B, int C, int H, int W
         }
     } else {
         __syncwarp();
-        for (int i = lane; i < cn * NB; i += 32) gdst[i] = sMain[i];
+        const T* tile = reinterpret_cast<const T*>(sMain);
+        for (int i = lane; i < cn * NB; i += 32) gdst[i] = tile[i];
     }
     B200_SPAN_END(span_slot);
 }
 
 // Any output size / any parameters: one thread per output element, direct sampling.
-template <bool NHWC>
+template <bool NHWC, typename T>
 __global__ void __launch_bounds__(256)
-roi_align_generic_kernel(const float* __restrict__ feat, int B, int C, int H, int W,
+roi_align_generic_kernel(const T* __restrict__ feat, int B, int C, int H, int W,
                          const float* __restrict__ rois, long long total, int PH, int PW, float scale,
-                         int sr, int aligned, float* __restrict__ out) {
+                         int sr, int aligned, T* __restrict__ out) {
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
         const int pw = (int)(idx % PW), ph = (int)((idx / PW) % PH);
@@ -380,32 +415,32 @@ roi_align_generic_kernel(const float* __restrict__ feat, int B, int C, int H, in
         float s = 0.0f;
         if (g.b >= 0 && g.b < B) {
             const size_t ps = NHWC ? (size_t)C : 1;
-            const float* base = feat + (NHWC ? (size_t)g.b * H * W * C + c : ((size_t)g.b * C + c) * H * W);
+            const T* base = feat + (NHWC ? (size_t)g.b * H * W * C + c : ((size_t)g.b * C + c) * H * W);
             for (int iy = 0; iy < g.gh; ++iy) {
                 const Tap ty = make_tap(sample_pos(g.sh, ph, g.bh, iy, g.gh), H);
                 for (int ix = 0; ix < g.gw; ++ix) {
                     const Tap tx = make_tap(sample_pos(g.sw, pw, g.bw, ix, g.gw), W);
                     if (ty.valid && tx.valid) {
-                        const float v1 = __ldg(base + ((size_t)ty.lo * W + tx.lo) * ps);
-                        const float v2 = __ldg(base + ((size_t)ty.lo * W + tx.hi) * ps);
-                        const float v3 = __ldg(base + ((size_t)ty.hi * W + tx.lo) * ps);
-                        const float v4 = __ldg(base + ((size_t)ty.hi * W + tx.hi) * ps);
+                        const float v1 = ldf<T>(base + ((size_t)ty.lo * W + tx.lo) * ps);
+                        const float v2 = ldf<T>(base + ((size_t)ty.lo * W + tx.hi) * ps);
+                        const float v3 = ldf<T>(base + ((size_t)ty.hi * W + tx.lo) * ps);
+                        const float v4 = ldf<T>(base + ((size_t)ty.hi * W + tx.hi) * ps);
                         s += ty.wlo * tx.wlo * v1 + ty.wlo * tx.whi * v2 + ty.whi * tx.wlo * v3 +
                              ty.whi * tx.whi * v4;
                     }
                 }
             }
         }
-        out[idx] = __fdiv_rn(s, g.count);
+        out[idx] = from_f<T>(__fdiv_rn(s, g.count));
     }
 }
 
-template <int PH, int PW, bool NHWC>
-int launch_tile(const float* feat, int B, int C, int H, int W, const float* rois, long long K,
-                float scale, int sr, int aligned, float* out, cudaStream_t st) {
+template <int PH, int PW, bool NHWC, typename T>
+int launch_tile(const T* feat, int B, int C, int H, int W, const float* rois, long long K,
+                float scale, int sr, int aligned, T* out, cudaStream_t st) {
     using L = TileSmem<PH, PW>;
     static bool configured = false;          // per instantiation; the attribute is idempotent
-    auto kern = roi_align_tile_kernel<PH, PW, NHWC>;
+    auto kern = roi_align_tile_kernel<PH, PW, NHWC, T>;
     if (!configured) {
         B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kBytesPerCta));
         configured = true;
@@ -419,13 +454,9 @@ int launch_tile(const float* feat, int B, int C, int H, int W, const float* rois
     return check_launch("roi_align_tile_kernel");
 }
 
-}  // namespace
-}  // namespace b200
-
-extern "C" int b200_roi_align_fwd_f32(const float* feat, int layout, int B, int C, int H, int W,
-                                      const float* rois, int64_t K, int PH, int PW, float spatial_scale,
-                                      int sampling_ratio, int aligned, float* out, void* stream) {
-    using namespace b200;
+template <typename T>
+int roi_align_dispatch(const T* feat, int layout, int B, int C, int H, int W, const float* rois, int64_t K, int PH,
+                       int PW, float spatial_scale, int sampling_ratio, int aligned, T* out, void* stream) {
     B200_REQUIRE(layout == B200_LAYOUT_NCHW || layout == B200_LAYOUT_NHWC, "roi_align: bad layout %d", layout);
     B200_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, "roi_align: bad feature shape [%d,%d,%d,%d]", B, C, H, W);
     B200_REQUIRE(PH > 0 && PW > 0, "roi_align: bad output size (%d,%d)", PH, PW);
@@ -434,12 +465,12 @@ extern "C" int b200_roi_align_fwd_f32(const float* feat, int layout, int B, int 
     B200_REQUIRE(feat && rois && out, "roi_align: null pointer");
     cudaStream_t st = as_stream(stream);
     const bool nhwc = layout == B200_LAYOUT_NHWC;
-#define B200_TILE(ph, pw)                                                                              \
-    if (PH == ph && PW == pw)                                                                          \
-        return nhwc ? launch_tile<ph, pw, true>(feat, B, C, H, W, rois, K, spatial_scale, sampling_ratio, \
-                                                aligned, out, st)                                      \
-                    : launch_tile<ph, pw, false>(feat, B, C, H, W, rois, K, spatial_scale,             \
-                                                 sampling_ratio, aligned, out, st);
+#define B200_TILE(ph, pw)                                                                                  \
+    if (PH == ph && PW == pw)                                                                              \
+        return nhwc ? launch_tile<ph, pw, true, T>(feat, B, C, H, W, rois, K, spatial_scale, sampling_ratio, \
+                                                   aligned, out, st)                                       \
+                    : launch_tile<ph, pw, false, T>(feat, B, C, H, W, rois, K, spatial_scale,              \
+                                                    sampling_ratio, aligned, out, st);
     B200_TILE(10, 10)
     B200_TILE(7, 7)
 #undef B200_TILE
@@ -447,12 +478,29 @@ extern "C" int b200_roi_align_fwd_f32(const float* feat, int layout, int B, int 
     const long long want = (total + 255) / 256;
     const unsigned blocks = (unsigned)(want < (long long)kSMs * 32 ? want : (long long)kSMs * 32);
     if (nhwc)
-        roi_align_generic_kernel<true><<<blocks, 256, 0, st>>>(feat, B, C, H, W, rois, total, PH, PW,
-                                                               spatial_scale, sampling_ratio, aligned, out);
+        roi_align_generic_kernel<true, T><<<blocks, 256, 0, st>>>(feat, B, C, H, W, rois, total, PH, PW,
+                                                                  spatial_scale, sampling_ratio, aligned, out);
     else
-        roi_align_generic_kernel<false><<<blocks, 256, 0, st>>>(feat, B, C, H, W, rois, total, PH, PW,
-                                                                spatial_scale, sampling_ratio, aligned, out);
+        roi_align_generic_kernel<false, T><<<blocks, 256, 0, st>>>(feat, B, C, H, W, rois, total, PH, PW,
+                                                                   spatial_scale, sampling_ratio, aligned, out);
     return check_launch("roi_align_generic_kernel");
+}
+
+}  // namespace
+}  // namespace b200
+
+extern "C" int b200_roi_align_fwd_f32(const float* feat, int layout, int B, int C, int H, int W,
+                                      const float* rois, int64_t K, int PH, int PW, float spatial_scale,
+                                      int sampling_ratio, int aligned, float* out, void* stream) {
+    return b200::roi_align_dispatch<float>(feat, layout, B, C, H, W, rois, K, PH, PW, spatial_scale, sampling_ratio,
+                                           aligned, out, stream);
+}
+
+extern "C" int b200_roi_align_fwd_f16(const void* feat, int layout, int B, int C, int H, int W,
+                                      const float* rois, int64_t K, int PH, int PW, float spatial_scale,
+                                      int sampling_ratio, int aligned, void* out, void* stream) {
+    return b200::roi_align_dispatch<__half>(static_cast<const __half*>(feat), layout, B, C, H, W, rois, K, PH, PW,
+                                            spatial_scale, sampling_ratio, aligned, static_cast<__half*>(out), stream);
 }
 
 B200_SPAN_GETTER(b200_debug_spans_roi)

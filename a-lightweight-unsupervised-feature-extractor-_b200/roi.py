@@ -35,16 +35,19 @@ def _boxes_to_rois(boxes, device):
 def roi_align(input: torch.Tensor, boxes: Union[torch.Tensor, Sequence[torch.Tensor]],
               output_size: Union[int, Tuple[int, int]], spatial_scale: float = 1.0,
               sampling_ratio: int = -1, aligned: bool = False) -> torch.Tensor:
-    """Drop-in for ``torchvision.ops.roi_align`` (forward only, float32 maps).
+    """Drop-in for ``torchvision.ops.roi_align`` (forward only).
 
-    ``input`` may be contiguous NCHW or ``torch.channels_last``; both are read in place.
-    Returns a new contiguous ``[K, C, PH, PW]`` float32 tensor on ``input``'s device.
+    ``input`` may be contiguous NCHW or ``torch.channels_last``; both are read in place.  float32 maps are
+    the parity contract; float16 maps (what the reference's live CUDA path feeds, tracking.py:177-178) are
+    read as stored, sampled with float32 arithmetic and rounded to float16 once at the end.  Boxes of any
+    float dtype are used at float32 (half-rounded boxes keep their half-rounded values).
+    Returns a new contiguous ``[K, C, PH, PW]`` tensor of ``input``'s dtype on ``input``'s device.
     """
     _lib.require_cuda(input, "input")
     if input.dim() != 4:
         raise ValueError("input must be [B, C, H, W]")
-    if input.dtype != torch.float32:
-        raise TypeError("roi_align: float32 feature maps only (got %s)" % input.dtype)
+    if input.dtype not in (torch.float32, torch.float16):
+        raise TypeError("roi_align: float32 or float16 feature maps only (got %s)" % input.dtype)
     B, C, H, W = input.shape
     if input.is_contiguous():
         layout = _lib.LAYOUT_NCHW
@@ -55,9 +58,10 @@ def roi_align(input: torch.Tensor, boxes: Union[torch.Tensor, Sequence[torch.Ten
     rois = _boxes_to_rois(boxes, input.device)
     PH, PW = _pair(output_size)
     K = rois.size(0)
-    out = torch.empty((K, C, PH, PW), dtype=torch.float32, device=input.device)
+    out = torch.empty((K, C, PH, PW), dtype=input.dtype, device=input.device)
+    fn = _lib.lib().b200_roi_align_fwd_f32 if input.dtype == torch.float32 else _lib.lib().b200_roi_align_fwd_f16
     with torch.cuda.device(input.device):
-        rc = _lib.lib().b200_roi_align_fwd_f32(
+        rc = fn(
             _lib.ptr(input), layout, B, C, H, W, _lib.ptr(rois), K, PH, PW, float(spatial_scale),
             int(sampling_ratio), int(bool(aligned)), _lib.ptr(out), _lib.stream_ptr(input.device))
     _lib.check(rc)

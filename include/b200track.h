@@ -53,6 +53,13 @@ int b200_roi_align_fwd_f32(const float* feat, int layout, int B, int C, int H, i
                            const float* rois, int64_t K, int PH, int PW, float spatial_scale,
                            int sampling_ratio, int aligned, float* out, void* stream);
 
+/* Same operator for float16 storage (the reference's live CUDA deployment runs the map in half precision,
+ * tracking.py:177-178): feat and out are IEEE half, rois stay float32 (pass the reference's half-rounded
+ * boxes converted to float), all arithmetic is float32 and the result is rounded to half once. */
+int b200_roi_align_fwd_f16(const void* feat, int layout, int B, int C, int H, int W,
+                           const float* rois, int64_t K, int PH, int PW, float spatial_scale,
+                           int sampling_ratio, int aligned, void* out, void* stream);
+
 /* ---- appearance cost -----------------------------------------------------------
  * Replaces Tracking.build_C_app_topk (model/mainTracking.py:141-211).
  * bank: [M,T,128] float32 history banks, bank_len[M] valid rows per track (0 = the row

@@ -147,3 +147,22 @@ def test_roi_huge_footprints_take_the_exact_fallbacks(nhwc):
     for ps, sr in [((10, 10), 2), ((7, 7), 2), ((10, 10), -1)]:
         want = native.roi_align(feat, rois, ps, 1.0, sr, True)
         assert_close(_run(feat, rois, ps, 1.0, sr, True, nhwc), want, rtol=1e-5, atol=2e-6, what="huge %s %s" % (ps, sr))
+
+
+@pytest.mark.parametrize("nhwc", [False, True])
+@pytest.mark.parametrize("ps", [(10, 10), (7, 7), (5, 4)])
+def test_roi_float16_storage(ps, nhwc):
+    """float16 map / float16 output (tracking.py:177-178): contract = float32 sampling of the half-rounded map,
+    rounded to half once, i.e. within half an ulp (2^-11 relative) of the float32 oracle on the same values."""
+    rng = np.random.default_rng(21)
+    feat16 = rng.standard_normal((2, 96, 40, 40)).astype(np.float16)
+    boxes = np.concatenate([synth.random_boxes(rng, 40, 1280, 1280), synth.edge_case_boxes(1280, 1280)])
+    boxes = boxes.astype(np.float16).astype(np.float64)              # the reference builds rois in half
+    rois = np.concatenate([rng.integers(0, 2, (len(boxes), 1)).astype(np.float64), boxes], 1).astype(np.float32)
+    f = torch.from_numpy(feat16).cuda()
+    if nhwc:
+        f = f.contiguous(memory_format=torch.channels_last)
+    got = roi.roi_align(f, torch.from_numpy(rois).cuda().half(), ps, 40 / 1280.0, 2, True)
+    assert got.dtype == torch.float16 and got.shape == (len(boxes), 96, ps[0], ps[1])
+    want = native.roi_align(feat16.astype(np.float32), rois, ps, 40 / 1280.0, 2, True)
+    assert_close(got.float().cpu().numpy(), want, rtol=1e-3, atol=2e-4, what="fp16 %s" % (ps,))

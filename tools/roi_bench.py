@@ -31,16 +31,19 @@ def timed(fn, iters, flush):
     return t[len(t) // 2] * 1e-3, t[0] * 1e-3
 
 
-def case(name, Bm, Hf, Wf, H_in, W_in, per_map, ps=(10, 10), nhwc=False, tv=False, iters=20):
+def case(name, Bm, Hf, Wf, H_in, W_in, per_map, ps=(10, 10), nhwc=False, tv=False, iters=20, half=False):
     rng = np.random.default_rng(0)
     boxes = np.concatenate([synth.random_boxes(rng, per_map, H_in, W_in) for _ in range(Bm)])
     rois = np.concatenate([np.repeat(np.arange(Bm), per_map)[:, None].astype(np.float64), boxes], 1).astype(np.float32)
     r = torch.from_numpy(rois).cuda()
     feat = torch.randn((Bm, 512, Hf, Wf), device="cuda")
+    if half:
+        feat = feat.half()
     if nhwc:
         feat = feat.contiguous(memory_format=torch.channels_last)
     K = r.shape[0]
-    alg = K * 512 * ps[0] * ps[1] * 4 + Bm * 512 * Hf * Wf * 4 + K * 20
+    es = 2 if half else 4
+    alg = K * 512 * ps[0] * ps[1] * es + Bm * 512 * Hf * Wf * es + K * 20
     flush = torch.empty(256 * 1024 * 1024 // 4, device="cuda") if alg < 512e6 else None
     if tv:
         import torchvision
@@ -50,7 +53,7 @@ def case(name, Bm, Hf, Wf, H_in, W_in, per_map, ps=(10, 10), nhwc=False, tv=Fals
     for _ in range(3):
         fn()
     med, best = timed(fn, iters, flush)
-    print(json.dumps({"case": name, "impl": "torchvision" if tv else "b200", "layout": "nhwc" if nhwc else "nchw",
+    print(json.dumps({"case": name, "impl": "torchvision" if tv else "b200", "layout": "nhwc" if nhwc else "nchw", "dtype": "f16" if half else "f32",
                       "K": K, "out": list(ps), "alg_MB": round(alg / 1e6, 2), "us_median": round(med * 1e6, 2),
                       "us_best": round(best * 1e6, 2), "GBps_median": round(alg / med / 1e9, 1),
                       "frac_of_measured_peak": round(alg / med / 1e9 / PEAK, 3)}), flush=True)
@@ -74,5 +77,8 @@ if __name__ == "__main__":
                 case("c5x64", 64, 34, 60, 1088, 1920, 128, nhwc=nhwc, tv=tv, iters=10)
             if "g64" in which:      # the bench.py stream group: 64 maps x 64 boxes per launch
                 case("g64", 64, 40, 40, 1280, 1280, 64, nhwc=nhwc, tv=tv, iters=10)
+            if "g64h" in which and not tv:      # float16 storage
+                case("g64", 64, 40, 40, 1280, 1280, 64, nhwc=nhwc, iters=10, half=True)
+                case("c3", 256, 40, 40, 1280, 1280, 16, nhwc=nhwc, iters=10, half=True)
             if "c2_7" in which:
                 case("c2_7x7", 1, 40, 40, 1280, 1280, 64, ps=(7, 7), nhwc=nhwc, tv=tv)
