@@ -68,11 +68,12 @@ __device__ __forceinline__ void predict(double* x, double* P, int stage, const f
     else predict_t<double, double>(x, P, q);
 }
 
-// inv(S) for a 4x4 matrix: LU with partial pivoting, then solves against the identity
-// (what numpy.linalg.inv's gesv does).
+// inv(S) for a 4x4 matrix: LU with partial pivoting, then solves against the identity (what
+// numpy.linalg.inv's gesv does).  Like LAPACK's getf2, pivots are inverted once and multiplied in: four
+// divisions per inverse instead of twenty (a double division is a ~40-instruction dependent chain).
 template <typename T>
 __device__ __forceinline__ void inv4(const T* S, T* SI) {
-    T a[4][4], b[4][4];
+    T a[4][4], b[4][4], rinv[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -95,10 +96,10 @@ __device__ __forceinline__ void inv4(const T* S, T* SI) {
                     t = b[j][k]; b[j][k] = b[i][k]; b[i][k] = t;
                 }
             }
-        const T r = (T)1 / a[j][j];
+        rinv[j] = (T)1 / a[j][j];
 #pragma unroll
         for (int i = j + 1; i < 4; ++i) {
-            a[i][j] *= r;
+            a[i][j] *= rinv[j];
 #pragma unroll
             for (int k = j + 1; k < 4; ++k) a[i][k] -= a[i][j] * a[j][k];
         }
@@ -113,7 +114,7 @@ __device__ __forceinline__ void inv4(const T* S, T* SI) {
         for (int i = 3; i >= 0; --i) {
 #pragma unroll
             for (int k = i + 1; k < 4; ++k) b[i][c] -= a[i][k] * b[k][c];
-            b[i][c] = b[i][c] / a[i][i];
+            b[i][c] *= rinv[i];
         }
     }
 #pragma unroll

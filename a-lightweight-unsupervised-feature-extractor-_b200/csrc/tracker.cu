@@ -1,13 +1,14 @@
-// GPU-resident multi-stream tracker: Tracking.update (model/mainTracking.py:450-610) as five
+// GPU-resident multi-stream tracker: Tracking.update (model/mainTracking.py:450-610) as six
 // kernels per frame-step, batched over independent streams (one CTA, or one grid slice, each).
 //
 //   begin   (CTA / stream)  :467-487  empty-frame shortcut, predict_all, main/ReID row split,
 //                                     detection prep (unit embeddings, z, float32 boxes), gate prep
 //   cost1   (grid)          :496-511  Mahalanobis gate first, then bank top-k appearance + box + conf terms
 //                                     for the surviving pairs, written once as C and C^T
-//   assign<1> (CTA / stream):514-538  LSAP + cost_max filter, update_matched, mark_missed
+//   assign<1> (CTA / stream):514-538  LSAP + cost_max filter, match bookkeeping, mark_missed
 //   cost2   (grid)          :552-558  ReID-only appearance cost for long-lost rows x leftover dets
-//   assign<2> (CTA / stream):560-610  LSAP, update_matched, mark_missed, births, purge, result table
+//   assign<2> (CTA / stream):560-610  LSAP, match bookkeeping, mark_missed, births, purge, result table
+//   update  (grid)          :375-448  Kalman update, posterior gate, EMA, bank push for every match of the step
 //
 // State never leaves the device.  Tracks live in fixed physical slots (banks are never moved);
 // `order` lists the live slots by ascending track id, which is the row order the reference uses
@@ -55,7 +56,10 @@ struct Dev {
     double* gate_SI;
     int *rows_main, *rows_reid, *cnt, *ud1, *det_used, *m_row, *m_det, *m_app, *tmp;
     int2 *work1, *work2;             // (stream, row * 64 + detection tile) items of the two cost launches
-    int* wcount;                     // [2] number of items queued for this step
+    int* wcount;                     // [3] items queued for this step: cost1, cost2, updates
+    int *upd_slot, *upd_det;         // update queue: global slot / detection index of every match
+    float* upd_cost;                 //               its (float32) cost, negative-zero-safe flag in upd_flag
+    uint8_t* upd_flag;               //               1 = matched in the ReID-only stage
     // configuration
     cost::PairWeights pw;
     double maha_thr, cost_max, conf_update_min, cost_update_max, reid_only_cost_max, init_conf_min;
@@ -146,7 +150,7 @@ __device__ inline void enqueue_cost_work(int2* work, int* counter, int s, int M,
 
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) begin_kernel(Dev d) {
-    Span span((d.frame_id[0] & 7) * 5 + 0);
+    Span span((d.frame_id[0] & 7) * 6 + 0);
     __shared__ int scratch[kThreads / 32];
     const int s = blockIdx.x, tid = threadIdx.x;
     int* hdr = d.hdr + s * kHdr;
@@ -175,6 +179,7 @@ __global__ void __launch_bounds__(kThreads) begin_kernel(Dev d) {
         }
         return;
     }
+    if (s == 0 && tid == 0) d.wcount[2] = 0;       // last step's update_kernel is done; nothing queued yet
     if (n < 0) {                                   // stream idle this step
         if (tid == 0) {
             cnt[C_MODE] = MODE_SKIP;
@@ -239,7 +244,7 @@ __global__ void __launch_bounds__(kThreads) begin_kernel(Dev d) {
 // ReID-only stage (:552-558): rows_reid x leftover detections, appearance cost only, dense tiles (bank and
 // 64 detection rows staged in shared memory, see assoc_cost.cuh).  Persistent CTAs over queued work items.
 __global__ void __launch_bounds__(cost::kThreads) cost2_kernel(Dev d) {
-    Span span((d.frame_id[0] & 7) * 5 + 3);
+    Span span((d.frame_id[0] & 7) * 6 + 3);
     extern __shared__ __align__(16) float smem[];
     __shared__ int s_idx[cost::kTileN];
     const int total = d.wcount[1];
@@ -300,7 +305,7 @@ __device__ __forceinline__ unsigned fkey(float f) {                 // order-pre
 }
 
 __global__ void __launch_bounds__(kCost1Warps * 32) cost1_sparse_kernel(Dev d) {
-    Span span((d.frame_id[0] & 7) * 5 + 1);
+    Span span((d.frame_id[0] & 7) * 6 + 1);
     const int total = d.wcount[0];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float kNegInf = -__int_as_float(0x7f800000);
@@ -406,7 +411,7 @@ __device__ __forceinline__ void transpose_reduce32(float (&p)[32]) {
 // whole bank is read once into registers (one global round trip, reused by every surviving detection) and
 // the 32 dot products of a detection are reduced together (transpose_reduce32).
 __global__ void __launch_bounds__(kCost1Warps * 32, 2) cost1_sparse32_kernel(Dev d) {
-    Span span((d.frame_id[0] & 7) * 5 + 1);
+    Span span((d.frame_id[0] & 7) * 6 + 1);
     const int total = d.wcount[0];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float kNegInf = -__int_as_float(0x7f800000);
@@ -489,80 +494,96 @@ __global__ void __launch_bounds__(kCost1Warps * 32, 2) cost1_sparse32_kernel(Dev
     }
 }
 
-// update_matched (:375-448) for `nm` (row, det) pairs listed in m_row / m_det (det = global index).
-__device__ inline void update_matched(const Dev& d, int s, int nm, const int* rows, const float* C, int ldc,
-                                      const int* m_col, double cost_update_max, double maha_thr, double* kf_scratch) {
+// update_matched (:375-448), part 1, inside the assignment kernel: the bookkeeping that later steps of the same
+// frame depend on (:403-415: last box / conf / frame, age, miss reset, match cost), and one queue entry per
+// match for update_kernel, which does the arithmetic (Kalman update, posterior gate, EMA, bank push).
+__device__ inline void note_matches(const Dev& d, int s, int nm, const int* rows, const float* C, int ldc,
+                                    const int* m_col, int reid_stage, int* scratch) {
+    if (nm <= 0) return;                                          // uniform across the CTA
     const size_t sb = (size_t)s * d.MT, db = (size_t)s * d.MD;
     const int frame = d.frame_id[s];
-    const float rdiag[4] = {1.f, 1.f, 1.f, 1.f};
-    // Kalman update (:400) + bookkeeping (:403-426): eight lanes per match (one per row of P), see
-    // kf::update_rows_t; a 256-thread CTA works on 32 matches at a time.
-    {
-        const int sub = threadIdx.x & 7, group = threadIdx.x >> 3, ngroups = blockDim.x >> 3;
-        double* sP = kf_scratch + (size_t)group * 96;
-        double* sK = sP + 64;
-        for (int q0 = 0; q0 < nm; q0 += ngroups) {
-            const int qd = q0 + group;
-            const bool on = qd < nm;
-            int r = 0, j = 0, st = -1;
-            size_t slot = 0;
-            if (on) {
-                r = d.m_row[sb + qd];
-                j = d.m_det[sb + qd];
-                slot = sb + rows[r];
-                st = d.kf_stage[slot];
-            }
-            const float* z = d.det_z + (db + j) * 4;
-            const double conf = on ? d.confs[db + j] : 0.0;
-            const double c = on ? (double)C[(size_t)r * ldc + m_col[qd]] : 0.0;
-            int app = on && !(conf < d.conf_update_min) && !(c > cost_update_max);      // :418-421
-            // :424-426 posterior gate.  Whether d2 is evaluated must be uniform over every group that shares a
-            // __syncwarp mask inside update_rows_t, so it only depends on the (CTA-uniform) threshold.
-            const bool want = maha_thr < 1e17;
-            const int nst = st < 2 ? st + 1 : 2;
-            double d2 = 0.0;
-#pragma unroll
-            for (int v = 0; v < 3; ++v) {                         // one pass per arithmetic variant (stage)
-                const unsigned mask = __ballot_sync(0xffffffffu, on && st == v);
-                if (on && st == v) {
-                    double* gx = d.kf_x + slot * 8;
-                    double* gP = d.kf_P + slot * 64;
-                    if (v == 0) d2 = kf::update_rows_t<float, float>(gx, gP, z, rdiag, sP, sK, sub, mask, nst, want);
-                    else if (v == 1) d2 = kf::update_rows_t<float, double>(gx, gP, z, rdiag, sP, sK, sub, mask, nst, want);
-                    else d2 = kf::update_rows_t<double, double>(gx, gP, z, rdiag, sP, sK, sub, mask, nst, want);
-                }
-            }
-            if (on && sub == 0) {
-                if (app && want && d2 > maha_thr) app = 0;
-                d.kf_stage[slot] = (uint8_t)nst;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) d.last_bbox[slot * 4 + k] = d.boxes[(db + j) * 4 + k];
-                d.last_conf[slot] = conf;
-                d.last_frame[slot] = frame;
-                d.age[slot] += 1;
-                d.miss[slot] = 0;
-                d.last_cost[slot] = c;
-                d.m_app[sb + qd] = app;
-            }
-            __syncwarp();
-        }
-    }
     __syncthreads();
-    TRK_STAMP(3);
-    // EMA + bank push (:429-448): a warp takes four matches at a time and issues all their loads first
-    const int lane = threadIdx.x & 31, nwarp = blockDim.x >> 5, warp = threadIdx.x >> 5;
-    for (int q0 = warp * 4; q0 < nm; q0 += nwarp * 4) {
+    if (threadIdx.x == 0) scratch[0] = atomicAdd(d.wcount + 2, nm);
+    __syncthreads();
+    const int base = scratch[0];
+    for (int qd = threadIdx.x; qd < nm; qd += blockDim.x) {
+        const int r = d.m_row[sb + qd], j = d.m_det[sb + qd];
+        const size_t slot = sb + rows[r];
+        const float c = C[(size_t)r * ldc + m_col[qd]];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) d.last_bbox[slot * 4 + k] = d.boxes[(db + j) * 4 + k];
+        d.last_conf[slot] = d.confs[db + j];
+        d.last_frame[slot] = frame;
+        d.age[slot] += 1;
+        d.miss[slot] = 0;
+        d.last_cost[slot] = (double)c;
+        d.upd_slot[base + qd] = (int)slot;
+        d.upd_det[base + qd] = (int)(db + j);
+        d.upd_cost[base + qd] = c;
+        d.upd_flag[base + qd] = (uint8_t)reid_stage;
+    }
+}
+
+// update_matched, part 2: every match of every stream, both stages (they touch disjoint tracks).  A warp takes
+// four queue entries: eight lanes per match run the Kalman update (:400, kf::update_rows_t) and the posterior
+// gate (:424-426), then the warp applies the EMA and pushes the bank rows of those four matches (:429-448).
+constexpr int kUpdWarps = 4;
+
+__global__ void __launch_bounds__(kUpdWarps * 32) update_kernel(Dev d) {
+    Span span((d.frame_id[0] & 7) * 6 + 5);
+    __shared__ double scratch[kUpdWarps * 4 * 96];
+    const int total = d.wcount[2];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, sub = lane & 7, grp = lane >> 3;
+    double* sP = scratch + (size_t)(warp * 4 + grp) * 96;
+    double* sK = sP + 64;
+    const float rdiag[4] = {1.f, 1.f, 1.f, 1.f};                           // KalmanFilter.py:98-99
+    for (int w0 = (blockIdx.x * kUpdWarps + warp) * 4; w0 < total; w0 += gridDim.x * kUpdWarps * 4) {
+        const int idx = w0 + grp;
+        const bool on = idx < total;
+        size_t slot = 0, det = 0;
+        int st = -1, reid = 0;
+        double c = 0.0, conf = 0.0;
+        if (on) {
+            slot = (size_t)d.upd_slot[idx];
+            det = (size_t)d.upd_det[idx];
+            c = (double)d.upd_cost[idx];
+            reid = d.upd_flag[idx];
+            st = d.kf_stage[slot];
+            conf = d.confs[det];
+        }
+        const float* z = d.det_z + det * 4;
+        const double cmax = reid ? d.reid_only_cost_max : d.cost_update_max;   // :563 / :530
+        int app = on && !(conf < d.conf_update_min) && !(c > cmax);             // :418-421
+        const int nst = st < 2 ? st + 1 : 2;
+        double d2 = 0.0;
+#pragma unroll
+        for (int v = 0; v < 6; ++v) {               // arithmetic variant x (stage 1: posterior gate, stage 2: none)
+            const bool mine = on && st == (v >> 1) && reid == (v & 1);
+            const unsigned mask = __ballot_sync(0xffffffffu, mine);
+            if (mine) {
+                double* gx = d.kf_x + slot * 8;
+                double* gP = d.kf_P + slot * 64;
+                const bool want = !(v & 1);          // uniform over the lanes of `mask`
+                if ((v >> 1) == 0) d2 = kf::update_rows_t<float, float>(gx, gP, z, rdiag, sP, sK, sub, mask, nst, want);
+                else if ((v >> 1) == 1) d2 = kf::update_rows_t<float, double>(gx, gP, z, rdiag, sP, sK, sub, mask, nst, want);
+                else d2 = kf::update_rows_t<double, double>(gx, gP, z, rdiag, sP, sK, sub, mask, nst, want);
+            }
+        }
+        if (on && sub == 0) d.kf_stage[slot] = (uint8_t)nst;
+        if (app && !reid && d2 > d.maha_thr) app = 0;                           // :424-426
+        // EMA + bank push for this warp's four matches, all loads first
         float4 e[4], o[4];
         size_t slots[4];
         int len[4], head[4];
-        bool on[4];
+        bool go[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            const int qd = q0 + u;
-            on[u] = qd < nm && d.m_app[sb + (qd < nm ? qd : 0)];
-            if (on[u]) {
-                slots[u] = sb + rows[d.m_row[sb + qd]];
-                e[u] = reinterpret_cast<const float4*>(d.det_unit + (db + d.m_det[sb + qd]) * cost::kD)[lane];
+            go[u] = __shfl_sync(0xffffffffu, app, u * 8) != 0;
+            const unsigned long long sl = __shfl_sync(0xffffffffu, (unsigned long long)slot, u * 8);
+            const unsigned long long dt = __shfl_sync(0xffffffffu, (unsigned long long)det, u * 8);
+            slots[u] = (size_t)sl;
+            if (go[u]) {
+                e[u] = reinterpret_cast<const float4*>(d.det_unit + (size_t)dt * cost::kD)[lane];
                 o[u] = reinterpret_cast<const float4*>(d.ema + slots[u] * cost::kD)[lane];
                 len[u] = d.bank_len[slots[u]];
                 head[u] = d.bank_head[slots[u]];
@@ -570,7 +591,7 @@ __device__ inline void update_matched(const Dev& d, int s, int nm, const int* ro
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            if (!on[u]) continue;
+            if (!go[u]) continue;
             float4 f;
             f.x = __fadd_rn(__fmul_rn(d.ema_a, o[u].x), __fmul_rn(d.ema_b, e[u].x));
             f.y = __fadd_rn(__fmul_rn(d.ema_a, o[u].y), __fmul_rn(d.ema_b, e[u].y));
@@ -581,18 +602,18 @@ __device__ inline void update_matched(const Dev& d, int s, int nm, const int* ro
             if (len[u] < d.HIST) { pos = head[u] + len[u]; if (pos >= d.HIST) pos -= d.HIST; ++len[u]; }
             else { pos = head[u]; head[u] = head[u] + 1 == d.HIST ? 0 : head[u] + 1; }
             reinterpret_cast<float4*>(d.bank + (slots[u] * d.HIST + pos) * cost::kD)[lane] = e[u];
+            __syncwarp();
             if (lane == 0) { d.bank_len[slots[u]] = len[u]; d.bank_head[slots[u]] = head[u]; }
         }
+        __syncwarp();
     }
-    __syncthreads();
-    TRK_STAMP(4);
 }
 
 // hungarian_assign (hung.py:5-45) for this stream's matrix; fills m_row/m_det, marks misses.
 // Returns the number of matches; *n_unmatched_rows is the count appended to the unmatched list.
 template <int STAGE>
 __global__ void __launch_bounds__(kThreads) assign_kernel(Dev d, int smem_matrix_floats) {
-    Span span((d.frame_id[0] & 7) * 5 + (STAGE == 1 ? 2 : 4));
+    Span span((d.frame_id[0] & 7) * 6 + (STAGE == 1 ? 2 : 4));
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int scratch[kThreads / 32];
     __shared__ int s_rc;
@@ -652,10 +673,7 @@ __global__ void __launch_bounds__(kThreads) assign_kernel(Dev d, int smem_matrix
                 out_ut[ut0 + pos] = d.tid[slot];
             }, scratch);
             __syncthreads();
-            if (STAGE == 1) TRK_STAMP(2);
-            update_matched(d, s, n_match, rows, C, d.MD, m_col,
-                           STAGE == 1 ? d.cost_update_max : d.reid_only_cost_max, STAGE == 1 ? d.maha_thr : 1e18,
-                           reinterpret_cast<double*>(smem_raw));          // the LSAP workspace is free again
+            note_matches(d, s, n_match, rows, C, d.MD, m_col, STAGE == 2, scratch);
         }
     } else if (M > 0) {                             // no detections left for these rows: all missed
         for (int r = tid; r < M; r += blockDim.x) {
@@ -783,7 +801,7 @@ __global__ void reset_kernel(Dev d) {
         d.hdr[s * kHdr + H_NLIVE] = 0;
         d.hdr[s * kHdr + H_NEXT] = 0;
         d.hdr[s * kHdr + H_NFREE] = d.MT;
-        if (s == 0) { d.wcount[0] = 0; d.wcount[1] = 0; }
+        if (s == 0) { d.wcount[0] = 0; d.wcount[1] = 0; d.wcount[2] = 0; }
     }
 }
 
@@ -800,7 +818,7 @@ struct b200_tracker {
     int* in_ndet = nullptr; int* in_frame = nullptr; double* in_boxes = nullptr; double* in_confs = nullptr;
     float* in_embs = nullptr; int* dev_result = nullptr;
     int ctl_threads = 256;              // CTA width of the per-stream control kernels (begin / assign)
-    int cost_grid = 0, cost1_grid = 0;   // persistent CTAs of the cost kernels (resident CTAs per SM x SMs)
+    int cost_grid = 0, cost1_grid = 0, upd_grid = 0;   // persistent CTAs of the cost kernels (resident CTAs per SM x SMs)
     size_t assign_smem = 0;
     int smem_matrix_floats = 0;
 };
@@ -851,7 +869,8 @@ extern "C" int b200_tracker_create(b200_tracker** out, int n_streams, int max_tr
     TAKE(ud1, int, S * MD); TAKE(det_used, int, S * MD); TAKE(m_row, int, S * MT); TAKE(m_det, int, S * MT);
     TAKE(m_app, int, S * MT); TAKE(tmp, int, S * MT);
     const size_t tiles_max = (MD + cost::kTileN - 1) / cost::kTileN;
-    TAKE(work1, int2, S * MT * tiles_max); TAKE(work2, int2, S * MT * tiles_max); TAKE(wcount, int, 2);
+    TAKE(work1, int2, S * MT * tiles_max); TAKE(work2, int2, S * MT * tiles_max); TAKE(wcount, int, 4);
+    TAKE(upd_slot, int, S * MT); TAKE(upd_det, int, S * MT); TAKE(upd_cost, float, S * MT); TAKE(upd_flag, uint8_t, S * MT);
     // inputs (one contiguous block so step_host needs a single H2D copy) and the result table
     const size_t o_in = c.take<double>(0);
     TAKE(in_ndet, int, S); TAKE(in_frame, int, S); TAKE(in_boxes, double, S * MD * 4); TAKE(in_confs, double, S * MD);
@@ -874,6 +893,7 @@ extern "C" int b200_tracker_create(b200_tracker** out, int n_streams, int max_tr
     PTR(prev_conff, float); PTR(C1, float); PTR(C1T, float); PTR(C2, float); PTR(C2T, float); PTR(gate_SI, double);
     PTR(rows_main, int); PTR(rows_reid, int); PTR(cnt, int); PTR(ud1, int); PTR(det_used, int); PTR(m_row, int);
     PTR(m_det, int); PTR(m_app, int); PTR(tmp, int); PTR(work1, int2); PTR(work2, int2); PTR(wcount, int);
+    PTR(upd_slot, int); PTR(upd_det, int); PTR(upd_cost, float); PTR(upd_flag, uint8_t);
 #undef PTR
     t->in_ndet = reinterpret_cast<int*>(base + o_in_ndet);
     t->in_frame = reinterpret_cast<int*>(base + o_in_frame);
@@ -912,8 +932,6 @@ extern "C" int b200_tracker_create(b200_tracker** out, int n_streams, int max_tr
     if (max_tracks <= 256 && max_dets <= 256 && mat > 32 * 1024) mat = 32 * 1024;
     t->smem_matrix_floats = (int)(mat / sizeof(float));
     t->assign_smem = wb + mat;
-    const size_t kf_scratch = (size_t)(trk::kThreads / 8) * 96 * sizeof(double);    // update_rows_t scratch
-    if (t->assign_smem < kf_scratch) t->assign_smem = kf_scratch;
     cudaFuncSetAttribute(trk::assign_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t->assign_smem);
     cudaFuncSetAttribute(trk::assign_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t->assign_smem);
     cudaFuncSetAttribute(trk::cost2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cost::smem_bytes(cost::kMaxBank));
@@ -937,6 +955,7 @@ extern "C" int b200_tracker_create(b200_tracker** out, int n_streams, int max_tr
         else
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trk::cost1_sparse_kernel, trk::kCost1Warps * 32, 0);
         t->cost1_grid = sms * (per_sm > 0 ? per_sm : 1);
+        t->upd_grid = sms * 2;
     }
     *out = t;
     return B200_OK;
@@ -977,6 +996,8 @@ extern "C" int b200_tracker_step(b200_tracker* t, const int32_t* n_det, const do
     if ((rc = check_launch("trk cost2_kernel"))) return rc;
     trk::assign_kernel<2><<<d.S, t->ctl_threads, t->assign_smem, st>>>(d, t->smem_matrix_floats);
     if ((rc = check_launch("trk assign_kernel<2>"))) return rc;
+    trk::update_kernel<<<t->upd_grid, trk::kUpdWarps * 32, 0, st>>>(d);
+    if ((rc = check_launch("trk update_kernel"))) return rc;
     return B200_OK;
 }
 

@@ -11,7 +11,7 @@ S, W = 64, 40
 dev = torch.device("cuda", 0)
 torch.cuda.set_device(0)
 lib = ctypes.CDLL(_lib.LIB_PATH)
-names = ["roi", "begin", "cost1", "assign1", "cost2", "assign2"]
+names = ["roi", "begin", "cost1", "assign1", "cost2", "assign2", "update"]
 for mode in ("serial", "overlap"):
     g = bench.StreamGroup(S, W + 12, 0, dev)
     if mode == "serial":
@@ -29,7 +29,7 @@ for mode in ("serial", "overlap"):
     lib.b200_debug_spans_roi(b1, 0)
     lib.b200_debug_spans_trk(b2, 0)
     roi = np.array(b1[:16], dtype=np.float64).reshape(8, 2)
-    trk = np.array(b2[:80], dtype=np.float64).reshape(8, 5, 2)
+    trk = np.array(b2[:96], dtype=np.float64).reshape(8, 6, 2)
     # ROI slot order is only known up to a rotation: sort the used slots by start time
     used = sorted([r for r in roi if r[1] > 0], key=lambda r: r[0])
     t0 = min(used[0][0], trk[0, 0, 0])
