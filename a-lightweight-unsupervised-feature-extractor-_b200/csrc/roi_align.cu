@@ -126,6 +126,9 @@ __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
 __device__ __forceinline__ void cp_async4_s(unsigned smem_addr, const void* gsrc) {     // shared-space address
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(smem_addr), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ void cp_async16_s(unsigned smem_addr, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_addr), "l"(gsrc) : "memory");
+}
 __device__ __forceinline__ void sts_f32(unsigned smem_addr, float v) {
     asm volatile("st.shared.f32 [%0], %1;\n" ::"r"(smem_addr), "f"(v) : "memory");
 }
@@ -145,6 +148,13 @@ __device__ __forceinline__ void bulk_store_issue(void* gdst, const void* ssrc, u
 __device__ __forceinline__ void bulk_store_wait_read() {
     asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
 }
+
+// Per-ROI record of the two-kernel path: the 16 channel tiles of a ROI share one geometry / footprint /
+// weight-table computation (roi_prep_kernel) instead of repeating it.
+struct __align__(16) RoiPrep {
+    int b, ymin, xmin, FY;
+    int FX, staged, pad0, pad1;     // staged = 0: footprint too large, the tile computes everything itself
+};
 
 template <int PH, int PW>
 struct TileSmem {
@@ -194,15 +204,72 @@ __device__ __forceinline__ void separable_accumulate(float (&acc)[PH][PW], const
     }
 }
 
+// Zeroes and fills the dense weight tables Wy[rows][PHP], Wx[cols][PWP] (one warp; lanes 0-15: y, 16-31: x;
+// lane p owns column p of its table).  The mean over samples rides on the x weights.
+template <int PH, int PW>
+__device__ __forceinline__ void build_tables(const Geom& g, float inv, int H, int W, int ymin, int xmin, int FY,
+                                             float* sWy, float* sWx, int n_floats, int lane) {
+    constexpr int PHP = (PH + 3) & ~3, PWP = (PW + 3) & ~3;
+    for (int i = lane; i < n_floats; i += 32) sWy[i] = 0.0f;      // sWx follows sWy in memory
+    __syncwarp();
+    const int axis = lane >> 4, p = lane & 15;
+    const int Pn = axis ? PW : PH, grid = axis ? g.gw : g.gh, dim = axis ? W : H;
+    const float start = axis ? g.sw : g.sh, bin = axis ? g.bw : g.bh;
+    float* tab = (axis ? sWx : sWy) + p;
+    const int stride = axis ? PWP : PHP, lo0 = axis ? xmin : ymin;
+    const float ws = axis ? inv : 1.0f;
+    if (p < Pn && FY)
+        for (int i = 0; i < grid; ++i) {
+            const Tap t = make_tap(sample_pos(start, p, bin, i, grid), dim);
+            if (t.valid) {
+                tab[(t.lo - lo0) * stride] += t.wlo * ws;
+                tab[(t.hi - lo0) * stride] += t.whi * ws;
+            }
+        }
+}
+
+// Two-kernel path, first kernel: one warp per ROI computes footprint + tables once for all channel tiles.
+template <int PH, int PW>
+__global__ void __launch_bounds__(128)
+roi_prep_kernel(const float* __restrict__ rois, long long K, int B, int H, int W, float scale, int sr, int aligned,
+                RoiPrep* __restrict__ prep, float* __restrict__ tabs) {
+    using L = TileSmem<PH, PW>;
+    __shared__ __align__(16) float sTabs[4][L::kTabFloats];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long k = (long long)blockIdx.x * 4 + warp;
+    if (k >= K) return;
+    const Geom g = roi_geometry(rois + 5 * k, scale, sr, aligned, PH, PW);
+    const float inv = __fdiv_rn(1.0f, g.count);
+    int ymin, xmin, FY, FX;
+    axis_footprint(g.sh, g.bh, PH, g.gh, H, &ymin, &FY);
+    axis_footprint(g.sw, g.bw, PW, g.gw, W, &xmin, &FX);
+    if (g.b < 0 || g.b >= B || FY == 0 || FX == 0) FY = FX = 0;
+    const bool staged = FY <= kFootCap && FX <= kFootCap;
+    if (staged) {
+        float* t = sTabs[warp];
+        build_tables<PH, PW>(g, inv, H, W, ymin, xmin, FY, t, t + kFootCap * L::kPHP, L::kTabFloats, lane);
+        __syncwarp();
+        float* dst = tabs + (size_t)k * L::kTabFloats;
+        for (int i = lane; i < L::kTabFloats / 4; i += 32)
+            reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(t)[i];
+    }
+    if (lane == 0) {
+        RoiPrep h;
+        h.b = g.b; h.ymin = ymin; h.xmin = xmin; h.FY = FY; h.FX = FX; h.staged = staged ? 1 : 0; h.pad0 = h.pad1 = 0;
+        prep[k] = h;
+    }
+}
+
 #ifndef B200_ROI_MIN_CTAS
 #define B200_ROI_MIN_CTAS 6
 #endif
 
-template <int PH, int PW, bool NHWC, typename T>
+template <int PH, int PW, bool NHWC, typename T, bool PREP>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, (B200_ROI_MIN_CTAS * 2 + kWarpsPerCta - 1) / kWarpsPerCta)
 roi_align_tile_kernel(const T* __restrict__ feat, int B, int C, int H, int W,
                       const float* __restrict__ rois, long long K, float scale, int sr, int aligned,
-                      T* __restrict__ out, int ctiles) {
+                      T* __restrict__ out, int ctiles, const RoiPrep* __restrict__ prep,
+                      const float* __restrict__ prep_tabs) {
     constexpr bool kF32 = sizeof(T) == 4;
     using L = TileSmem<PH, PW>;
     constexpr int PHP = L::kPHP, PWP = L::kPWP, NB = PH * PW;
@@ -220,12 +287,26 @@ roi_align_tile_kernel(const T* __restrict__ feat, int B, int C, int H, int W,
     const long long k = wi32 / (unsigned)ctiles;
     const int c0 = (int)(wi32 % (unsigned)ctiles) * 32;
     const int cn = min(32, C - c0);
-    const Geom g = roi_geometry(rois + 5 * k, scale, sr, aligned, PH, PW);
-
-    int ymin, xmin, FY, FX;
-    axis_footprint(g.sh, g.bh, PH, g.gh, H, &ymin, &FY);
-    axis_footprint(g.sw, g.bw, PW, g.gw, W, &xmin, &FX);
-    if (g.b < 0 || g.b >= B || FY == 0 || FX == 0) FY = FX = 0;      // nothing sampled: zeros
+    Geom g;
+    float inv = 0.0f;
+    int ymin = 0, xmin = 0, FY = 0, FX = 0;
+    bool pre = false;                         // footprint and tables come from roi_prep_kernel
+    if (PREP) {
+        const int4 h0 = reinterpret_cast<const int4*>(prep + k)[0], h1 = reinterpret_cast<const int4*>(prep + k)[1];
+        if (h1.y) {
+            pre = true;
+            g.b = h0.x; ymin = h0.y; xmin = h0.z; FY = h0.w; FX = h1.x;
+        }
+    }
+    if (!pre) {
+        g = roi_geometry(rois + 5 * k, scale, sr, aligned, PH, PW);
+        // mean over samples: 1/count is exact for the power-of-two counts of sampling_ratio 1, 2, 4; otherwise
+        // within 1 ulp of the reference's division
+        inv = __fdiv_rn(1.0f, g.count);
+        axis_footprint(g.sh, g.bh, PH, g.gh, H, &ymin, &FY);
+        axis_footprint(g.sw, g.bw, PW, g.gw, W, &xmin, &FX);
+        if (g.b < 0 || g.b >= B || FY == 0 || FX == 0) FY = FX = 0;      // nothing sampled: zeros
+    }
     const bool staged = FY <= kFootCap && FX <= kFootCap;
     // Larger footprints keep their (bigger) weight tables in the output-tile area and read V
     // straight from global memory; only absurdly large ones take the per-bin path.
@@ -280,29 +361,16 @@ roi_align_tile_kernel(const T* __restrict__ feat, int B, int C, int H, int W,
                     }
             }
         }
-        // ---- dense separable weight tables over the footprint (lanes 0-15: y, 16-31: x) ------
+        // ---- dense separable weight tables over the footprint ----------------------------------------
         float* sWy = staged ? sTab : sMain;
         float* sWx = sWy + (staged ? kFootCap : FY) * PHP;
-        if (staged) {
-            for (int i = lane; i < L::kTabFloats / 4; i += 32) reinterpret_cast<float4*>(sTab)[i] = make_float4(0, 0, 0, 0);
+        if (pre) {                             // ready-made: one more asynchronous copy
+            const unsigned st = (unsigned)__cvta_generic_to_shared(sTab);
+            const float* src = prep_tabs + (size_t)k * L::kTabFloats;
+            for (int i = lane; i < L::kTabFloats / 4; i += 32) cp_async16_s(st + 16u * i, src + 4 * i);
         } else {
-            for (int i = lane; i < FY * PHP + FX * PWP; i += 32) sMain[i] = 0.0f;
-        }
-        __syncwarp();
-        {
-            const int axis = lane >> 4, p = lane & 15;
-            const int Pn = axis ? PW : PH, grid = axis ? g.gw : g.gh, dim = axis ? W : H;
-            const float start = axis ? g.sw : g.sh, bin = axis ? g.bw : g.bh;
-            float* tab = (axis ? sWx : sWy) + p;
-            const int stride = axis ? PWP : PHP, lo0 = axis ? xmin : ymin;
-            if (p < Pn && FY)
-                for (int i = 0; i < grid; ++i) {              // column p of the table has one writer
-                    const Tap t = make_tap(sample_pos(start, p, bin, i, grid), dim);
-                    if (t.valid) {
-                        tab[(t.lo - lo0) * stride] += t.wlo;
-                        tab[(t.hi - lo0) * stride] += t.whi;
-                    }
-                }
+            build_tables<PH, PW>(g, inv, H, W, ymin, xmin, FY, sWy, sWx,
+                                 staged ? L::kTabFloats : FY * PHP + FX * PWP, lane);
         }
         if (staged) {
             cp_async_wait_all();
@@ -349,35 +417,33 @@ roi_align_tile_kernel(const T* __restrict__ feat, int B, int C, int H, int W,
 #pragma unroll
         for (int a = 0; a < PH; ++a)
 #pragma unroll
-            for (int b = 0; b < PW; ++b) acc[a][b] = sMain[lane * NB + a * PW + b];
+            for (int b = 0; b < PW; ++b) acc[a][b] = sMain[lane * NB + a * PW + b] * inv;
         __syncwarp();
     }
 
-    // ---- mean over samples (1/count is exact for the power-of-two counts of sampling_ratio 1, 2, 4;
-    // otherwise within 1 ulp of the reference's division), output tile to shared memory ----------
-    const float inv = __fdiv_rn(1.0f, g.count);
+    // ---- output tile to shared memory (the accumulators already hold the mean) ------------------------
     if (kF32) {
         float* myrow = sMain + lane * NB;
         if ((NB & 3) == 0) {
 #pragma unroll
             for (int q = 0; q < NB / 4; ++q)
                 reinterpret_cast<float4*>(myrow)[q] =
-                    make_float4(acc[(4 * q) / PW][(4 * q) % PW] * inv, acc[(4 * q + 1) / PW][(4 * q + 1) % PW] * inv,
-                                acc[(4 * q + 2) / PW][(4 * q + 2) % PW] * inv, acc[(4 * q + 3) / PW][(4 * q + 3) % PW] * inv);
+                    make_float4(acc[(4 * q) / PW][(4 * q) % PW], acc[(4 * q + 1) / PW][(4 * q + 1) % PW],
+                                acc[(4 * q + 2) / PW][(4 * q + 2) % PW], acc[(4 * q + 3) / PW][(4 * q + 3) % PW]);
         } else {
 #pragma unroll
-            for (int i = 0; i < NB; ++i) myrow[i] = acc[i / PW][i % PW] * inv;
+            for (int i = 0; i < NB; ++i) myrow[i] = acc[i / PW][i % PW];
         }
-    } else {                                   // 16-bit output: round once, after the fp32 mean
+    } else {                                   // 16-bit output: one rounding of the fp32 result
         __half* myrow = reinterpret_cast<__half*>(sMain) + lane * NB;
         if ((NB & 1) == 0) {
 #pragma unroll
             for (int q = 0; q < NB / 2; ++q)
-                reinterpret_cast<__half2*>(myrow)[q] = __floats2half2_rn(acc[(2 * q) / PW][(2 * q) % PW] * inv,
-                                                                         acc[(2 * q + 1) / PW][(2 * q + 1) % PW] * inv);
+                reinterpret_cast<__half2*>(myrow)[q] = __floats2half2_rn(acc[(2 * q) / PW][(2 * q) % PW],
+                                                                         acc[(2 * q + 1) / PW][(2 * q + 1) % PW]);
         } else {
 #pragma unroll
-            for (int i = 0; i < NB; ++i) myrow[i] = __float2half_rn(acc[i / PW][i % PW] * inv);
+            for (int i = 0; i < NB; ++i) myrow[i] = __float2half_rn(acc[i / PW][i % PW]);
         }
     }
 
@@ -435,23 +501,56 @@ roi_align_generic_kernel(const T* __restrict__ feat, int B, int C, int H, int W,
     }
 }
 
+// Below this many tiles one fused kernel is faster (the prep kernel costs a dependent launch); above it the
+// per-ROI work is done once by roi_prep_kernel and shared by the ROI's channel tiles.
+constexpr long long kPrepMinTiles = 16384;
+
 template <int PH, int PW, bool NHWC, typename T>
 int launch_tile(const T* feat, int B, int C, int H, int W, const float* rois, long long K,
                 float scale, int sr, int aligned, T* out, cudaStream_t st) {
     using L = TileSmem<PH, PW>;
     static bool configured = false;          // per instantiation; the attribute is idempotent
-    auto kern = roi_align_tile_kernel<PH, PW, NHWC, T>;
+    auto fused = roi_align_tile_kernel<PH, PW, NHWC, T, false>;
+    auto tiled = roi_align_tile_kernel<PH, PW, NHWC, T, true>;
     if (!configured) {
-        B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kBytesPerCta));
+        B200_CUDA(cudaFuncSetAttribute(fused, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kBytesPerCta));
+        B200_CUDA(cudaFuncSetAttribute(tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kBytesPerCta));
         configured = true;
     }
     const int ctiles = (C + 31) / 32;
     const long long warps = K * ctiles;
     const long long blocks = (warps + kWarpsPerCta - 1) / kWarpsPerCta;
     if (blocks > 0x7fffffffLL) return fail(B200_EINVAL, "roi_align: too many ROI tiles (%lld)", blocks);
-    kern<<<(unsigned)blocks, kWarpsPerCta * 32, L::kBytesPerCta, st>>>(feat, B, C, H, W, rois, K, scale, sr,
-                                                                     aligned, out, ctiles);
-    return check_launch("roi_align_tile_kernel");
+    if (warps < kPrepMinTiles || ctiles < 4) {
+        fused<<<(unsigned)blocks, kWarpsPerCta * 32, L::kBytesPerCta, st>>>(feat, B, C, H, W, rois, K, scale, sr,
+                                                                            aligned, out, ctiles, nullptr, nullptr);
+        return check_launch("roi_align_tile_kernel");
+    }
+    static bool pool_ready = false;          // keep freed scratch cached in the device's default pool: by default
+    if (!pool_ready) {                       // the pool hands memory back at every synchronisation point
+        int dev = 0;
+        cudaMemPool_t pool;
+        B200_CUDA(cudaGetDevice(&dev));
+        B200_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+        unsigned long long keep = ~0ull, cur = 0;
+        B200_CUDA(cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &cur));
+        if (cur < (64ull << 20)) B200_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        pool_ready = true;
+    }
+    char* ws = nullptr;                      // stream-ordered scratch: K records + K tables
+    const size_t rec = (size_t)K * sizeof(RoiPrep), tab = (size_t)K * L::kTabFloats * sizeof(float);
+    B200_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ws), rec + tab, st));
+    RoiPrep* prep = reinterpret_cast<RoiPrep*>(ws);
+    float* tabs = reinterpret_cast<float*>(ws + rec);
+    roi_prep_kernel<PH, PW><<<(unsigned)((K + 3) / 4), 128, 0, st>>>(rois, K, B, H, W, scale, sr, aligned, prep, tabs);
+    int rc = check_launch("roi_prep_kernel");
+    if (rc == B200_OK) {
+        tiled<<<(unsigned)blocks, kWarpsPerCta * 32, L::kBytesPerCta, st>>>(feat, B, C, H, W, rois, K, scale, sr,
+                                                                            aligned, out, ctiles, prep, tabs);
+        rc = check_launch("roi_align_tile_kernel");
+    }
+    B200_CUDA(cudaFreeAsync(ws, st));
+    return rc;
 }
 
 template <typename T>
