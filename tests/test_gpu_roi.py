@@ -136,6 +136,32 @@ def test_roi_full_size_properties():
 
 
 @pytest.mark.parametrize("nhwc", [False, True])
+@pytest.mark.parametrize("ps", [(10, 10), (7, 7)])
+def test_roi_large_launch_path_vs_oracle(ps, nhwc):
+    """More than 16 384 (ROI, channel-tile) pairs: the per-ROI prep pass + the persistent producer/consumer
+    kernel.  Every ROI is checked against the oracle; the list mixes ordinary boxes, the reference's edge
+    cases, boxes whose footprint is too large to stage (handled inside a consumer warp), bad batch indices,
+    and a channel count with a ragged last tile."""
+    rng = np.random.default_rng(17)
+    Bm, C, Hf, Wf = 3, 150, 40, 48
+    feat = rng.standard_normal((Bm, C, Hf, Wf), dtype=np.float32)
+    n = 3400                                            # x 5 channel tiles = 17 000 tiles
+    boxes = synth.random_boxes(rng, n, 1280, 1536)
+    edge = synth.edge_case_boxes(1280, 1536)
+    boxes[100:100 + len(edge)] = edge
+    boxes[500:540] = [[0, 0, 1536, 1280]] * 40          # whole map
+    boxes[900:940, 2:] = boxes[900:940, :2] + rng.uniform(300, 700, (40, 2))
+    bidx = rng.integers(0, Bm, (n, 1)).astype(np.float64)
+    bidx[1200:1204] = [[-1], [3], [7], [-2]]
+    rois = np.concatenate([bidx, boxes], 1).astype(np.float32)
+    good = (bidx[:, 0] >= 0) & (bidx[:, 0] < Bm)
+    want = np.zeros((n, C, ps[0], ps[1]), np.float32)
+    want[good] = native.roi_align(feat, rois[good], ps, 40 / 1280.0, 2, True)
+    got = _run(feat, rois, ps, 40 / 1280.0, 2, True, nhwc)
+    assert_close(got, want, rtol=1e-5, atol=2e-6, what="large launch %s nhwc=%s" % (ps, nhwc))
+
+
+@pytest.mark.parametrize("nhwc", [False, True])
 def test_roi_huge_footprints_take_the_exact_fallbacks(nhwc):
     """Whole-map boxes on a 150x140 map: the weight tables no longer fit next to the output tile, so the
     kernel's per-bin path runs; medium boxes on the same map use the unstaged separable path."""
