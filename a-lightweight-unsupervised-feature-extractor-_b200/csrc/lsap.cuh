@@ -16,6 +16,10 @@ namespace b200 {
 namespace lsap {
 
 constexpr int kMaxThreads = 256;
+#ifndef B200_LSAP_WARP_MAX_COLS
+#define B200_LSAP_WARP_MAX_COLS 128
+#endif
+constexpr int kWarpSolverMaxCols = B200_LSAP_WARP_MAX_COLS;   // wider problems use the multi-warp register solver
 
 struct Work {              // all arrays in shared memory, sized for R rows / Cc columns
     double* u;             // [R]
@@ -323,38 +327,173 @@ __device__ inline int solve_warp(const float* cost, int R, int Cc, int ld, doubl
     return B200_OK;
 }
 
+// ---- multi-warp register solver: wide problems ---------------------------------------------------------
+// The same search with the columns spread over nt = 32 * W threads (W <= 8), CPL columns each, all
+// per-column state but the predecessor in registers.  A Dijkstra step is: local best -> warp redux (as in
+// solve_warp) -> the W per-warp candidates go to a double-buffered shared-memory slot -> ONE named barrier ->
+// every thread combines the W candidates with the same (distance, tie-key) order and applies the removal to
+// its own registers.  The augmentation walks pred / col4row / row4col in shared memory on thread 0 while the
+// other threads apply the dual update; one more barrier ends the search.  Exactness argument as above: the
+// combine is the associative (min distance, then scipy's tie rule) order.
+template <int CPL>
+__device__ inline int solve_regs(const float* cost, int R, int Cc, int ld, const Work& w, int tid, int nt) {
+    __shared__ __align__(16) unsigned slot[2][kMaxThreads / 32][8];
+    const unsigned kFull = 0xffffffffu;
+    const double kInf = __longlong_as_double(0x7ff0000000000000LL);
+    const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+    double v[CPL], dist[CPL];
+    int r4c[CPL], pos[CPL];
+#pragma unroll
+    for (int q = 0; q < CPL; ++q) { v[q] = 0.0; r4c[q] = -1; }
+    for (int i = tid; i < R; i += nt) { w.u[i] = 0.0; w.c4r[i] = -1; }
+    for (int j = tid; j < Cc; j += nt) { w.r4c[j] = -1; w.pred[j] = -1; }
+    group_sync(nt);
+    int par = 0;
+    for (int cur = 0; cur < R; ++cur) {
+#pragma unroll
+        for (int q = 0; q < CPL; ++q) {
+            const int j = tid + nt * q;
+            pos[q] = j < Cc ? Cc - 1 - j : -1;
+            dist[q] = kInf;
+        }
+        if (cur + 1 < R && tid * 32 < Cc)                // the matrix may sit in L2: pull the next first row closer
+            asm volatile("prefetch.L1 [%0];" ::"l"(cost + (size_t)(cur + 1) * ld + tid * 32));
+        unsigned scanned = 0;
+        int i = cur, n_todo = Cc, sink = -1;
+        double minv = 0.0;
+        while (sink < 0) {
+            const double ui = w.u[i];
+            const float* crow = cost + (size_t)i * ld;
+            unsigned long long bk = ~0ull;
+            unsigned bt = 0xffffffffu;
+            int bq = 0;
+#pragma unroll
+            for (int q = 0; q < CPL; ++q) {
+                if (pos[q] >= 0) {
+                    const int j = tid + nt * q;
+                    const double r = ((minv + (double)crow[j]) - ui) - v[q];
+                    if (r < dist[q]) { dist[q] = r; w.pred[j] = i; }
+                    const unsigned long long k = dist_key(dist[q]);
+                    const unsigned t = tie_key(pos[q], r4c[q] < 0);
+                    if (k < bk || (k == bk && t < bt)) { bk = k; bt = t; bq = q; }
+                }
+            }
+            const unsigned hi = (unsigned)(bk >> 32), lo = (unsigned)bk;
+            const unsigned mh = __reduce_min_sync(kFull, hi);
+            const unsigned ml = __reduce_min_sync(kFull, hi == mh ? lo : 0xffffffffu);
+            bool cand = hi == mh && lo == ml && bt != 0xffffffffu;
+            unsigned who = __ballot_sync(kFull, cand);
+            if (__popc(who) > 1) {
+                const unsigned mt = __reduce_min_sync(kFull, cand ? bt : 0xffffffffu);
+                cand = cand && bt == mt;
+                who = __ballot_sync(kFull, cand);
+            }
+            if (lane == (who ? __ffs(who) - 1 : 0)) {      // this warp's candidate (or "none")
+                int pj = 0, pp = 0, pr = 0;
+#pragma unroll
+                for (int q = 0; q < CPL; ++q)
+                    if (q == bq) { pj = tid + nt * q; pp = pos[q]; pr = r4c[q]; }
+                uint4* sl = reinterpret_cast<uint4*>(slot[par][wid]);
+                sl[0] = make_uint4(who ? mh : 0xffffffffu, who ? ml : 0xffffffffu, who ? bt : 0xffffffffu, (unsigned)pj);
+                sl[1] = make_uint4((unsigned)pp, (unsigned)pr, 0u, 0u);
+            }
+            group_sync(nt);
+            unsigned gh = 0xffffffffu, gl = 0xffffffffu, gt = 0xffffffffu;
+            int gw = 0, j = 0;
+            for (int ww = 0; ww < nw; ++ww) {
+                const uint4 c = reinterpret_cast<const uint4*>(slot[par][ww])[0];
+                if (c.x < gh || (c.x == gh && (c.y < gl || (c.y == gl && c.z < gt)))) {
+                    gh = c.x; gl = c.y; gt = c.z; j = (int)c.w; gw = ww;
+                }
+            }
+            minv = key_dist(((unsigned long long)gh << 32) | gl);
+            if (gt == 0xffffffffu || minv == kInf) return B200_EINFEASIBLE;      // uniform across the group
+            const uint4 c1 = reinterpret_cast<const uint4*>(slot[par][gw])[1];
+            const int freed = (int)c1.x, rj = (int)c1.y;
+            par ^= 1;
+            --n_todo;
+#pragma unroll
+            for (int q = 0; q < CPL; ++q) {
+                if (tid + nt * q == j) { pos[q] = -1; scanned |= 1u << q; }
+                else if (pos[q] == n_todo) pos[q] = freed;
+            }
+            if (rj < 0) sink = j; else i = rj;
+        }
+        if (tid == 0) {                                   // augment along the predecessor chain
+            w.u[cur] += minv;
+            int j = sink;
+            for (;;) {
+                const int r = w.pred[j];
+                w.r4c[j] = r;
+                const int prev = w.c4r[r];
+                w.c4r[r] = j;
+                j = prev;
+                if (r == cur) break;
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < CPL; ++q)
+            if (scanned & (1u << q)) {
+                const double delta = minv - dist[q];
+                if (r4c[q] >= 0) w.u[r4c[q]] += delta;
+                v[q] -= delta;
+            }
+        group_sync(nt);
+#pragma unroll
+        for (int q = 0; q < CPL; ++q)
+            if (tid + nt * q < Cc) r4c[q] = w.r4c[tid + nt * q];
+    }
+    return B200_OK;
+}
+
 // Block-level driver shared by the operator kernel and the tracker: validates the matrix (all
 // threads, flattened so loads overlap), optionally stages it in shared memory, then runs the
-// single-warp solver (Cc <= 256) or the multi-warp one.  Every thread of the CTA must call; the
+// single-warp solver (Cc <= 128), the multi-warp register solver (up to 4 columns per thread) or, beyond
+// that, the shared-memory one.  Measured on B200 (association step, one stream): 64 columns 135 us (warp) vs
+// 149 us (multi-warp); 128: 213 vs 220; 256: 752 vs 392; 512: 1 387 (shared-memory solver) vs 897.  Every thread of the CTA must call; the
 // status is returned on every thread and w.c4r / w.r4c hold the assignment.
 __device__ inline int solve_block(const float* cost, int R, int Cc, int ld, const Work& w, float* stage_or_null) {
     const int tid = threadIdx.x, nthr = blockDim.x;
     int bad = 0;
-    const int total = R * Cc;
+    const float kNegInf = -__int_as_float(0x7f800000);
+    if (!stage_or_null && ((Cc | ld) & 3) == 0 && (reinterpret_cast<uintptr_t>(cost) & 15) == 0) {
+        const int c4 = Cc >> 2, total4 = R * c4;       // large matrix left in L2: 16-byte loads, eight in flight
+#pragma unroll 8
+        for (int idx = tid; idx < total4; idx += nthr) {
+            const int i = idx / c4, j = idx - i * c4;
+            const float4 c = reinterpret_cast<const float4*>(cost + (size_t)i * ld)[j];
+            if (c.x != c.x || c.y != c.y || c.z != c.z || c.w != c.w || c.x == kNegInf || c.y == kNegInf ||
+                c.z == kNegInf || c.w == kNegInf)
+                bad = 1;
+        }
+    } else {
+        const int total = R * Cc;
 #pragma unroll 4
-    for (int idx = tid; idx < total; idx += nthr) {
-        const int i = idx / Cc, j = idx - i * Cc;
-        const float c = cost[(size_t)i * ld + j];
-        if (c != c || c == -__int_as_float(0x7f800000)) bad = 1;
-        if (stage_or_null) stage_or_null[idx] = c;
+        for (int idx = tid; idx < total; idx += nthr) {
+            const int i = idx / Cc, j = idx - i * Cc;
+            const float c = cost[(size_t)i * ld + j];
+            if (c != c || c == kNegInf) bad = 1;
+            if (stage_or_null) stage_or_null[idx] = c;
+        }
     }
     bad = __syncthreads_or(bad);
     if (bad) return B200_ENUMERIC;
     if (stage_or_null) { cost = stage_or_null; ld = Cc; }
     __shared__ int s_status;
-    if (Cc <= 256) {
+    const int nt = nthr < kMaxThreads ? (nthr & ~31) : kMaxThreads;
+    if (Cc <= kWarpSolverMaxCols) {
         if (tid < 32) {
             const int rc = Cc <= 64    ? solve_warp<2>(cost, R, Cc, ld, w.u, w.c4r, w.r4c)
-                           : Cc <= 128 ? solve_warp<4>(cost, R, Cc, ld, w.u, w.c4r, w.r4c)
-                                       : solve_warp<8>(cost, R, Cc, ld, w.u, w.c4r, w.r4c);
+                                       : solve_warp<4>(cost, R, Cc, ld, w.u, w.c4r, w.r4c);
             if (tid == 0) s_status = rc;
         }
-    } else {
-        const int nt = nthr < kMaxThreads ? (nthr & ~31) : kMaxThreads;
-        if (tid < nt) {
-            const int rc = solve(cost, R, Cc, ld, w, tid, nt, true);
-            if (tid == 0) s_status = rc;
-        }
+    } else if (tid < nt) {
+        const int per = (Cc + nt - 1) / nt;
+        const int rc = per <= 1   ? solve_regs<1>(cost, R, Cc, ld, w, tid, nt)
+                       : per <= 2 ? solve_regs<2>(cost, R, Cc, ld, w, tid, nt)
+                       : per <= 4 ? solve_regs<4>(cost, R, Cc, ld, w, tid, nt)
+                                  : solve(cost, R, Cc, ld, w, tid, nt, true);
+        if (tid == 0) s_status = rc;
     }
     __syncthreads();
     return s_status;

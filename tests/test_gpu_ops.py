@@ -48,6 +48,12 @@ def test_lsap_ties_and_degenerate_exact_vs_oracle():
     rng = np.random.default_rng(2)
     mats = [np.zeros((9, 9), np.float32), np.ones((5, 12), np.float32), np.full((40, 40), 1e9, np.float32)]
     mats += [rng.integers(0, 3, (m, n)).astype(np.float32) for m, n in [(17, 17), (33, 20), (20, 33), (70, 140)]]
+    # 257..512 columns: the 16-columns-per-lane warp solver (ties, a NaN-free but -0.0 / inf-sprinkled matrix)
+    mats += [rng.integers(0, 4, (m, n)).astype(np.float32) for m, n in [(260, 260), (300, 512), (400, 290), (512, 511)]]
+    wide = rng.integers(0, 50, (384, 448)).astype(np.float32)
+    wide[rng.random(wide.shape) < 0.3] = np.inf
+    wide[np.arange(384), rng.permutation(448)[:384]] = -0.0
+    mats.append(wide)
     for C in mats:
         c4r, _ = native.lsap(C)
         col, _, st = hung.lsap_batched(torch.from_numpy(C).cuda()[None], 1e9)
