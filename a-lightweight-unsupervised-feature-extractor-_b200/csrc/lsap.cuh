@@ -203,6 +203,19 @@ __device__ inline int solve(const float* cost, int R, int Cc, int ld, const Work
 }
 
 
+// ---- rows whose search is known in advance ---------------------------------------------------------------
+// The search for row `cur` starts with minv = 0 and u[cur] = 0, so its first Dijkstra step sees the reduced
+// costs c[cur][j] - v[j].  Column duals only ever decrease (v[j] -= minv - dist[j] with minv >= dist[j]), and
+// only for columns scanned by a search of length > 1.  Hence, if the row's smallest entry is attained by ONE
+// column fj, that column is still unassigned and v[fj] == 0 (and no v[j] > 0 has ever appeared, which rounding
+// could produce in principle), every other reduced cost is strictly larger, the step selects fj whatever the
+// tie rule says, fj is the sink, and the search degenerates to: u[cur] = c[cur][fj], col4row[cur] = fj,
+// row4col[fj] = cur, v untouched (minv - dist[fj] == 0).  solve_block computes (fj, unique?) for all rows in
+// parallel while it validates the matrix; the solvers take the shortcut when its premises hold and run the
+// full search otherwise, so the result is still scipy's, step for step.  In a tracker's steady state (one
+// clearly best detection per track) almost every row takes it.
+__device__ __forceinline__ double first_step_dual(float c) { return 0.0 + (((0.0 + (double)c) - 0.0) - 0.0); }
+
 // ---- single-warp solver: all per-column state in registers -------------------------------------
 // Same algorithm and tie rule as solve(), for Cc <= 32 * CPL columns.  Lane l owns columns
 // l, l+32, ...; for each it keeps dist, v, pred, r4c and the column's POSITION in scipy's
@@ -226,7 +239,8 @@ __device__ __forceinline__ double key_dist(unsigned long long k) {
 __device__ __forceinline__ unsigned tie_key(int it, bool un) { return un ? (0xFFFFu - (unsigned)it) : (0x10000u | (unsigned)it); }
 
 template <int CPL>
-__device__ inline int solve_warp(const float* cost, int R, int Cc, int ld, double* u_s, int* c4r_s, int* r4c_s) {
+__device__ inline int solve_warp(const float* cost, int R, int Cc, int ld, double* u_s, int* c4r_s, int* r4c_s,
+                                 const int* first_col, const float* first_val) {
     const unsigned kFull = 0xffffffffu;
     const double kInf = __longlong_as_double(0x7ff0000000000000LL);
     const int lane = threadIdx.x & 31;
@@ -236,7 +250,26 @@ __device__ inline int solve_warp(const float* cost, int R, int Cc, int ld, doubl
     for (int q = 0; q < CPL; ++q) { v[q] = 0.0; r4c[q] = -1; pred[q] = -1; }
     for (int i = lane; i < R; i += 32) { u_s[i] = 0.0; c4r_s[i] = -1; }
     __syncwarp();
+    bool v_positive = false;                             // some v[j] > 0 appeared: no more shortcuts
     for (int cur = 0; cur < R; ++cur) {
+        const int fj = first_col[cur];
+        if (fj >= 0 && !v_positive) {                    // known first step (see above)
+            bool ok = false;
+            if (lane == (fj & 31)) {
+#pragma unroll
+                for (int q = 0; q < CPL; ++q)
+                    if (q == (fj >> 5)) ok = r4c[q] < 0 && v[q] == 0.0;
+            }
+            if (__ballot_sync(kFull, ok)) {
+                if (ok) {
+#pragma unroll
+                    for (int q = 0; q < CPL; ++q)
+                        if (q == (fj >> 5)) r4c[q] = cur;
+                }
+                if (lane == 0) { u_s[cur] = first_step_dual(first_val[cur]); c4r_s[cur] = fj; }
+                continue;
+            }
+        }
 #pragma unroll
         for (int q = 0; q < CPL; ++q) {
             const int j = lane + 32 * q;
@@ -293,13 +326,16 @@ __device__ inline int solve_warp(const float* cost, int R, int Cc, int ld, doubl
         // dual update: u[cur] += minv; for every scanned column j with a row: u[r4c[j]] += minv - dist[j];
         // v[j] -= minv - dist[j]  (the sink column has dist == minv, so it does not move)
         if (lane == 0) u_s[cur] += minv;
+        bool vp = false;
 #pragma unroll
         for (int q = 0; q < CPL; ++q)
             if (scanned & (1u << q)) {
                 const double delta = minv - dist[q];
                 if (r4c[q] >= 0) u_s[r4c[q]] += delta;
                 v[q] -= delta;
+                vp = vp || v[q] > 0.0;
             }
+        v_positive = v_positive || __any_sync(kFull, vp);
         // augment along the predecessor chain; only lane 0 touches col4row
         int j = sink;
         for (;;) {
@@ -345,16 +381,35 @@ __device__ inline int solve_regs(const float* cost, int R, int Cc, int ld, const
     int r4c[CPL], pos[CPL];
 #pragma unroll
     for (int q = 0; q < CPL; ++q) { v[q] = 0.0; r4c[q] = -1; }
+    const int* first_col = w.seen_rows;                   // filled by solve_block
+    const float* first_val = reinterpret_cast<const float*>(w.dist);
     for (int i = tid; i < R; i += nt) { w.u[i] = 0.0; w.c4r[i] = -1; }
-    for (int j = tid; j < Cc; j += nt) { w.r4c[j] = -1; w.pred[j] = -1; }
+    for (int j = tid; j < Cc; j += nt) { w.r4c[j] = -1; w.pred[j] = -1; w.v[j] = 0.0; }
+    if (tid == 0) w.red_un[0] = 0;                        // "some v[j] > 0 appeared"
     group_sync(nt);
     int par = 0;
-    for (int cur = 0; cur < R; ++cur) {
+    for (int cur = 0;; ++cur) {
+        if (tid == 0) {                                   // run of rows with a known first step (see above)
+            int c = cur;
+            if (!w.red_un[0])
+                for (; c < R; ++c) {
+                    const int fj = first_col[c];
+                    if (fj < 0 || w.r4c[fj] >= 0 || w.v[fj] != 0.0) break;
+                    w.r4c[fj] = c;
+                    w.c4r[c] = fj;
+                    w.u[c] = first_step_dual(first_val[c]);
+                }
+            *w.flag = c;
+        }
+        group_sync(nt);
+        cur = *w.flag;
+        if (cur >= R) break;
 #pragma unroll
         for (int q = 0; q < CPL; ++q) {
             const int j = tid + nt * q;
             pos[q] = j < Cc ? Cc - 1 - j : -1;
             dist[q] = kInf;
+            if (j < Cc) r4c[q] = w.r4c[j];
         }
         if (cur + 1 < R && tid * 32 < Cc)                // the matrix may sit in L2: pull the next first row closer
             asm volatile("prefetch.L1 [%0];" ::"l"(cost + (size_t)(cur + 1) * ld + tid * 32));
@@ -437,44 +492,49 @@ __device__ inline int solve_regs(const float* cost, int R, int Cc, int ld, const
                 const double delta = minv - dist[q];
                 if (r4c[q] >= 0) w.u[r4c[q]] += delta;
                 v[q] -= delta;
+                w.v[tid + nt * q] = v[q];
+                if (v[q] > 0.0) w.red_un[0] = 1;
             }
         group_sync(nt);
-#pragma unroll
-        for (int q = 0; q < CPL; ++q)
-            if (tid + nt * q < Cc) r4c[q] = w.r4c[tid + nt * q];
     }
     return B200_OK;
 }
 
-// Block-level driver shared by the operator kernel and the tracker: validates the matrix (all
-// threads, flattened so loads overlap), optionally stages it in shared memory, then runs the
+// Block-level driver shared by the operator kernel and the tracker: validates the matrix, optionally
+// stages it in shared memory and finds every row's unique minimum (all warps, a row each), then runs the
 // single-warp solver (Cc <= 128), the multi-warp register solver (up to 4 columns per thread) or, beyond
 // that, the shared-memory one.  Measured on B200 (association step, one stream): 64 columns 135 us (warp) vs
 // 149 us (multi-warp); 128: 213 vs 220; 256: 752 vs 392; 512: 1 387 (shared-memory solver) vs 897.  Every thread of the CTA must call; the
 // status is returned on every thread and w.c4r / w.r4c hold the assignment.
 __device__ inline int solve_block(const float* cost, int R, int Cc, int ld, const Work& w, float* stage_or_null) {
-    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31;
     int bad = 0;
     const float kNegInf = -__int_as_float(0x7f800000);
-    if (!stage_or_null && ((Cc | ld) & 3) == 0 && (reinterpret_cast<uintptr_t>(cost) & 15) == 0) {
-        const int c4 = Cc >> 2, total4 = R * c4;       // large matrix left in L2: 16-byte loads, eight in flight
-#pragma unroll 8
-        for (int idx = tid; idx < total4; idx += nthr) {
-            const int i = idx / c4, j = idx - i * c4;
-            const float4 c = reinterpret_cast<const float4*>(cost + (size_t)i * ld)[j];
-            if (c.x != c.x || c.y != c.y || c.z != c.z || c.w != c.w || c.x == kNegInf || c.y == kNegInf ||
-                c.z == kNegInf || c.w == kNegInf)
-                bad = 1;
-        }
-    } else {
-        const int total = R * Cc;
+    int* first_col = w.seen_rows;                         // [R] column of the row's unique minimum, or -1
+    float* first_val = reinterpret_cast<float*>(w.dist);  // [R] that minimum
+    // One pass over the matrix, a warp per row: NaN / -inf check, optional copy to shared memory, row minimum.
+    for (int i = tid >> 5; i < R; i += nthr >> 5) {
+        const float* row = cost + (size_t)i * ld;
+        float m = __int_as_float(0x7f800000);
+        int mj = -1, cnt = 0;
 #pragma unroll 4
-        for (int idx = tid; idx < total; idx += nthr) {
-            const int i = idx / Cc, j = idx - i * Cc;
-            const float c = cost[(size_t)i * ld + j];
+        for (int j = lane; j < Cc; j += 32) {
+            const float c = row[j];
             if (c != c || c == kNegInf) bad = 1;
-            if (stage_or_null) stage_or_null[idx] = c;
+            if (stage_or_null) stage_or_null[i * Cc + j] = c;
+            if (c < m) { m = c; mj = j; cnt = 1; }
+            else if (c == m) ++cnt;
         }
+        const unsigned bits = (unsigned)__float_as_int(m + 0.0f);                      // -0.0 ties with +0.0
+        const unsigned key = bits ^ ((unsigned)((int)bits >> 31) | 0x80000000u);      // order-preserving
+        const unsigned kmin = __reduce_min_sync(0xffffffffu, key);
+        const unsigned eq = __ballot_sync(0xffffffffu, key == kmin && mj >= 0);
+        if (eq && lane == __ffs(eq) - 1) {
+            const bool unique = __popc(eq) == 1 && cnt == 1 && m < __int_as_float(0x7f800000);
+            first_col[i] = unique ? mj : -1;
+            first_val[i] = m;
+        }
+        if (!eq && lane == 0) first_col[i] = -1;
     }
     bad = __syncthreads_or(bad);
     if (bad) return B200_ENUMERIC;
@@ -483,8 +543,8 @@ __device__ inline int solve_block(const float* cost, int R, int Cc, int ld, cons
     const int nt = nthr < kMaxThreads ? (nthr & ~31) : kMaxThreads;
     if (Cc <= kWarpSolverMaxCols) {
         if (tid < 32) {
-            const int rc = Cc <= 64    ? solve_warp<2>(cost, R, Cc, ld, w.u, w.c4r, w.r4c)
-                                       : solve_warp<4>(cost, R, Cc, ld, w.u, w.c4r, w.r4c);
+            const int rc = Cc <= 64 ? solve_warp<2>(cost, R, Cc, ld, w.u, w.c4r, w.r4c, first_col, first_val)
+                                    : solve_warp<4>(cost, R, Cc, ld, w.u, w.c4r, w.r4c, first_col, first_val);
             if (tid == 0) s_status = rc;
         }
     } else if (tid < nt) {

@@ -60,6 +60,36 @@ def test_lsap_ties_and_degenerate_exact_vs_oracle():
         assert int(st[0]) == 0 and np.array_equal(col[0].cpu().numpy().astype(np.int64), c4r)
 
 
+@pytest.mark.parametrize("n", [8, 64, 100, 128, 200, 300, 512])
+def test_lsap_known_first_step_shortcut_is_exact(n):
+    """Tracker-like matrices: most rows have one clearly best column (the solvers skip their search), some
+    rows compete for the same column (full search, duals move, later shortcuts must notice), some rows tie,
+    some minima are -0.0 / +0.0 pairs.  Column-for-column equality with the scipy restatement."""
+    rng = np.random.default_rng(n)
+    mats = []
+    for conflict, density in [(0.0, 0.02), (0.3, 0.05), (0.6, 0.3), (0.1, 1.0)]:
+        m = n - n // 7
+        C = np.full((m, n), 1e9, np.float32)
+        mask = rng.random((m, n)) < density
+        C[mask] = rng.uniform(0.5, 2.0, int(mask.sum())).astype(np.float32)
+        perm = rng.permutation(n)[:m]
+        clash = rng.random(m) < conflict
+        perm[clash] = rng.choice(perm, int(clash.sum()))           # several rows want the same column
+        C[np.arange(m), perm] = rng.uniform(0.05, 0.3, m).astype(np.float32)
+        mats += [C, np.ascontiguousarray(C.T)]
+    T = rng.integers(0, 5, (n, n)).astype(np.float32) + 1.0        # ties everywhere, unique minima in some rows
+    rows = rng.choice(n, n // 2, replace=False)
+    T[rows, rng.integers(0, n, n // 2)] = 0.5
+    Z = rng.uniform(1, 2, (n, n)).astype(np.float32)               # -0.0 next to +0.0 must count as a tie
+    Z[:, 0] = -0.0
+    Z[:, n - 1] = 0.0
+    mats += [T, Z]
+    for C in mats:
+        want, _ = native.lsap(C)
+        col, _, st = hung.lsap_batched(torch.from_numpy(C).cuda()[None], 1e9)
+        assert int(st[0]) == 0 and np.array_equal(col[0].cpu().numpy().astype(np.int64), want), C.shape
+
+
 def test_lsap_batched_and_errors():
     rng = np.random.default_rng(4)
     C = np.stack([synth.lsap_matrix(rng, 40, 48, 0.6) for _ in range(9)])
