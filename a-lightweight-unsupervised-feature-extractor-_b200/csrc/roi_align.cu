@@ -24,6 +24,7 @@
 #include <cuda_fp16.h>
 
 #include "common.cuh"
+#include <type_traits>
 
 namespace b200 {
 namespace {
@@ -264,29 +265,18 @@ roi_prep_kernel(const float* __restrict__ rois, long long K, int B, int H, int W
 #define B200_ROI_MIN_CTAS 6
 #endif
 
+// One (ROI k, channels c0 .. c0+cn) tile, start to finish, by one warp.  sMain: L::kMainFloats floats (V staging /
+// big tables, later the output tile), sTab: L::kTabFloats floats; both private to the warp.
 template <int PH, int PW, bool NHWC, typename T, bool PREP>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, (B200_ROI_MIN_CTAS * 2 + kWarpsPerCta - 1) / kWarpsPerCta)
-roi_align_tile_kernel(const T* __restrict__ feat, int B, int C, int H, int W,
-                      const float* __restrict__ rois, long long K, float scale, int sr, int aligned,
-                      T* __restrict__ out, int ctiles, const RoiPrep* __restrict__ prep,
-                      const float* __restrict__ prep_tabs) {
+__device__ __forceinline__ void process_tile(const T* __restrict__ feat, int B, int C, int H, int W,
+                                             const float* __restrict__ rois, float scale, int sr, int aligned,
+                                             T* __restrict__ out, long long k, int c0, int cn,
+                                             const RoiPrep* __restrict__ prep, const float* __restrict__ prep_tabs,
+                                             float* sMain, float* sTab, int lane) {
     constexpr bool kF32 = sizeof(T) == 4;
     using L = TileSmem<PH, PW>;
     constexpr int PHP = L::kPHP, PWP = L::kPWP, NB = PH * PW;
     static_assert(PH <= 16 && PW <= 16, "one lane per output row/column");
-    extern __shared__ __align__(16) float smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // Warps are independent: no block-wide barriers anywhere below.
-    const long long wi = (long long)blockIdx.x * kWarpsPerCta + warp;
-    if (wi >= K * ctiles) return;
-    const int span_slot = (int)((reinterpret_cast<uintptr_t>(rois) / (size_t)(K * 20)) & 7);   // debug: step index mod 8
-    B200_SPAN_BEGIN(span_slot);
-    float* sMain = smem + (size_t)warp * L::kFloatsPerWarp;   // V staging / big tables, later the output tile
-    float* sTab = sMain + L::kMainFloats;
-    const unsigned wi32 = (unsigned)wi;       // the launcher keeps the tile count below 2^31
-    const long long k = wi32 / (unsigned)ctiles;
-    const int c0 = (int)(wi32 % (unsigned)ctiles) * 32;
-    const int cn = min(32, C - c0);
     Geom g;
     float inv = 0.0f;
     int ymin = 0, xmin = 0, FY = 0, FX = 0;
@@ -463,6 +453,190 @@ roi_align_tile_kernel(const T* __restrict__ feat, int B, int C, int H, int W,
         const T* tile = reinterpret_cast<const T*>(sMain);
         for (int i = lane; i < cn * NB; i += 32) gdst[i] = tile[i];
     }
+}
+
+template <int PH, int PW, bool NHWC, typename T, bool PREP>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, (B200_ROI_MIN_CTAS * 2 + kWarpsPerCta - 1) / kWarpsPerCta)
+roi_align_tile_kernel(const T* __restrict__ feat, int B, int C, int H, int W,
+                      const float* __restrict__ rois, long long K, float scale, int sr, int aligned,
+                      T* __restrict__ out, int ctiles, const RoiPrep* __restrict__ prep,
+                      const float* __restrict__ prep_tabs) {
+    using L = TileSmem<PH, PW>;
+    extern __shared__ __align__(16) float smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // Warps are independent: no block-wide barriers anywhere below.
+    const long long wi = (long long)blockIdx.x * kWarpsPerCta + warp;
+    if (wi >= K * ctiles) return;
+    const int span_slot = (int)((reinterpret_cast<uintptr_t>(rois) / (size_t)(K * 20)) & 7);   // debug: step index mod 8
+    B200_SPAN_BEGIN(span_slot);
+    float* sMain = smem + (size_t)warp * L::kFloatsPerWarp;
+    const unsigned wi32 = (unsigned)wi;       // the launcher keeps the tile count below 2^31
+    const long long k = wi32 / (unsigned)ctiles;
+    const int c0 = (int)(wi32 % (unsigned)ctiles) * 32;
+    process_tile<PH, PW, NHWC, T, PREP>(feat, B, C, H, W, rois, scale, sr, aligned, out, k, c0, min(32, C - c0), prep,
+                                        prep_tabs, sMain, sMain + L::kMainFloats, lane);
+    B200_SPAN_END(span_slot);
+}
+
+// ---- software-pipelined persistent kernel: large float32 launches -------------------------------------
+// Once roi_prep_kernel has done the per-ROI work, a tile in the kernel above is three dependent memory round
+// trips (record -> footprint + tables -> drain of the bulk store) around ~1 000 instructions of arithmetic,
+// and the 168-register warps that sit through them cap an SM at 12 tiles in flight.  Here a warp walks many
+// tiles (grid = what is resident at once) and keeps TWO footprint buffers: while it accumulates tile n from
+// one, the cp.asyncs of tile n+1 fill the other and the record of tile n+2 is on its way to registers.  The
+// buffers fit because there is no separate output tile: the buffer whose V has just been consumed stages the
+// result, 16 channels (one contiguous 16*PH*PW*4-byte block of the NCHW output) at a time, and the warp
+// copies it out with coalesced 16-byte streaming stores.  (Storing straight from registers -- lane c owns
+// the row of channel c0+c -- is a 400-byte-stride scatter: 32 wavefronts per store instruction, 395 us
+// instead of 232 us on the bench launch.)  Tiles whose footprint does not fit a buffer flush the pipeline
+// and go through process_tile() with the warp's whole shared-memory region.
+constexpr int kPipeWarps = 2;
+
+template <int PH, int PW>
+struct PipeSmem {
+    using L = TileSmem<PH, PW>;
+    static constexpr int kBufFloats = kCellCap * 32 + L::kTabFloats;       // V | Wy | Wx of one tile
+    static constexpr int kFloatsPerWarp = 2 * kBufFloats;
+    static constexpr int kBytesPerCta = kFloatsPerWarp * 4 * kPipeWarps;
+    static_assert(kFloatsPerWarp >= L::kFloatsPerWarp, "the fallback path needs an output tile + tables");
+};
+
+template <int PH, int PW, bool NHWC>
+__device__ __forceinline__ void pipe_issue(const float* __restrict__ feat, int C, int H, int W, const int4 h0,
+                                           const int4 h1, long long k, int c0, int cn,
+                                           const float* __restrict__ prep_tabs, unsigned sv, int lane) {
+    using L = TileSmem<PH, PW>;
+    const int b = h0.x, ymin = h0.y, xmin = h0.z, FY = h0.w, FX = h1.x;
+    int nxp = 1;
+    while (nxp < FX) nxp <<= 1;
+    const int cper = 32 / nxp, xmask = nxp - 1;
+    if (NHWC) {
+        const float* row = feat + (((size_t)b * H + ymin) * W + xmin) * C + c0 + lane;
+        unsigned dst = sv;
+        if (lane < cn)
+            for (int r = 0; r < FY; ++r, row += (size_t)W * C) {
+                const float* src = row;
+#pragma unroll 4
+                for (int x = 0; x < FX; ++x, src += C, dst += 128)
+                    cp_async4_s(dst + 4u * ((lane + (x & xmask) * cper) & 31), src);
+            }
+    } else {
+        const int xi = lane & xmask, cs = lane / nxp;
+        const size_t plane = (size_t)H * W, cstep = plane * cper;
+        const float* row = feat + (((size_t)b * C + c0 + cs) * H + ymin) * W + xmin + xi;
+        unsigned dst = sv + 128u * xi;
+        const int skew0 = cs + xi * cper;
+        if (xi < FX)
+            for (int r = 0; r < FY; ++r, row += W, dst += 128u * FX) {
+                const float* src = row;
+                int sk = skew0;
+#pragma unroll 4
+                for (int c = cs; c < cn; c += cper, src += cstep, sk += cper) cp_async4_s(dst + 4u * (sk & 31), src);
+            }
+    }
+    const float* tsrc = prep_tabs + (size_t)k * L::kTabFloats;
+    for (int i = lane; i < L::kTabFloats / 4; i += 32) cp_async16_s(sv + 4u * (kCellCap * 32) + 16u * i, tsrc + 4 * i);
+}
+
+template <int PH, int PW, bool NHWC>
+__global__ void __launch_bounds__(kPipeWarps * 32, (B200_ROI_MIN_CTAS * 2 + kPipeWarps - 1) / kPipeWarps)
+roi_align_pipe_kernel(const float* __restrict__ feat, int B, int C, int H, int W, const float* __restrict__ rois,
+                      long long K, float scale, int sr, int aligned, float* __restrict__ out, int ctiles,
+                      const RoiPrep* __restrict__ prep, const float* __restrict__ prep_tabs) {
+    using L = TileSmem<PH, PW>;
+    using P = PipeSmem<PH, PW>;
+    constexpr int PHP = L::kPHP, NB = PH * PW;
+    static_assert(NB % 4 == 0, "16-byte stores of a lane's output row");
+    extern __shared__ __align__(16) float smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* base = smem + (size_t)warp * P::kFloatsPerWarp;
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(base);
+    const unsigned total = (unsigned)(K * ctiles), stride = gridDim.x * kPipeWarps;
+    unsigned t = blockIdx.x * kPipeWarps + warp;
+    if (t >= total) return;
+    const int span_slot = (int)((reinterpret_cast<uintptr_t>(rois) / (size_t)(K * 20)) & 7);   // debug: step index mod 8
+    B200_SPAN_BEGIN(span_slot);
+
+    // current tile (a*), next tile (n*): ROI index, first channel, prep record
+    unsigned ka = t / (unsigned)ctiles;
+    int ca = (int)(t - ka * (unsigned)ctiles) * 32;
+    int4 a0 = reinterpret_cast<const int4*>(prep + ka)[0], a1 = reinterpret_cast<const int4*>(prep + ka)[1];
+    if (a1.y) pipe_issue<PH, PW, NHWC>(feat, C, H, W, a0, a1, ka, ca, min(32, C - ca), prep_tabs, sbase, lane);
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+    unsigned tn = t + stride, kn = 0;
+    int cnx = 0;
+    int4 n0 = make_int4(0, 0, 0, 0), n1 = n0;
+    if (tn < total) {
+        kn = tn / (unsigned)ctiles;
+        cnx = (int)(tn - kn * (unsigned)ctiles) * 32;
+        n0 = reinterpret_cast<const int4*>(prep + kn)[0];
+        n1 = reinterpret_cast<const int4*>(prep + kn)[1];
+    }
+    int par = 0;
+    for (;;) {
+        const bool have_next = tn < total;
+        const int cn = min(32, C - ca);
+        if (!a1.y) {            // footprint too large for a buffer: nothing is in flight, use the whole region
+            process_tile<PH, PW, NHWC, float, false>(feat, B, C, H, W, rois, scale, sr, aligned, out, (long long)ka, ca,
+                                                     cn, nullptr, nullptr, base, base + L::kMainFloats, lane);
+            __syncwarp();
+        }
+        if (have_next && n1.y)
+            pipe_issue<PH, PW, NHWC>(feat, C, H, W, n0, n1, kn, cnx, min(32, C - cnx), prep_tabs,
+                                     sbase + 4u * (unsigned)((par ^ 1) * P::kBufFloats), lane);
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+        // record of the tile after next: in registers by the time this tile is done
+        const unsigned tm = tn + stride;
+        unsigned km = 0;
+        int cm = 0;
+        int4 m0 = make_int4(0, 0, 0, 0), m1 = m0;
+        if (have_next && tm < total) {
+            km = tm / (unsigned)ctiles;
+            cm = (int)(tm - km * (unsigned)ctiles) * 32;
+            m0 = reinterpret_cast<const int4*>(prep + km)[0];
+            m1 = reinterpret_cast<const int4*>(prep + km)[1];
+        }
+        if (a1.y) {
+            asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+            __syncwarp();
+            const float* sV = base + par * P::kBufFloats;
+            const float* sWy = sV + kCellCap * 32;
+            const int FY = a0.w, FX = a1.x;
+            int nxp = 1;
+            while (nxp < FX) nxp <<= 1;
+            const int cper = 32 / nxp, xmask = nxp - 1;
+            float acc[PH][PW];
+#pragma unroll
+            for (int a = 0; a < PH; ++a)
+#pragma unroll
+                for (int bq = 0; bq < PW; ++bq) acc[a][bq] = 0.0f;
+            separable_accumulate<PH, PW>(acc, sWy, sWy + kFootCap * PHP, FY, FX, [&](int r, int x) {
+                return sV[(r * FX + x) * 32 + ((lane + (x & xmask) * cper) & 31)];
+            });
+            __syncwarp();       // V of this tile is dead: its buffer now stages the output, 16 channels at a time
+            float* so = base + par * P::kBufFloats;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                if ((lane >> 4) == h) {
+                    float4* row = reinterpret_cast<float4*>(so + (lane & 15) * NB);
+#pragma unroll
+                    for (int q = 0; q < NB / 4; ++q)
+                        row[q] = make_float4(acc[(4 * q) / PW][(4 * q) % PW], acc[(4 * q + 1) / PW][(4 * q + 1) % PW],
+                                             acc[(4 * q + 2) / PW][(4 * q + 2) % PW], acc[(4 * q + 3) / PW][(4 * q + 3) % PW]);
+                }
+                __syncwarp();
+                const int nch = min(16, cn - 16 * h);                 // contiguous [nch][PH*PW] block of the result
+                float4* g4 = reinterpret_cast<float4*>(out + ((size_t)ka * C + ca + 16 * h) * NB);
+                for (int i = lane; i < nch * (NB / 4); i += 32) __stcs(g4 + i, reinterpret_cast<const float4*>(so)[i]);
+                __syncwarp();
+            }
+            __syncwarp();       // every lane is done with this buffer before the next iteration refills it
+        }
+        if (!have_next) break;
+        t = tn; ka = kn; ca = cnx; a0 = n0; a1 = n1;
+        tn = tm; kn = km; cnx = cm; n0 = m0; n1 = m1;
+        par ^= 1;
+    }
     B200_SPAN_END(span_slot);
 }
 
@@ -505,6 +679,39 @@ roi_align_generic_kernel(const T* __restrict__ feat, int B, int C, int H, int W,
 // per-ROI work is done once by roi_prep_kernel and shared by the ROI's channel tiles.
 constexpr long long kPrepMinTiles = 16384;
 
+// Launches the pipelined kernel when it applies (channels-last float32 map, PH*PW a multiple of 4, 16-byte
+// aligned output);
+// returns 1 when it does not.
+template <int PH, int PW, bool NHWC, typename T>
+int launch_pipe(const T* feat, int B, int C, int H, int W, const float* rois, long long K, float scale, int sr,
+                int aligned, T* out, int ctiles, const RoiPrep* prep, const float* tabs, long long tiles,
+                cudaStream_t st) {
+    // Channels-last maps only: with NCHW maps the 4-byte plane-strided staging already keeps the LSU pipe ~40 %
+    // busy, and the extra shared-memory pass of the copy-out makes the pipelined kernel slower than the tiled one
+    // (g64 launch: 275 us vs 232 us); channels-last has the headroom (191 us vs 208 us).
+    if constexpr (NHWC && std::is_same<T, float>::value && (PH * PW) % 4 == 0) {
+        using P = PipeSmem<PH, PW>;
+        if (reinterpret_cast<uintptr_t>(out) & 15) return 1;
+        static int resident = 0;             // CTAs the device holds at once (per instantiation)
+        auto kern = roi_align_pipe_kernel<PH, PW, NHWC>;
+        if (!resident) {
+            int dev = 0, sms = 0, per_sm = 0;
+            B200_CUDA(cudaGetDevice(&dev));
+            B200_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+            B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P::kBytesPerCta));
+            B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kPipeWarps * 32, P::kBytesPerCta));
+            resident = sms * (per_sm > 0 ? per_sm : 1);
+        }
+        const long long want = (tiles + kPipeWarps - 1) / kPipeWarps;
+        const unsigned grid = (unsigned)(want < resident ? want : resident);
+        kern<<<grid, kPipeWarps * 32, P::kBytesPerCta, st>>>(feat, B, C, H, W, rois, K, scale, sr, aligned, out, ctiles,
+                                                             prep, tabs);
+        return check_launch("roi_align_pipe_kernel");
+    } else {
+        return 1;
+    }
+}
+
 template <int PH, int PW, bool NHWC, typename T>
 int launch_tile(const T* feat, int B, int C, int H, int W, const float* rois, long long K,
                 float scale, int sr, int aligned, T* out, cudaStream_t st) {
@@ -545,9 +752,12 @@ int launch_tile(const T* feat, int B, int C, int H, int W, const float* rois, lo
     roi_prep_kernel<PH, PW><<<(unsigned)((K + 3) / 4), 128, 0, st>>>(rois, K, B, H, W, scale, sr, aligned, prep, tabs);
     int rc = check_launch("roi_prep_kernel");
     if (rc == B200_OK) {
-        tiled<<<(unsigned)blocks, kWarpsPerCta * 32, L::kBytesPerCta, st>>>(feat, B, C, H, W, rois, K, scale, sr,
-                                                                            aligned, out, ctiles, prep, tabs);
-        rc = check_launch("roi_align_tile_kernel");
+        rc = launch_pipe<PH, PW, NHWC>(feat, B, C, H, W, rois, K, scale, sr, aligned, out, ctiles, prep, tabs, warps, st);
+        if (rc == 1) {                       // no pipelined kernel for this type / size / alignment
+            tiled<<<(unsigned)blocks, kWarpsPerCta * 32, L::kBytesPerCta, st>>>(feat, B, C, H, W, rois, K, scale, sr,
+                                                                                aligned, out, ctiles, prep, tabs);
+            rc = check_launch("roi_align_tile_kernel");
+        }
     }
     B200_CUDA(cudaFreeAsync(ws, st));
     return rc;

@@ -207,7 +207,7 @@ class StreamGroup:
     that frame's ROI launch (in the real pipeline the encoder sits between them), so ROI Align of
     frame t+1 overlaps the association of frame t."""
 
-    def __init__(self, S, n_frames, rank, dev):
+    def __init__(self, S, n_frames, rank, dev, channels_last=False):
         import torch
         import alufe_b200
         from alufe_b200 import _lib
@@ -228,7 +228,9 @@ class StreamGroup:
         self.nmap = max(2, -(-160 // max(1, (S * C * HF * WF * 4) // 1000000)))
         self.nout = max(2, -(-260 // max(1, (S * NBOX * C * PS * PS * 4) // 1000000)))
         gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-        self.maps = torch.randn((self.nmap, S, C, HF, WF), device=dev, generator=gen)
+        self.nhwc = 1 if channels_last else 0          # same values; only the memory order of each map differs
+        self.maps = torch.randn((self.nmap, S, HF, WF, C) if channels_last else (self.nmap, S, C, HF, WF),
+                                device=dev, generator=gen)
         self.outs = torch.empty((self.nout, S * NBOX, C, PS, PS), device=dev)
         self.trk = alufe_b200.MultiStreamTracker(S, alufe_b200.SHIPPED_CONF, max_tracks=256, max_dets=NBOX, device=dev)
         self.results = torch.zeros((n_frames, S, self.trk.stride), dtype=torch.int32, device=dev)
@@ -244,7 +246,7 @@ class StreamGroup:
 
     def roi(self, i):
         P, S, p = ctypes.c_void_p, self.S, self.ptr
-        rc = self.lib.b200_roi_align_fwd_f32(P(p["maps"] + (i % self.nmap) * self.map_b), 0, S, C, HF, WF,
+        rc = self.lib.b200_roi_align_fwd_f32(P(p["maps"] + (i % self.nmap) * self.map_b), self.nhwc, S, C, HF, WF,
                                              P(p["d_rois"] + i * S * NBOX * 20), S * NBOX, PS, PS, HF / float(H_IN), 2, 1,
                                              P(p["outs"] + (i % self.nout) * self.out_b), P(self.sA.cuda_stream))
         if rc:
@@ -428,6 +430,23 @@ def main():
             del g1
         except Exception as exc:                                    # noqa: BLE001
             extra["single_stream_error"] = repr(exc)
+
+    # ---- the same stream group fed channels-last maps (what a channels_last detector would hand over) ----
+    if rank == 0 and world == 1 and not args.no_extra:
+        try:
+            del grp.maps, grp.outs
+            torch.cuda.empty_cache()
+            Kc = min(K, 100)
+            gc = StreamGroup(S, pre + W + Kc, 9000 + rank, dev, channels_last=True)
+            gc.run(0, pre + W)
+            msc, roic = gc.run(pre + W, Kc, n_probe=min(Kc, 16))
+            extra["channels_last_maps"] = {"value": S * Kc / (msc * 1e-3), "unit": "frames/s", "ms_per_step": msc / Kc,
+                                           "roi_us_per_launch": float(np.mean(roic)),
+                                           "roi_frac_of_peak": gc.roi_alg_bytes / float(np.mean(roic)) / 1e3 / peak,
+                                           "kernel": "roi_prep_kernel + roi_align_pipe_kernel<10,10,NHWC>"}
+            del gc
+        except Exception as exc:                                    # noqa: BLE001
+            extra["channels_last_error"] = repr(exc)
 
     # ---- CPU baseline on this box's host cores (rank 0, N == 1 only) ---------------------------------
     cpu = None
