@@ -13,6 +13,7 @@ CSRC = os.path.join(_HERE, "csrc")
 
 OK, EINVAL, ECUDA, ECAPACITY, ENUMERIC, EINFEASIBLE = 0, -1, -2, -3, -4, -5
 LAYOUT_NCHW, LAYOUT_NHWC = 0, 1
+DTYPE_F32, DTYPE_F16 = 0, 1
 
 _lib = None
 
@@ -45,6 +46,7 @@ SIGNATURES = {
     "b200_launch_count": (ctypes.c_int64, []),
     "b200_roi_align_fwd_f32": (_I, [_P, _I, _I, _I, _I, _I, _P, _L, _I, _I, _F, _I, _I, _P, _P]),
     "b200_roi_align_fwd_f16": (_I, [_P, _I, _I, _I, _I, _I, _P, _L, _I, _I, _F, _I, _I, _P, _P]),
+    "b200_roi_align_fwd_ex": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _L, _I, _I, _F, _I, _I, _P, _I, _P]),
     "b200_app_cost_topk_f32": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _I, _P]),
     "b200_pair_cost_f32": (_I, [_P, _P, _P, _P, _P, _I, _I, _F, _F, _F, _F, _F, _F, _P, _P, _P, _P, _P, _I, _P]),
     "b200_kalman_init": (_I, [_P, _I, _P, _P, _P, _P]),

@@ -267,7 +267,7 @@ roi_prep_kernel(const float* __restrict__ rois, long long K, int B, int H, int W
 
 // One (ROI k, channels c0 .. c0+cn) tile, start to finish, by one warp.  sMain: L::kMainFloats floats (V staging /
 // big tables, later the output tile), sTab: L::kTabFloats floats; both private to the warp.
-template <int PH, int PW, bool NHWC, typename T, bool PREP>
+template <int PH, int PW, bool NHWC, typename T, bool PREP, bool OCL = false>
 __device__ __forceinline__ void process_tile(const T* __restrict__ feat, int B, int C, int H, int W,
                                              const float* __restrict__ rois, float scale, int sr, int aligned,
                                              T* __restrict__ out, long long k, int c0, int cn,
@@ -411,6 +411,18 @@ __device__ __forceinline__ void process_tile(const T* __restrict__ feat, int B, 
         __syncwarp();
     }
 
+    if (OCL) {
+        // ---- channels-last result [K][PH][PW][C]: the 32 lanes of a bin are 32 consecutive channels, so every
+        // store instruction is one full 128-byte (64-byte for half) line straight from the accumulators ----------
+        T* gl = out + (size_t)k * NB * C + c0 + lane;
+        if (lane < cn) {
+#pragma unroll
+            for (int a = 0; a < PH; ++a)
+#pragma unroll
+                for (int b = 0; b < PW; ++b) gl[(size_t)(a * PW + b) * C] = from_f<T>(acc[a][b]);
+        }
+        return;
+    }
     // ---- output tile to shared memory (the accumulators already hold the mean) ------------------------
     if (kF32) {
         float* myrow = sMain + lane * NB;
@@ -455,7 +467,7 @@ __device__ __forceinline__ void process_tile(const T* __restrict__ feat, int B, 
     }
 }
 
-template <int PH, int PW, bool NHWC, typename T, bool PREP>
+template <int PH, int PW, bool NHWC, typename T, bool PREP, bool OCL>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, (B200_ROI_MIN_CTAS * 2 + kWarpsPerCta - 1) / kWarpsPerCta)
 roi_align_tile_kernel(const T* __restrict__ feat, int B, int C, int H, int W,
                       const float* __restrict__ rois, long long K, float scale, int sr, int aligned,
@@ -473,16 +485,16 @@ roi_align_tile_kernel(const T* __restrict__ feat, int B, int C, int H, int W,
     const unsigned wi32 = (unsigned)wi;       // the launcher keeps the tile count below 2^31
     const long long k = wi32 / (unsigned)ctiles;
     const int c0 = (int)(wi32 % (unsigned)ctiles) * 32;
-    process_tile<PH, PW, NHWC, T, PREP>(feat, B, C, H, W, rois, scale, sr, aligned, out, k, c0, min(32, C - c0), prep,
-                                        prep_tabs, sMain, sMain + L::kMainFloats, lane);
+    process_tile<PH, PW, NHWC, T, PREP, OCL>(feat, B, C, H, W, rois, scale, sr, aligned, out, k, c0, min(32, C - c0),
+                                             prep, prep_tabs, sMain, sMain + L::kMainFloats, lane);
     B200_SPAN_END(span_slot);
 }
 
 // ---- software-pipelined persistent kernel: large float32 launches -------------------------------------
 // Once roi_prep_kernel has done the per-ROI work, a tile in the kernel above is three dependent memory round
 // trips (record -> footprint + tables -> drain of the bulk store) around ~1 000 instructions of arithmetic,
-// and the 168-register warps that sit through them cap an SM at 12 tiles in flight.  Here a warp walks many
-// tiles (grid = what is resident at once) and keeps TWO footprint buffers: while it accumulates tile n from
+// and the 168-register warps that sit through them cap an SM at 12 tiles in flight.  Here a warp walks a run
+// of consecutive tiles and keeps TWO footprint buffers: while it accumulates tile n from
 // one, the cp.asyncs of tile n+1 fill the other and the record of tile n+2 is on its way to registers.  The
 // buffers fit because there is no separate output tile: the buffer whose V has just been consumed stages the
 // result, 16 channels (one contiguous 16*PH*PW*4-byte block of the NCHW output) at a time, and the warp
@@ -491,6 +503,10 @@ roi_align_tile_kernel(const T* __restrict__ feat, int B, int C, int H, int W,
 // instead of 232 us on the bench launch.)  Tiles whose footprint does not fit a buffer flush the pipeline
 // and go through process_tile() with the warp's whole shared-memory region.
 constexpr int kPipeWarps = 2;
+#ifndef B200_ROI_PIPE_TILES
+#define B200_ROI_PIPE_TILES 8
+#endif
+constexpr int kPipeTilesPerWarp = B200_ROI_PIPE_TILES;
 
 template <int PH, int PW>
 struct PipeSmem {
@@ -538,21 +554,29 @@ __device__ __forceinline__ void pipe_issue(const float* __restrict__ feat, int C
     for (int i = lane; i < L::kTabFloats / 4; i += 32) cp_async16_s(sv + 4u * (kCellCap * 32) + 16u * i, tsrc + 4 * i);
 }
 
-template <int PH, int PW, bool NHWC>
+template <int PH, int PW, bool NHWC, bool OCL>
 __global__ void __launch_bounds__(kPipeWarps * 32, (B200_ROI_MIN_CTAS * 2 + kPipeWarps - 1) / kPipeWarps)
 roi_align_pipe_kernel(const float* __restrict__ feat, int B, int C, int H, int W, const float* __restrict__ rois,
                       long long K, float scale, int sr, int aligned, float* __restrict__ out, int ctiles,
-                      const RoiPrep* __restrict__ prep, const float* __restrict__ prep_tabs) {
+                      const RoiPrep* __restrict__ prep, const float* __restrict__ prep_tabs, int group_warps,
+                      int tiles_per_warp) {
     using L = TileSmem<PH, PW>;
     using P = PipeSmem<PH, PW>;
     constexpr int PHP = L::kPHP, NB = PH * PW;
-    static_assert(NB % 4 == 0, "16-byte stores of a lane's output row");
+    static_assert(OCL || NB % 4 == 0, "16-byte stores of a lane's output row");
     extern __shared__ __align__(16) float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* base = smem + (size_t)warp * P::kFloatsPerWarp;
     const unsigned sbase = (unsigned)__cvta_generic_to_shared(base);
-    const unsigned total = (unsigned)(K * ctiles), stride = gridDim.x * kPipeWarps;
-    unsigned t = blockIdx.x * kPipeWarps + warp;
+    // Warps are taken in groups of `group_warps` (what the device holds at once); a group covers a window of
+    // group_warps * tiles_per_warp consecutive tiles, warp i of the group taking tiles i, i + group_warps, ... of
+    // the window, so at any time the resident warps work on neighbouring ROIs (same maps, same DRAM pages), and
+    // a warp retires after tiles_per_warp tiles so that other streams' kernels (the association chain) get SM
+    // slots every few tens of microseconds.
+    const unsigned gw = blockIdx.x * kPipeWarps + warp, grp = gw / (unsigned)group_warps;
+    const unsigned stride = (unsigned)group_warps, window = stride * (unsigned)tiles_per_warp;
+    unsigned t = grp * window + (gw - grp * stride);
+    const unsigned total = (unsigned)min((long long)(grp + 1) * window, K * ctiles);
     if (t >= total) return;
     const int span_slot = (int)((reinterpret_cast<uintptr_t>(rois) / (size_t)(K * 20)) & 7);   // debug: step index mod 8
     B200_SPAN_BEGIN(span_slot);
@@ -577,8 +601,8 @@ roi_align_pipe_kernel(const float* __restrict__ feat, int B, int C, int H, int W
         const bool have_next = tn < total;
         const int cn = min(32, C - ca);
         if (!a1.y) {            // footprint too large for a buffer: nothing is in flight, use the whole region
-            process_tile<PH, PW, NHWC, float, false>(feat, B, C, H, W, rois, scale, sr, aligned, out, (long long)ka, ca,
-                                                     cn, nullptr, nullptr, base, base + L::kMainFloats, lane);
+            process_tile<PH, PW, NHWC, float, false, OCL>(feat, B, C, H, W, rois, scale, sr, aligned, out, (long long)ka,
+                                                          ca, cn, nullptr, nullptr, base, base + L::kMainFloats, lane);
             __syncwarp();
         }
         if (have_next && n1.y)
@@ -613,10 +637,19 @@ roi_align_pipe_kernel(const float* __restrict__ feat, int B, int C, int H, int W
             separable_accumulate<PH, PW>(acc, sWy, sWy + kFootCap * PHP, FY, FX, [&](int r, int x) {
                 return sV[(r * FX + x) * 32 + ((lane + (x & xmask) * cper) & 31)];
             });
+            if (OCL) {          // channels-last result: full-line stores straight from the accumulators
+                float* gl = out + (size_t)ka * NB * C + ca + lane;
+                if (lane < cn) {
+#pragma unroll
+                    for (int a = 0; a < PH; ++a)
+#pragma unroll
+                        for (int bq = 0; bq < PW; ++bq) __stcs(gl + (size_t)(a * PW + bq) * C, acc[a][bq]);
+                }
+            }
             __syncwarp();       // V of this tile is dead: its buffer now stages the output, 16 channels at a time
             float* so = base + par * P::kBufFloats;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
+            for (int h = 0; h < (OCL ? 0 : 2); ++h) {
                 if ((lane >> 4) == h) {
                     float4* row = reinterpret_cast<float4*>(so + (lane & 15) * NB);
 #pragma unroll
@@ -645,11 +678,16 @@ template <bool NHWC, typename T>
 __global__ void __launch_bounds__(256)
 roi_align_generic_kernel(const T* __restrict__ feat, int B, int C, int H, int W,
                          const float* __restrict__ rois, long long total, int PH, int PW, float scale,
-                         int sr, int aligned, T* __restrict__ out) {
+                         int sr, int aligned, T* __restrict__ out, int out_cl) {
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
-        const int pw = (int)(idx % PW), ph = (int)((idx / PW) % PH);
-        const int c = (int)((idx / ((long long)PW * PH)) % C);
+        // idx is the linear index of the output element in its own layout ([K][C][PH][PW] or [K][PH][PW][C])
+        int pw, ph, c;
+        if (out_cl) {
+            c = (int)(idx % C); pw = (int)((idx / C) % PW); ph = (int)((idx / ((long long)C * PW)) % PH);
+        } else {
+            pw = (int)(idx % PW); ph = (int)((idx / PW) % PH); c = (int)((idx / ((long long)PW * PH)) % C);
+        }
         const long long k = idx / ((long long)PW * PH * C);
         const Geom g = roi_geometry(rois + 5 * k, scale, sr, aligned, PH, PW);
         float s = 0.0f;
@@ -682,43 +720,45 @@ constexpr long long kPrepMinTiles = 16384;
 // Launches the pipelined kernel when it applies (channels-last float32 map, PH*PW a multiple of 4, 16-byte
 // aligned output);
 // returns 1 when it does not.
-template <int PH, int PW, bool NHWC, typename T>
+template <int PH, int PW, bool NHWC, bool OCL, typename T>
 int launch_pipe(const T* feat, int B, int C, int H, int W, const float* rois, long long K, float scale, int sr,
                 int aligned, T* out, int ctiles, const RoiPrep* prep, const float* tabs, long long tiles,
                 cudaStream_t st) {
     // Channels-last maps only: with NCHW maps the 4-byte plane-strided staging already keeps the LSU pipe ~40 %
     // busy, and the extra shared-memory pass of the copy-out makes the pipelined kernel slower than the tiled one
     // (g64 launch: 275 us vs 232 us); channels-last has the headroom (191 us vs 208 us).
-    if constexpr (NHWC && std::is_same<T, float>::value && (PH * PW) % 4 == 0) {
+    if constexpr (NHWC && std::is_same<T, float>::value && (OCL || (PH * PW) % 4 == 0)) {
         using P = PipeSmem<PH, PW>;
-        if (reinterpret_cast<uintptr_t>(out) & 15) return 1;
-        static int resident = 0;             // CTAs the device holds at once (per instantiation)
-        auto kern = roi_align_pipe_kernel<PH, PW, NHWC>;
-        if (!resident) {
+        if (!OCL && (reinterpret_cast<uintptr_t>(out) & 15)) return 1;
+        static int resident_warps = 0;       // warps the device holds at once (per instantiation)
+        auto kern = roi_align_pipe_kernel<PH, PW, NHWC, OCL>;
+        if (!resident_warps) {
             int dev = 0, sms = 0, per_sm = 0;
             B200_CUDA(cudaGetDevice(&dev));
             B200_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
             B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P::kBytesPerCta));
             B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kPipeWarps * 32, P::kBytesPerCta));
-            resident = sms * (per_sm > 0 ? per_sm : 1);
+            resident_warps = sms * (per_sm > 0 ? per_sm : 1) * kPipeWarps;
         }
-        const long long want = (tiles + kPipeWarps - 1) / kPipeWarps;
-        const unsigned grid = (unsigned)(want < resident ? want : resident);
-        kern<<<grid, kPipeWarps * 32, P::kBytesPerCta, st>>>(feat, B, C, H, W, rois, K, scale, sr, aligned, out, ctiles,
-                                                             prep, tabs);
+        const long long window = (long long)resident_warps * kPipeTilesPerWarp;
+        const long long groups = (tiles + window - 1) / window;
+        const long long last = tiles - (groups - 1) * window;                 // tiles in the last window
+        const long long warps = (groups - 1) * resident_warps + (last < resident_warps ? last : resident_warps);
+        kern<<<(unsigned)((warps + kPipeWarps - 1) / kPipeWarps), kPipeWarps * 32, P::kBytesPerCta, st>>>(
+            feat, B, C, H, W, rois, K, scale, sr, aligned, out, ctiles, prep, tabs, resident_warps, kPipeTilesPerWarp);
         return check_launch("roi_align_pipe_kernel");
     } else {
         return 1;
     }
 }
 
-template <int PH, int PW, bool NHWC, typename T>
+template <int PH, int PW, bool NHWC, bool OCL, typename T>
 int launch_tile(const T* feat, int B, int C, int H, int W, const float* rois, long long K,
                 float scale, int sr, int aligned, T* out, cudaStream_t st) {
     using L = TileSmem<PH, PW>;
     static bool configured = false;          // per instantiation; the attribute is idempotent
-    auto fused = roi_align_tile_kernel<PH, PW, NHWC, T, false>;
-    auto tiled = roi_align_tile_kernel<PH, PW, NHWC, T, true>;
+    auto fused = roi_align_tile_kernel<PH, PW, NHWC, T, false, OCL>;
+    auto tiled = roi_align_tile_kernel<PH, PW, NHWC, T, true, OCL>;
     if (!configured) {
         B200_CUDA(cudaFuncSetAttribute(fused, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kBytesPerCta));
         B200_CUDA(cudaFuncSetAttribute(tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kBytesPerCta));
@@ -752,7 +792,7 @@ int launch_tile(const T* feat, int B, int C, int H, int W, const float* rois, lo
     roi_prep_kernel<PH, PW><<<(unsigned)((K + 3) / 4), 128, 0, st>>>(rois, K, B, H, W, scale, sr, aligned, prep, tabs);
     int rc = check_launch("roi_prep_kernel");
     if (rc == B200_OK) {
-        rc = launch_pipe<PH, PW, NHWC>(feat, B, C, H, W, rois, K, scale, sr, aligned, out, ctiles, prep, tabs, warps, st);
+        rc = launch_pipe<PH, PW, NHWC, OCL>(feat, B, C, H, W, rois, K, scale, sr, aligned, out, ctiles, prep, tabs, warps, st);
         if (rc == 1) {                       // no pipelined kernel for this type / size / alignment
             tiled<<<(unsigned)blocks, kWarpsPerCta * 32, L::kBytesPerCta, st>>>(feat, B, C, H, W, rois, K, scale, sr,
                                                                                 aligned, out, ctiles, prep, tabs);
@@ -765,21 +805,30 @@ int launch_tile(const T* feat, int B, int C, int H, int W, const float* rois, lo
 
 template <typename T>
 int roi_align_dispatch(const T* feat, int layout, int B, int C, int H, int W, const float* rois, int64_t K, int PH,
-                       int PW, float spatial_scale, int sampling_ratio, int aligned, T* out, void* stream) {
+                       int PW, float spatial_scale, int sampling_ratio, int aligned, T* out, int out_layout,
+                       void* stream) {
     B200_REQUIRE(layout == B200_LAYOUT_NCHW || layout == B200_LAYOUT_NHWC, "roi_align: bad layout %d", layout);
+    B200_REQUIRE(out_layout == B200_LAYOUT_NCHW || out_layout == B200_LAYOUT_NHWC, "roi_align: bad output layout %d",
+                 out_layout);
     B200_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, "roi_align: bad feature shape [%d,%d,%d,%d]", B, C, H, W);
     B200_REQUIRE(PH > 0 && PW > 0, "roi_align: bad output size (%d,%d)", PH, PW);
     B200_REQUIRE(K >= 0, "roi_align: negative ROI count");
     if (K == 0) return B200_OK;
     B200_REQUIRE(feat && rois && out, "roi_align: null pointer");
     cudaStream_t st = as_stream(stream);
-    const bool nhwc = layout == B200_LAYOUT_NHWC;
-#define B200_TILE(ph, pw)                                                                                  \
-    if (PH == ph && PW == pw)                                                                              \
-        return nhwc ? launch_tile<ph, pw, true, T>(feat, B, C, H, W, rois, K, spatial_scale, sampling_ratio, \
-                                                   aligned, out, st)                                       \
-                    : launch_tile<ph, pw, false, T>(feat, B, C, H, W, rois, K, spatial_scale,              \
-                                                    sampling_ratio, aligned, out, st);
+    const bool nhwc = layout == B200_LAYOUT_NHWC, ocl = out_layout == B200_LAYOUT_NHWC;
+#define B200_TILE(ph, pw)                                                                                            \
+    if (PH == ph && PW == pw) {                                                                                      \
+        if (ocl)                                                                                                     \
+            return nhwc ? launch_tile<ph, pw, true, true, T>(feat, B, C, H, W, rois, K, spatial_scale, sampling_ratio, \
+                                                             aligned, out, st)                                       \
+                        : launch_tile<ph, pw, false, true, T>(feat, B, C, H, W, rois, K, spatial_scale,              \
+                                                              sampling_ratio, aligned, out, st);                     \
+        return nhwc ? launch_tile<ph, pw, true, false, T>(feat, B, C, H, W, rois, K, spatial_scale, sampling_ratio,    \
+                                                          aligned, out, st)                                          \
+                    : launch_tile<ph, pw, false, false, T>(feat, B, C, H, W, rois, K, spatial_scale,                 \
+                                                           sampling_ratio, aligned, out, st);                        \
+    }
     B200_TILE(10, 10)
     B200_TILE(7, 7)
 #undef B200_TILE
@@ -788,10 +837,10 @@ int roi_align_dispatch(const T* feat, int layout, int B, int C, int H, int W, co
     const unsigned blocks = (unsigned)(want < (long long)kSMs * 32 ? want : (long long)kSMs * 32);
     if (nhwc)
         roi_align_generic_kernel<true, T><<<blocks, 256, 0, st>>>(feat, B, C, H, W, rois, total, PH, PW,
-                                                                  spatial_scale, sampling_ratio, aligned, out);
+                                                                  spatial_scale, sampling_ratio, aligned, out, ocl);
     else
         roi_align_generic_kernel<false, T><<<blocks, 256, 0, st>>>(feat, B, C, H, W, rois, total, PH, PW,
-                                                                   spatial_scale, sampling_ratio, aligned, out);
+                                                                   spatial_scale, sampling_ratio, aligned, out, ocl);
     return check_launch("roi_align_generic_kernel");
 }
 
@@ -802,14 +851,29 @@ extern "C" int b200_roi_align_fwd_f32(const float* feat, int layout, int B, int 
                                       const float* rois, int64_t K, int PH, int PW, float spatial_scale,
                                       int sampling_ratio, int aligned, float* out, void* stream) {
     return b200::roi_align_dispatch<float>(feat, layout, B, C, H, W, rois, K, PH, PW, spatial_scale, sampling_ratio,
-                                           aligned, out, stream);
+                                           aligned, out, B200_LAYOUT_NCHW, stream);
 }
 
 extern "C" int b200_roi_align_fwd_f16(const void* feat, int layout, int B, int C, int H, int W,
                                       const float* rois, int64_t K, int PH, int PW, float spatial_scale,
                                       int sampling_ratio, int aligned, void* out, void* stream) {
     return b200::roi_align_dispatch<__half>(static_cast<const __half*>(feat), layout, B, C, H, W, rois, K, PH, PW,
-                                            spatial_scale, sampling_ratio, aligned, static_cast<__half*>(out), stream);
+                                            spatial_scale, sampling_ratio, aligned, static_cast<__half*>(out),
+                                            B200_LAYOUT_NCHW, stream);
+}
+
+extern "C" int b200_roi_align_fwd_ex(const void* feat, int dtype, int layout, int B, int C, int H, int W,
+                                     const float* rois, int64_t K, int PH, int PW, float spatial_scale,
+                                     int sampling_ratio, int aligned, void* out, int out_layout, void* stream) {
+    if (dtype == B200_DTYPE_F32)
+        return b200::roi_align_dispatch<float>(static_cast<const float*>(feat), layout, B, C, H, W, rois, K, PH, PW,
+                                               spatial_scale, sampling_ratio, aligned, static_cast<float*>(out),
+                                               out_layout, stream);
+    if (dtype == B200_DTYPE_F16)
+        return b200::roi_align_dispatch<__half>(static_cast<const __half*>(feat), layout, B, C, H, W, rois, K, PH, PW,
+                                                spatial_scale, sampling_ratio, aligned, static_cast<__half*>(out),
+                                                out_layout, stream);
+    return b200::fail(B200_EINVAL, "roi_align: bad dtype %d", dtype);
 }
 
 B200_SPAN_GETTER(b200_debug_spans_roi)

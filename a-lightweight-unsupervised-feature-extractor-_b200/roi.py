@@ -34,7 +34,7 @@ def _boxes_to_rois(boxes, device):
 
 def roi_align(input: torch.Tensor, boxes: Union[torch.Tensor, Sequence[torch.Tensor]],
               output_size: Union[int, Tuple[int, int]], spatial_scale: float = 1.0,
-              sampling_ratio: int = -1, aligned: bool = False) -> torch.Tensor:
+              sampling_ratio: int = -1, aligned: bool = False, *, out_channels_last: bool = False) -> torch.Tensor:
     """Drop-in for ``torchvision.ops.roi_align`` (forward only).
 
     ``input`` may be contiguous NCHW or ``torch.channels_last``; both are read in place.  float32 maps are
@@ -42,6 +42,10 @@ def roi_align(input: torch.Tensor, boxes: Union[torch.Tensor, Sequence[torch.Ten
     read as stored, sampled with float32 arithmetic and rounded to float16 once at the end.  Boxes of any
     float dtype are used at float32 (half-rounded boxes keep their half-rounded values).
     Returns a new contiguous ``[K, C, PH, PW]`` tensor of ``input``'s dtype on ``input``'s device.
+
+    ``out_channels_last=True`` (extension; SURVEY 8f-3, the ROI -> encoder hand-off) returns the same values as a
+    ``[K, C, PH, PW]`` tensor in ``torch.channels_last`` memory format, which a channels_last encoder
+    (model/utils/encoder/card.py:24-41) consumes without a copy and which the kernel writes as whole cache lines.
     """
     _lib.require_cuda(input, "input")
     if input.dim() != 4:
@@ -58,23 +62,36 @@ def roi_align(input: torch.Tensor, boxes: Union[torch.Tensor, Sequence[torch.Ten
     rois = _boxes_to_rois(boxes, input.device)
     PH, PW = _pair(output_size)
     K = rois.size(0)
-    out = torch.empty((K, C, PH, PW), dtype=input.dtype, device=input.device)
-    fn = _lib.lib().b200_roi_align_fwd_f32 if input.dtype == torch.float32 else _lib.lib().b200_roi_align_fwd_f16
+    out = torch.empty((K, C, PH, PW), dtype=input.dtype, device=input.device,
+                      memory_format=torch.channels_last if out_channels_last else torch.contiguous_format)
+    dtype = _lib.DTYPE_F32 if input.dtype == torch.float32 else _lib.DTYPE_F16
     with torch.cuda.device(input.device):
-        rc = fn(
-            _lib.ptr(input), layout, B, C, H, W, _lib.ptr(rois), K, PH, PW, float(spatial_scale),
-            int(sampling_ratio), int(bool(aligned)), _lib.ptr(out), _lib.stream_ptr(input.device))
+        rc = _lib.lib().b200_roi_align_fwd_ex(
+            _lib.ptr(input), dtype, layout, B, C, H, W, _lib.ptr(rois), K, PH, PW, float(spatial_scale),
+            int(sampling_ratio), int(bool(aligned)), _lib.ptr(out),
+            _lib.LAYOUT_NHWC if out_channels_last else _lib.LAYOUT_NCHW, _lib.stream_ptr(input.device))
     _lib.check(rc)
     return out
 
 
-def roi_align_from_input_boxes(feat: torch.Tensor, boxes_in: List[List[float]], input_hw: Tuple[int, int],
-                               out_size=(7, 7), aligned: bool = True, sampling_ratio: int = 2) -> torch.Tensor:
-    """tracking.py:193-221: boxes are in letterboxed-input pixels, scale = Hf / H_in, batch 0."""
+def roi_align_from_input_boxes(feat: torch.Tensor, boxes_in, input_hw: Tuple[int, int],
+                               out_size=(7, 7), aligned: bool = True, sampling_ratio: int = 2, *,
+                               out_channels_last: bool = False) -> torch.Tensor:
+    """tracking.py:193-221: boxes are in letterboxed-input pixels, scale = Hf / H_in, batch 0.
+
+    ``boxes_in`` is the reference's ``List[[x1, y1, x2, y2]]`` or (extension; SURVEY 8f-4, the detector -> ROI
+    hand-off) a ``[N, >=4]`` tensor whose first four columns are the box -- e.g. the detector's NMS output still
+    on the device, which then never visits the host (yoloDetects2.py:135-157 does ``.cpu().tolist()`` per box).
+    """
     H_in, _ = input_hw
     Hf = feat.shape[2]
-    rois = torch.tensor([[0.0, b[0], b[1], b[2], b[3]] for b in boxes_in], dtype=torch.float32).reshape(-1, 5)
-    return roi_align(feat, rois.to(feat.device), out_size, Hf / float(H_in), sampling_ratio, aligned)
+    if isinstance(boxes_in, torch.Tensor):
+        b = boxes_in.reshape(-1, boxes_in.shape[-1])[:, :4].to(device=feat.device, dtype=torch.float32)
+        rois = torch.cat([torch.zeros((b.shape[0], 1), dtype=torch.float32, device=feat.device), b], dim=1)
+    else:
+        rois = torch.tensor([[0.0, b[0], b[1], b[2], b[3]] for b in boxes_in], dtype=torch.float32).reshape(-1, 5)
+    return roi_align(feat, rois.to(feat.device), out_size, Hf / float(H_in), sampling_ratio, aligned,
+                     out_channels_last=out_channels_last)
 
 
 def preprocess_roi(feat: torch.Tensor, bboxes_xyxy: torch.Tensor, img_hw: Tuple[int, int],

@@ -35,6 +35,9 @@ extern "C" {
 #define B200_LAYOUT_NCHW 0
 #define B200_LAYOUT_NHWC 1      /* torch.channels_last storage of a [B,C,H,W] tensor */
 
+#define B200_DTYPE_F32 0
+#define B200_DTYPE_F16 1
+
 #define B200_EMB_DIM 128        /* embedding width the reference validates (mainTracking.py:109,267) */
 
 int         b200_version(void);
@@ -59,6 +62,16 @@ int b200_roi_align_fwd_f32(const float* feat, int layout, int B, int C, int H, i
 int b200_roi_align_fwd_f16(const void* feat, int layout, int B, int C, int H, int W,
                            const float* rois, int64_t K, int PH, int PW, float spatial_scale,
                            int sampling_ratio, int aligned, void* out, void* stream);
+
+/* Extended form: element type as an argument (B200_DTYPE_*) and a choice of output layout.
+ * out_layout = B200_LAYOUT_NCHW is the operator above; B200_LAYOUT_NHWC writes the patches as [K,PH,PW,C]
+ * (torch.channels_last storage of a [K,C,PH,PW] tensor) -- the hand-off a channels_last encoder
+ * (model/utils/encoder/card.py:24-41, first layers 1x1 / 3x3 convolutions) consumes without a copy, and the
+ * layout in which this kernel's lane-per-channel accumulators store whole cache lines directly.  Same values
+ * as the NCHW form, element for element. */
+int b200_roi_align_fwd_ex(const void* feat, int dtype, int layout, int B, int C, int H, int W,
+                          const float* rois, int64_t K, int PH, int PW, float spatial_scale,
+                          int sampling_ratio, int aligned, void* out, int out_layout, void* stream);
 
 /* ---- appearance cost -----------------------------------------------------------
  * Replaces Tracking.build_C_app_topk (model/mainTracking.py:141-211).

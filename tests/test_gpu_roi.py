@@ -192,3 +192,41 @@ def test_roi_float16_storage(ps, nhwc):
     assert got.dtype == torch.float16 and got.shape == (len(boxes), 96, ps[0], ps[1])
     want = native.roi_align(feat16.astype(np.float32), rois, ps, 40 / 1280.0, 2, True)
     assert_close(got.float().cpu().numpy(), want, rtol=1e-3, atol=2e-4, what="fp16 %s" % (ps,))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+@pytest.mark.parametrize("in_cl", [False, True])
+def test_roi_channels_last_output_equals_nchw_output(in_cl, dtype):
+    """out_channels_last=True (ROI -> encoder hand-off): same values, element for element, as the NCHW result, for
+    the tiled sizes (10x10, 7x7), a generic size, small and large launches, ragged channel counts, edge boxes,
+    huge footprints and bad batch indices; the returned tensor is a channels_last [K,C,PH,PW] view."""
+    rng = np.random.default_rng(31)
+    for (Bm, C, Hf, Wf, n) in [(2, 70, 23, 37, 60), (3, 150, 40, 48, 3400)]:
+        feat = torch.from_numpy(rng.standard_normal((Bm, C, Hf, Wf), dtype=np.float32)).cuda().to(dtype)
+        if in_cl:
+            feat = feat.contiguous(memory_format=torch.channels_last)
+        boxes = synth.random_boxes(rng, n, 32 * Hf, 32 * Wf)
+        edge = synth.edge_case_boxes(32 * Hf, 32 * Wf)
+        boxes[:len(edge)] = edge
+        boxes[len(edge):len(edge) + 4] = [[0, 0, 32 * Wf, 32 * Hf]] * 4
+        bidx = rng.integers(0, Bm, (n, 1)).astype(np.float64)
+        bidx[-3:] = [[-1], [Bm], [9]]
+        rois = torch.from_numpy(np.concatenate([bidx, boxes], 1).astype(np.float32)).cuda()
+        for ps, sr in [((10, 10), 2), ((7, 7), 2), ((5, 4), -1)]:
+            a = roi.roi_align(feat, rois, ps, 1 / 32.0, sr, True)
+            b = roi.roi_align(feat, rois, ps, 1 / 32.0, sr, True, out_channels_last=True)
+            assert b.shape == a.shape and b.is_contiguous(memory_format=torch.channels_last)
+            assert torch.equal(a, b.contiguous()), (Bm, C, ps, in_cl, dtype)
+
+
+def test_roi_device_boxes_hand_off():
+    """roi_align_from_input_boxes with the detector's [N,6] output still on the device == the list form."""
+    rng = np.random.default_rng(9)
+    feat = torch.from_numpy(synth.feature_map(2, 1, 64, 40, 40)).cuda()
+    boxes = synth.random_boxes(rng, 20, 1280, 1280)
+    det = torch.from_numpy(np.concatenate([boxes, rng.random((20, 2))], 1).astype(np.float32)).cuda()
+    a = roi.roi_align_from_input_boxes(feat, boxes.astype(np.float32).tolist(), (1280, 1280), out_size=(10, 10))
+    b = roi.roi_align_from_input_boxes(feat, det, (1280, 1280), out_size=(10, 10))
+    c = roi.roi_align_from_input_boxes(feat.contiguous(memory_format=torch.channels_last), det, (1280, 1280),
+                                       out_size=(10, 10), out_channels_last=True)
+    assert torch.equal(a, b) and torch.allclose(a, c.contiguous(), rtol=1e-6, atol=1e-6)

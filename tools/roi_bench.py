@@ -31,7 +31,7 @@ def timed(fn, iters, flush):
     return t[len(t) // 2] * 1e-3, t[0] * 1e-3
 
 
-def case(name, Bm, Hf, Wf, H_in, W_in, per_map, ps=(10, 10), nhwc=False, tv=False, iters=20, half=False):
+def case(name, Bm, Hf, Wf, H_in, W_in, per_map, ps=(10, 10), nhwc=False, tv=False, iters=20, half=False, out_cl=False):
     rng = np.random.default_rng(0)
     boxes = np.concatenate([synth.random_boxes(rng, per_map, H_in, W_in) for _ in range(Bm)])
     rois = np.concatenate([np.repeat(np.arange(Bm), per_map)[:, None].astype(np.float64), boxes], 1).astype(np.float32)
@@ -49,11 +49,11 @@ def case(name, Bm, Hf, Wf, H_in, W_in, per_map, ps=(10, 10), nhwc=False, tv=Fals
         import torchvision
         fn = lambda: torchvision.ops.roi_align(feat, r, ps, Hf / float(H_in), 2, True)
     else:
-        fn = lambda: roi.roi_align(feat, r, ps, Hf / float(H_in), 2, True)
+        fn = lambda: roi.roi_align(feat, r, ps, Hf / float(H_in), 2, True, out_channels_last=out_cl)
     for _ in range(3):
         fn()
     med, best = timed(fn, iters, flush)
-    print(json.dumps({"case": name, "impl": "torchvision" if tv else "b200", "layout": "nhwc" if nhwc else "nchw", "dtype": "f16" if half else "f32",
+    print(json.dumps({"case": name, "impl": "torchvision" if tv else "b200", "layout": ("nhwc" if nhwc else "nchw") + ("->nhwc" if out_cl else ""), "dtype": "f16" if half else "f32",
                       "K": K, "out": list(ps), "alg_MB": round(alg / 1e6, 2), "us_median": round(med * 1e6, 2),
                       "us_best": round(best * 1e6, 2), "GBps_median": round(alg / med / 1e9, 1),
                       "frac_of_measured_peak": round(alg / med / 1e9 / PEAK, 3)}), flush=True)
@@ -73,10 +73,16 @@ if __name__ == "__main__":
                 case("c2", 1, 40, 40, 1280, 1280, 64, nhwc=nhwc, tv=tv)
             if "c3" in which:
                 case("c3", 256, 40, 40, 1280, 1280, 16, nhwc=nhwc, tv=tv, iters=10)
+                if nhwc and not tv:
+                    case("c3", 256, 40, 40, 1280, 1280, 16, nhwc=True, iters=10, out_cl=True)
             if "c5" in which:
                 case("c5x64", 64, 34, 60, 1088, 1920, 128, nhwc=nhwc, tv=tv, iters=10)
+                if nhwc and not tv:
+                    case("c5x64", 64, 34, 60, 1088, 1920, 128, nhwc=True, iters=10, out_cl=True)
             if "g64" in which:      # the bench.py stream group: 64 maps x 64 boxes per launch
                 case("g64", 64, 40, 40, 1280, 1280, 64, nhwc=nhwc, tv=tv, iters=10)
+                if not tv:
+                    case("g64", 64, 40, 40, 1280, 1280, 64, nhwc=nhwc, iters=10, out_cl=True)
             if "g64h" in which and not tv:      # float16 storage
                 case("g64", 64, 40, 40, 1280, 1280, 64, nhwc=nhwc, iters=10, half=True)
                 case("c3", 256, 40, 40, 1280, 1280, 16, nhwc=nhwc, iters=10, half=True)
