@@ -517,44 +517,42 @@ struct PipeSmem {
     static_assert(kFloatsPerWarp >= L::kFloatsPerWarp, "the fallback path needs an output tile + tables");
 };
 
-template <int PH, int PW, bool NHWC>
+// Starts the copies of one tile of a channels-last map: V[cell][channel] (no skew needed: a cell's 32 channels are
+// one 128-byte line in both the map and the buffer) and the ROI's ready-made weight tables.  With a full,
+// 16-byte aligned tile, eight lanes move one cell (16 bytes each) and a warp instruction moves four cells.
+template <int PH, int PW>
 __device__ __forceinline__ void pipe_issue(const float* __restrict__ feat, int C, int H, int W, const int4 h0,
-                                           const int4 h1, long long k, int c0, int cn,
+                                           const int4 h1, long long k, int c0, int cn, bool vec16,
                                            const float* __restrict__ prep_tabs, unsigned sv, int lane) {
     using L = TileSmem<PH, PW>;
     const int b = h0.x, ymin = h0.y, xmin = h0.z, FY = h0.w, FX = h1.x;
-    int nxp = 1;
-    while (nxp < FX) nxp <<= 1;
-    const int cper = 32 / nxp, xmask = nxp - 1;
-    if (NHWC) {
-        const float* row = feat + (((size_t)b * H + ymin) * W + xmin) * C + c0 + lane;
-        unsigned dst = sv;
-        if (lane < cn)
-            for (int r = 0; r < FY; ++r, row += (size_t)W * C) {
-                const float* src = row;
-#pragma unroll 4
-                for (int x = 0; x < FX; ++x, src += C, dst += 128)
-                    cp_async4_s(dst + 4u * ((lane + (x & xmask) * cper) & 31), src);
-            }
-    } else {
-        const int xi = lane & xmask, cs = lane / nxp;
-        const size_t plane = (size_t)H * W, cstep = plane * cper;
-        const float* row = feat + (((size_t)b * C + c0 + cs) * H + ymin) * W + xmin + xi;
-        unsigned dst = sv + 128u * xi;
-        const int skew0 = cs + xi * cper;
-        if (xi < FX)
-            for (int r = 0; r < FY; ++r, row += W, dst += 128u * FX) {
-                const float* src = row;
-                int sk = skew0;
-#pragma unroll 4
-                for (int c = cs; c < cn; c += cper, src += cstep, sk += cper) cp_async4_s(dst + 4u * (sk & 31), src);
-            }
-    }
     const float* tsrc = prep_tabs + (size_t)k * L::kTabFloats;
     for (int i = lane; i < L::kTabFloats / 4; i += 32) cp_async16_s(sv + 4u * (kCellCap * 32) + 16u * i, tsrc + 4 * i);
+    const int cells = FY * FX;
+    if (vec16 && cn == 32) {
+        int m = lane >> 3, x = m, r = 0;
+        while (x >= FX && r < FY) { x -= FX; ++r; }
+        const float* src = feat + (((size_t)b * H + ymin + r) * W + xmin + x) * C + c0 + (lane & 7) * 4;
+        const size_t step = (size_t)4 * C, wrap = (size_t)(W - FX) * C;
+        unsigned dst = sv + 128u * m + 16u * (lane & 7);
+        for (; m < cells; m += 4, dst += 512u) {
+            cp_async16_s(dst, src);
+            x += 4;
+            src += step;
+            while (x >= FX) { x -= FX; src += wrap; }
+        }
+    } else if (lane < cn) {
+        const float* row = feat + (((size_t)b * H + ymin) * W + xmin) * C + c0 + lane;
+        unsigned dst = sv + 4u * lane;
+        for (int r = 0; r < FY; ++r, row += (size_t)W * C) {
+            const float* src = row;
+#pragma unroll 4
+            for (int x = 0; x < FX; ++x, src += C, dst += 128) cp_async4_s(dst, src);
+        }
+    }
 }
 
-template <int PH, int PW, bool NHWC, bool OCL>
+template <int PH, int PW, bool OCL>
 __global__ void __launch_bounds__(kPipeWarps * 32, (B200_ROI_MIN_CTAS * 2 + kPipeWarps - 1) / kPipeWarps)
 roi_align_pipe_kernel(const float* __restrict__ feat, int B, int C, int H, int W, const float* __restrict__ rois,
                       long long K, float scale, int sr, int aligned, float* __restrict__ out, int ctiles,
@@ -585,7 +583,8 @@ roi_align_pipe_kernel(const float* __restrict__ feat, int B, int C, int H, int W
     unsigned ka = t / (unsigned)ctiles;
     int ca = (int)(t - ka * (unsigned)ctiles) * 32;
     int4 a0 = reinterpret_cast<const int4*>(prep + ka)[0], a1 = reinterpret_cast<const int4*>(prep + ka)[1];
-    if (a1.y) pipe_issue<PH, PW, NHWC>(feat, C, H, W, a0, a1, ka, ca, min(32, C - ca), prep_tabs, sbase, lane);
+    const bool vec16 = (C & 3) == 0 && (reinterpret_cast<uintptr_t>(feat) & 15) == 0;
+    if (a1.y) pipe_issue<PH, PW>(feat, C, H, W, a0, a1, ka, ca, min(32, C - ca), vec16, prep_tabs, sbase, lane);
     asm volatile("cp.async.commit_group;\n" ::: "memory");
     unsigned tn = t + stride, kn = 0;
     int cnx = 0;
@@ -601,13 +600,13 @@ roi_align_pipe_kernel(const float* __restrict__ feat, int B, int C, int H, int W
         const bool have_next = tn < total;
         const int cn = min(32, C - ca);
         if (!a1.y) {            // footprint too large for a buffer: nothing is in flight, use the whole region
-            process_tile<PH, PW, NHWC, float, false, OCL>(feat, B, C, H, W, rois, scale, sr, aligned, out, (long long)ka,
+            process_tile<PH, PW, true, float, false, OCL>(feat, B, C, H, W, rois, scale, sr, aligned, out, (long long)ka,
                                                           ca, cn, nullptr, nullptr, base, base + L::kMainFloats, lane);
             __syncwarp();
         }
         if (have_next && n1.y)
-            pipe_issue<PH, PW, NHWC>(feat, C, H, W, n0, n1, kn, cnx, min(32, C - cnx), prep_tabs,
-                                     sbase + 4u * (unsigned)((par ^ 1) * P::kBufFloats), lane);
+            pipe_issue<PH, PW>(feat, C, H, W, n0, n1, kn, cnx, min(32, C - cnx), vec16, prep_tabs,
+                               sbase + 4u * (unsigned)((par ^ 1) * P::kBufFloats), lane);
         asm volatile("cp.async.commit_group;\n" ::: "memory");
         // record of the tile after next: in registers by the time this tile is done
         const unsigned tm = tn + stride;
@@ -626,17 +625,13 @@ roi_align_pipe_kernel(const float* __restrict__ feat, int B, int C, int H, int W
             const float* sV = base + par * P::kBufFloats;
             const float* sWy = sV + kCellCap * 32;
             const int FY = a0.w, FX = a1.x;
-            int nxp = 1;
-            while (nxp < FX) nxp <<= 1;
-            const int cper = 32 / nxp, xmask = nxp - 1;
             float acc[PH][PW];
 #pragma unroll
             for (int a = 0; a < PH; ++a)
 #pragma unroll
                 for (int bq = 0; bq < PW; ++bq) acc[a][bq] = 0.0f;
-            separable_accumulate<PH, PW>(acc, sWy, sWy + kFootCap * PHP, FY, FX, [&](int r, int x) {
-                return sV[(r * FX + x) * 32 + ((lane + (x & xmask) * cper) & 31)];
-            });
+            separable_accumulate<PH, PW>(acc, sWy, sWy + kFootCap * PHP, FY, FX,
+                                         [&](int r, int x) { return sV[(r * FX + x) * 32 + lane]; });
             if (OCL) {          // channels-last result: full-line stores straight from the accumulators
                 float* gl = out + (size_t)ka * NB * C + ca + lane;
                 if (lane < cn) {
@@ -660,7 +655,24 @@ roi_align_pipe_kernel(const float* __restrict__ feat, int B, int C, int H, int W
                 __syncwarp();
                 const int nch = min(16, cn - 16 * h);                 // contiguous [nch][PH*PW] block of the result
                 float4* g4 = reinterpret_cast<float4*>(out + ((size_t)ka * C + ca + 16 * h) * NB);
-                for (int i = lane; i < nch * (NB / 4); i += 32) __stcs(g4 + i, reinterpret_cast<const float4*>(so)[i]);
+                const float4* s4 = reinterpret_cast<const float4*>(so);
+                if (nch == 16) {                                      // loads in batches of four, then their stores
+                    constexpr int kN4 = 16 * (NB / 4), kIt = (kN4 + 31) / 32;
+#pragma unroll
+                    for (int i0 = 0; i0 < kIt; i0 += 4) {
+                        float4 v[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            if (i0 + u < kIt && (32 * (i0 + u + 1) <= kN4 || lane + 32 * (i0 + u) < kN4))
+                                v[u] = s4[lane + 32 * (i0 + u)];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            if (i0 + u < kIt && (32 * (i0 + u + 1) <= kN4 || lane + 32 * (i0 + u) < kN4))
+                                __stcs(g4 + lane + 32 * (i0 + u), v[u]);
+                    }
+                } else {
+                    for (int i = lane; i < nch * (NB / 4); i += 32) __stcs(g4 + i, s4[i]);
+                }
                 __syncwarp();
             }
             __syncwarp();       // every lane is done with this buffer before the next iteration refills it
@@ -731,7 +743,7 @@ int launch_pipe(const T* feat, int B, int C, int H, int W, const float* rois, lo
         using P = PipeSmem<PH, PW>;
         if (!OCL && (reinterpret_cast<uintptr_t>(out) & 15)) return 1;
         static int resident_warps = 0;       // warps the device holds at once (per instantiation)
-        auto kern = roi_align_pipe_kernel<PH, PW, NHWC, OCL>;
+        auto kern = roi_align_pipe_kernel<PH, PW, OCL>;
         if (!resident_warps) {
             int dev = 0, sms = 0, per_sm = 0;
             B200_CUDA(cudaGetDevice(&dev));
