@@ -385,18 +385,37 @@ def main():
     NPIN = 2
     pin_maps = torch.randn((NPIN, S, C, HF, WF), generator=torch.Generator().manual_seed(99 + rank)).pin_memory()
     pin_rois = torch.from_numpy(grp.rois).pin_memory()
-    feat_dev = torch.empty((S, C, HF, WF), device=dev)
-    rois_dev = torch.empty((S * NBOX, 5), device=dev)
+    feat_dev = [torch.empty((S, C, HF, WF), device=dev) for _ in range(2)]     # double-buffered upload target
+    rois_dev = [torch.empty((S * NBOX, 5), device=dev) for _ in range(2)]
     n_det = np.full(S, NBOX, np.int32)
     n_e2e = min(K, 60)
     scale = HF / float(H_IN)
+    copy_stream = torch.cuda.Stream(dev)
+    uploaded = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+
+    def upload(i):                                   # frame i's map and boxes, host (pinned) -> device
+        b = i & 1
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[b])      # the ROI launch that read this buffer two frames ago
+            feat_dev[b].copy_(pin_maps[i % NPIN], non_blocking=True)
+            rois_dev[b].copy_(pin_rois[i % len(pin_rois)], non_blocking=True)
+            uploaded[b].record(copy_stream)
 
     def e2e_step(i):
-        feat_dev.copy_(pin_maps[i % NPIN], non_blocking=True)
-        rois_dev.copy_(pin_rois[i], non_blocking=True)
-        patches = alufe_b200.roi_align(feat_dev, rois_dev, (PS, PS), scale, 2, True)
+        """One frame of every stream through the public API.  The upload of frame i+1 is queued on a copy stream
+        before the (synchronising) tracker call of frame i, as a caller feeding frames from the host would do."""
+        b = i & 1
+        main = torch.cuda.current_stream(dev)
+        main.wait_event(uploaded[b])
+        patches = alufe_b200.roi_align(feat_dev[b], rois_dev[b], (PS, PS), scale, 2, True)
+        consumed[b].record(main)
+        upload(i + 1)
         return patches, ms2.step(n_det, grp.boxes[i], grp.confs[i], grp.embs[i], np.full(S, i, np.int32))
 
+    for b in range(2):
+        consumed[b].record(torch.cuda.current_stream(dev))
+    upload(0)
     for i in range(pre + W):
         e2e_step(i)
     if world > 1:

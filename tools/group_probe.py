@@ -6,13 +6,13 @@ import torch
 import bench
 
 S = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+CL = len(sys.argv) > 2 and sys.argv[2] == "cl"      # channels-last maps
 W, K = 40, 100
 dev = torch.device("cuda", 0)
 torch.cuda.set_device(0)
 out = {}
 for mode in ("roi_only", "assoc_only", "serial", "overlap_prio"):
-    g = bench.StreamGroup(S, W + K, 0, dev)
-    if mode == "overlap_prio_noevent":
+    g = bench.StreamGroup(S, W + K, 0, dev, channels_last=CL)
     if mode == "serial":
         g.sB = g.sA
     if mode == "roi_only":
@@ -24,4 +24,4 @@ for mode in ("roi_only", "assoc_only", "serial", "overlap_prio"):
     out[mode] = round(ms / K * 1e3, 1)
     del g
     torch.cuda.empty_cache()
-print(json.dumps({"streams": S, "us_per_step": out}))
+print(json.dumps({"streams": S, "channels_last_maps": CL, "us_per_step": out}))
