@@ -37,6 +37,15 @@ __device__ long long g_timing[32];
 #define TRK_STAMP(k) do { } while (0)
 #endif
 
+// Programmatic dependent launch (used for small stream counts, see b200_tracker_step): let the next kernel of
+// the step become resident while this one runs, then wait until the previous kernel has completed and its
+// writes are visible.  Both instructions are no-ops for a kernel launched without the attribute.
+#define TRK_PDL_PROLOGUE()                                        \
+    do {                                                          \
+        asm volatile("griddepcontrol.launch_dependents;");        \
+        asm volatile("griddepcontrol.wait;" ::: "memory");        \
+    } while (0)
+
 constexpr int kThreads = 256;
 constexpr int kHdr = 8;                 // ints per stream in hdr / cnt
 enum { H_NLIVE = 0, H_NEXT = 1, H_NFREE = 2 };
@@ -245,6 +254,7 @@ __global__ void __launch_bounds__(kThreads) begin_kernel(Dev d) {
 // 64 detection rows staged in shared memory, see assoc_cost.cuh).  Persistent CTAs over queued work items.
 __global__ void __launch_bounds__(cost::kThreads) cost2_kernel(Dev d) {
     Span span((d.frame_id[0] & 7) * 6 + 3);
+    TRK_PDL_PROLOGUE();
     extern __shared__ __align__(16) float smem[];
     __shared__ int s_idx[cost::kTileN];
     const int total = d.wcount[1];
@@ -306,6 +316,7 @@ __device__ __forceinline__ unsigned fkey(float f) {                 // order-pre
 
 __global__ void __launch_bounds__(kCost1Warps * 32) cost1_sparse_kernel(Dev d) {
     Span span((d.frame_id[0] & 7) * 6 + 1);
+    TRK_PDL_PROLOGUE();
     const int total = d.wcount[0];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float kNegInf = -__int_as_float(0x7f800000);
@@ -412,6 +423,7 @@ __device__ __forceinline__ void transpose_reduce32(float (&p)[32]) {
 // the 32 dot products of a detection are reduced together (transpose_reduce32).
 __global__ void __launch_bounds__(kCost1Warps * 32, 2) cost1_sparse32_kernel(Dev d) {
     Span span((d.frame_id[0] & 7) * 6 + 1);
+    TRK_PDL_PROLOGUE();
     const int total = d.wcount[0];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float kNegInf = -__int_as_float(0x7f800000);
@@ -531,6 +543,7 @@ constexpr int kUpdWarps = 4;
 
 __global__ void __launch_bounds__(kUpdWarps * 32) update_kernel(Dev d) {
     Span span((d.frame_id[0] & 7) * 6 + 5);
+    TRK_PDL_PROLOGUE();
     __shared__ double scratch[kUpdWarps * 4 * 96];
     const int total = d.wcount[2];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, sub = lane & 7, grp = lane >> 3;
@@ -614,6 +627,7 @@ __global__ void __launch_bounds__(kUpdWarps * 32) update_kernel(Dev d) {
 template <int STAGE>
 __global__ void __launch_bounds__(kThreads) assign_kernel(Dev d, int smem_matrix_floats) {
     Span span((d.frame_id[0] & 7) * 6 + (STAGE == 1 ? 2 : 4));
+    TRK_PDL_PROLOGUE();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int scratch[kThreads / 32];
     __shared__ int s_rc;
@@ -987,16 +1001,31 @@ extern "C" int b200_tracker_step(b200_tracker* t, const int32_t* n_det, const do
     trk::begin_kernel<<<dim3(d.S, 2), t->ctl_threads, 0, st>>>(d);
     int rc = check_launch("trk begin_kernel");
     if (rc) return rc;
-    if (d.HIST <= 32) trk::cost1_sparse32_kernel<<<t->cost1_grid, trk::kCost1Warps * 32, 0, st>>>(d);
-    else trk::cost1_sparse_kernel<<<t->cost1_grid, trk::kCost1Warps * 32, 0, st>>>(d);
+    // With a handful of streams the step is a chain of short, latency-bound kernels: launch the dependent ones
+    // with programmatic stream serialisation so that each is resident (and past its launch latency) by the
+    // time its predecessor finishes.  With many streams the chain shares the GPU with ROI Align of the next
+    // frame and early-resident CTAs would only take SM slots away from it.
+    const bool pdl = d.S <= 8;
+    auto launch = [&](auto kern, dim3 grid, dim3 block, size_t smem, auto... args) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = pdl ? 1 : 0;
+        (void)cudaLaunchKernelEx(&cfg, kern, args...);     // errors surface in check_launch()
+    };
+    if (d.HIST <= 32) launch(trk::cost1_sparse32_kernel, dim3(t->cost1_grid), dim3(trk::kCost1Warps * 32), 0, d);
+    else launch(trk::cost1_sparse_kernel, dim3(t->cost1_grid), dim3(trk::kCost1Warps * 32), 0, d);
     if ((rc = check_launch("trk cost1_sparse_kernel"))) return rc;
-    trk::assign_kernel<1><<<d.S, t->ctl_threads, t->assign_smem, st>>>(d, t->smem_matrix_floats);
+    launch(trk::assign_kernel<1>, dim3(d.S), dim3(t->ctl_threads), t->assign_smem, d, t->smem_matrix_floats);
     if ((rc = check_launch("trk assign_kernel<1>"))) return rc;
-    trk::cost2_kernel<<<cost_grid, cost::kThreads, csm, st>>>(d);
+    launch(trk::cost2_kernel, dim3(cost_grid), dim3(cost::kThreads), csm, d);
     if ((rc = check_launch("trk cost2_kernel"))) return rc;
-    trk::assign_kernel<2><<<d.S, t->ctl_threads, t->assign_smem, st>>>(d, t->smem_matrix_floats);
+    launch(trk::assign_kernel<2>, dim3(d.S), dim3(t->ctl_threads), t->assign_smem, d, t->smem_matrix_floats);
     if ((rc = check_launch("trk assign_kernel<2>"))) return rc;
-    trk::update_kernel<<<t->upd_grid, trk::kUpdWarps * 32, 0, st>>>(d);
+    launch(trk::update_kernel, dim3(t->upd_grid), dim3(trk::kUpdWarps * 32), 0, d);
     if ((rc = check_launch("trk update_kernel"))) return rc;
     return B200_OK;
 }
