@@ -267,12 +267,17 @@ roi_prep_kernel(const float* __restrict__ rois, long long K, int B, int H, int W
 
 // One (ROI k, channels c0 .. c0+cn) tile, start to finish, by one warp.  sMain: L::kMainFloats floats (V staging /
 // big tables, later the output tile), sTab: L::kTabFloats floats; both private to the warp.
-template <int PH, int PW, bool NHWC, typename T, bool PREP, bool OCL = false>
+// MULTI (a warp that walks several tiles, roi_align_multi_kernel): the ROI's record arrives in registers (rec0 /
+// rec1, loaded while the previous tile was computed) and the bulk store of the output tile is not waited for at
+// the end; `*pending` says that sMain may still be being read, and the wait happens in the next call right
+// before sMain is written again, i.e. after that tile's address arithmetic.
+template <int PH, int PW, bool NHWC, typename T, bool PREP, bool OCL = false, bool MULTI = false>
 __device__ __forceinline__ void process_tile(const T* __restrict__ feat, int B, int C, int H, int W,
                                              const float* __restrict__ rois, float scale, int sr, int aligned,
                                              T* __restrict__ out, long long k, int c0, int cn,
                                              const RoiPrep* __restrict__ prep, const float* __restrict__ prep_tabs,
-                                             float* sMain, float* sTab, int lane) {
+                                             float* sMain, float* sTab, int lane, int4 rec0 = make_int4(0, 0, 0, 0),
+                                             int4 rec1 = make_int4(0, 0, 0, 0), bool* pending = nullptr) {
     constexpr bool kF32 = sizeof(T) == 4;
     using L = TileSmem<PH, PW>;
     constexpr int PHP = L::kPHP, PWP = L::kPWP, NB = PH * PW;
@@ -282,7 +287,8 @@ __device__ __forceinline__ void process_tile(const T* __restrict__ feat, int B, 
     int ymin = 0, xmin = 0, FY = 0, FX = 0;
     bool pre = false;                         // footprint and tables come from roi_prep_kernel
     if (PREP) {
-        const int4 h0 = reinterpret_cast<const int4*>(prep + k)[0], h1 = reinterpret_cast<const int4*>(prep + k)[1];
+        const int4 h0 = MULTI ? rec0 : reinterpret_cast<const int4*>(prep + k)[0];
+        const int4 h1 = MULTI ? rec1 : reinterpret_cast<const int4*>(prep + k)[1];
         if (h1.y) {
             pre = true;
             g.b = h0.x; ymin = h0.y; xmin = h0.z; FY = h0.w; FX = h1.x;
@@ -308,6 +314,11 @@ __device__ __forceinline__ void process_tile(const T* __restrict__ feat, int B, 
 #pragma unroll
         for (int b = 0; b < PW; ++b) acc[a][b] = 0.0f;
 
+    if (MULTI && !OCL) {                       // the previous tile's bulk store must have left sMain
+        if (*pending && lane == 0) bulk_store_wait_read();
+        *pending = false;
+        __syncwarp();
+    }
     if (staged || direct) {
         float* sV = sMain;
         // ---- stage V[cell][channel], fully asynchronous, BEFORE the weight tables are built so the
@@ -458,8 +469,9 @@ __device__ __forceinline__ void process_tile(const T* __restrict__ feat, int B, 
         __syncwarp();
         if (lane == 0) {
             bulk_store_issue(gdst, sMain, bytes);
-            bulk_store_wait_read();           // shared memory must outlive the copy's read
+            if (!MULTI) bulk_store_wait_read();           // shared memory must outlive the copy's read
         }
+        if (MULTI) *pending = true;
     } else {
         __syncwarp();
         const T* tile = reinterpret_cast<const T*>(sMain);
@@ -487,6 +499,55 @@ roi_align_tile_kernel(const T* __restrict__ feat, int B, int C, int H, int W,
     const int c0 = (int)(wi32 % (unsigned)ctiles) * 32;
     process_tile<PH, PW, NHWC, T, PREP, OCL>(feat, B, C, H, W, rois, scale, sr, aligned, out, k, c0, min(32, C - c0),
                                              prep, prep_tabs, sMain, sMain + L::kMainFloats, lane);
+    B200_SPAN_END(span_slot);
+}
+
+// Large launches that cannot use the pipelined kernel below (NCHW maps, half storage, 7x7): the tile kernel with a
+// warp walking a few tiles.  Nothing is double-buffered, but the next ROI record is loaded during the current
+// tile and the wait for the output tile's bulk store moves behind the next tile's address arithmetic, which
+// takes two of the three exposed round trips off the critical path; tiles are handed out in groups the size of
+// the resident warp set as in the pipelined kernel.
+#ifndef B200_ROI_MULTI_TILES
+#define B200_ROI_MULTI_TILES 8
+#endif
+template <int PH, int PW, bool NHWC, typename T, bool OCL>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, (B200_ROI_MIN_CTAS * 2 + kWarpsPerCta - 1) / kWarpsPerCta)
+roi_align_multi_kernel(const T* __restrict__ feat, int B, int C, int H, int W, const float* __restrict__ rois,
+                       long long K, float scale, int sr, int aligned, T* __restrict__ out, int ctiles,
+                       const RoiPrep* __restrict__ prep, const float* __restrict__ prep_tabs, int group_warps,
+                       int tiles_per_warp) {
+    using L = TileSmem<PH, PW>;
+    extern __shared__ __align__(16) float smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned gw = blockIdx.x * kWarpsPerCta + warp, grp = gw / (unsigned)group_warps;
+    const unsigned stride = (unsigned)group_warps, window = stride * (unsigned)tiles_per_warp;
+    unsigned t = grp * window + (gw - grp * stride);
+    const unsigned total = (unsigned)min((long long)(grp + 1) * window, K * ctiles);
+    if (t >= total) return;
+    const int span_slot = (int)((reinterpret_cast<uintptr_t>(rois) / (size_t)(K * 20)) & 7);   // debug: step index mod 8
+    B200_SPAN_BEGIN(span_slot);
+    float* sMain = smem + (size_t)warp * L::kFloatsPerWarp;
+    unsigned k = t / (unsigned)ctiles;
+    int4 h0 = reinterpret_cast<const int4*>(prep + k)[0], h1 = reinterpret_cast<const int4*>(prep + k)[1];
+    bool pending = false;
+    for (;;) {
+        const unsigned tn = t + stride;
+        const bool have_next = tn < total;
+        unsigned kn = 0;
+        int4 n0 = make_int4(0, 0, 0, 0), n1 = n0;
+        if (have_next) {
+            kn = tn / (unsigned)ctiles;
+            n0 = reinterpret_cast<const int4*>(prep + kn)[0];
+            n1 = reinterpret_cast<const int4*>(prep + kn)[1];
+        }
+        const int c0 = (int)(t - k * (unsigned)ctiles) * 32;
+        process_tile<PH, PW, NHWC, T, true, OCL, true>(feat, B, C, H, W, rois, scale, sr, aligned, out, (long long)k, c0,
+                                                       min(32, C - c0), prep, prep_tabs, sMain, sMain + L::kMainFloats,
+                                                       lane, h0, h1, &pending);
+        if (!have_next) break;
+        t = tn; k = kn; h0 = n0; h1 = n1;
+    }
+    if (pending && lane == 0) bulk_store_wait_read();
     B200_SPAN_END(span_slot);
 }
 
@@ -770,10 +831,8 @@ int launch_tile(const T* feat, int B, int C, int H, int W, const float* rois, lo
     using L = TileSmem<PH, PW>;
     static bool configured = false;          // per instantiation; the attribute is idempotent
     auto fused = roi_align_tile_kernel<PH, PW, NHWC, T, false, OCL>;
-    auto tiled = roi_align_tile_kernel<PH, PW, NHWC, T, true, OCL>;
     if (!configured) {
         B200_CUDA(cudaFuncSetAttribute(fused, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kBytesPerCta));
-        B200_CUDA(cudaFuncSetAttribute(tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kBytesPerCta));
         configured = true;
     }
     const int ctiles = (C + 31) / 32;
@@ -805,10 +864,26 @@ int launch_tile(const T* feat, int B, int C, int H, int W, const float* rois, lo
     int rc = check_launch("roi_prep_kernel");
     if (rc == B200_OK) {
         rc = launch_pipe<PH, PW, NHWC, OCL>(feat, B, C, H, W, rois, K, scale, sr, aligned, out, ctiles, prep, tabs, warps, st);
-        if (rc == 1) {                       // no pipelined kernel for this type / size / alignment
-            tiled<<<(unsigned)blocks, kWarpsPerCta * 32, L::kBytesPerCta, st>>>(feat, B, C, H, W, rois, K, scale, sr,
-                                                                                aligned, out, ctiles, prep, tabs);
-            rc = check_launch("roi_align_tile_kernel");
+        if (rc == 1) {                       // no pipelined kernel for this layout / type / size / alignment
+            static int resident_warps = 0;   // per instantiation
+            auto multi = roi_align_multi_kernel<PH, PW, NHWC, T, OCL>;
+            if (!resident_warps) {
+                int dev = 0, sms = 0, per_sm = 0;
+                B200_CUDA(cudaGetDevice(&dev));
+                B200_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+                B200_CUDA(cudaFuncSetAttribute(multi, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kBytesPerCta));
+                B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, multi, kWarpsPerCta * 32,
+                                                                        L::kBytesPerCta));
+                resident_warps = sms * (per_sm > 0 ? per_sm : 1) * kWarpsPerCta;
+            }
+            const long long window = (long long)resident_warps * B200_ROI_MULTI_TILES;
+            const long long groups = (warps + window - 1) / window;
+            const long long last = warps - (groups - 1) * window;
+            const long long nw = (groups - 1) * resident_warps + (last < resident_warps ? last : resident_warps);
+            multi<<<(unsigned)((nw + kWarpsPerCta - 1) / kWarpsPerCta), kWarpsPerCta * 32, L::kBytesPerCta, st>>>(
+                feat, B, C, H, W, rois, K, scale, sr, aligned, out, ctiles, prep, tabs, resident_warps,
+                B200_ROI_MULTI_TILES);
+            rc = check_launch("roi_align_multi_kernel");
         }
     }
     B200_CUDA(cudaFreeAsync(ws, st));

@@ -492,7 +492,7 @@ def main():
             "e2e": {"value": world * S * n_e2e / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": n_e2e, "api": "alufe_b200.roi_align + MultiStreamTracker.step (pinned host buffers)"},
             "gpu_launches": int(launches),
-            "roofline": {"kernel": "roi_align_tile_kernel<10,10,NCHW>", "bound": "hbm",
+            "roofline": {"kernel": "roi_prep_kernel + roi_align_multi_kernel<10,10,NCHW> (one ROI Align launch)", "bound": "hbm",
                          "achieved": grp.roi_alg_bytes / roi_us_avg / 1e3, "peak": peak, "unit": "GB/s",
                          "frac": grp.roi_alg_bytes / roi_us_avg / 1e3 / peak, "traffic": traffic,
                          "alg_bytes_per_launch": grp.roi_alg_bytes, "us_per_launch": roi_us_avg, "launches_timed": len(roi_us),
