@@ -15,6 +15,16 @@
 namespace b200 {
 namespace lsap {
 
+#ifdef B200_TRK_TIMING             // debug builds: [0] searches skipped by the known-first-step rule, [1] full searches,
+__device__ unsigned long long g_lsap_stats[4];      // [2] Dijkstra steps of the full searches (per translation unit)
+__device__ long long g_lsap_clk[8];                 // SM-clock stamps inside solve_block (CTA 0)
+#define LSAP_STAT(i, n) do { if ((threadIdx.x & 31) == 0 && blockIdx.x == 0) g_lsap_stats[i] += (n); } while (0)
+#define LSAP_CLK(k) do { if (threadIdx.x == 0 && blockIdx.x == 0) g_lsap_clk[k] = clock64(); } while (0)
+#else
+#define LSAP_STAT(i, n) do { } while (0)
+#define LSAP_CLK(k) do { } while (0)
+#endif
+
 constexpr int kMaxThreads = 256;
 #ifndef B200_LSAP_WARP_MAX_COLS
 #define B200_LSAP_WARP_MAX_COLS 128
@@ -216,6 +226,35 @@ __device__ inline int solve(const float* cost, int R, int Cc, int ld, const Work
 // clearly best detection per track) almost every row takes it.
 __device__ __forceinline__ double first_step_dual(float c) { return 0.0 + (((0.0 + (double)c) - 0.0) - 0.0); }
 
+// Applies the rule to a run of consecutive rows, 32 at a time (one warp; lane l looks at row cur + l): a lane's
+// row qualifies if its column is free, unmoved, and not claimed by an earlier lane of the batch (then the rows
+// before it only take other free columns and leave every v alone, so applying them together equals applying
+// them in order).  The batch is applied up to the first row that does not qualify; returns that row (or R).
+// r4c_s / v_s / u_s / c4r_s are the shared-memory copies of row4col, v, u, col4row.
+__device__ inline int known_first_step_run(int cur, int R, const int* first_col, const float* first_val, int* r4c_s,
+                                           const double* v_s, double* u_s, int* c4r_s, int lane) {
+    const unsigned kFull = 0xffffffffu;
+    while (cur < R) {
+        const int row = cur + lane;
+        const int fj = row < R ? first_col[row] : -1;
+        bool ok = fj >= 0;
+        if (ok) ok = r4c_s[fj] < 0 && v_s[fj] == 0.0;
+        const unsigned same = __match_any_sync(kFull, fj);
+        ok = ok && (__ffs(same) - 1 == lane);
+        const unsigned bad = ~__ballot_sync(kFull, ok);
+        const int lead = bad ? __ffs(bad) - 1 : 32;
+        if (lane < lead) {
+            r4c_s[fj] = row;
+            c4r_s[row] = fj;
+            u_s[row] = first_step_dual(first_val[row]);
+        }
+        __syncwarp();
+        cur += lead;
+        if (lead < 32) break;
+    }
+    return cur < R ? cur : R;
+}
+
 // ---- single-warp solver: all per-column state in registers -------------------------------------
 // Same algorithm and tie rule as solve(), for Cc <= 32 * CPL columns.  Lane l owns columns
 // l, l+32, ...; for each it keeps dist, v, pred, r4c and the column's POSITION in scipy's
@@ -240,7 +279,7 @@ __device__ __forceinline__ unsigned tie_key(int it, bool un) { return un ? (0xFF
 
 template <int CPL>
 __device__ inline int solve_warp(const float* cost, int R, int Cc, int ld, double* u_s, int* c4r_s, int* r4c_s,
-                                 const int* first_col, const float* first_val) {
+                                 double* v_s, const int* first_col, const float* first_val) {
     const unsigned kFull = 0xffffffffu;
     const double kInf = __longlong_as_double(0x7ff0000000000000LL);
     const int lane = threadIdx.x & 31;
@@ -249,26 +288,16 @@ __device__ inline int solve_warp(const float* cost, int R, int Cc, int ld, doubl
 #pragma unroll
     for (int q = 0; q < CPL; ++q) { v[q] = 0.0; r4c[q] = -1; pred[q] = -1; }
     for (int i = lane; i < R; i += 32) { u_s[i] = 0.0; c4r_s[i] = -1; }
+    for (int j = lane; j < Cc; j += 32) { r4c_s[j] = -1; v_s[j] = 0.0; }
     __syncwarp();
     bool v_positive = false;                             // some v[j] > 0 appeared: no more shortcuts
     for (int cur = 0; cur < R; ++cur) {
-        const int fj = first_col[cur];
-        if (fj >= 0 && !v_positive) {                    // known first step (see above)
-            bool ok = false;
-            if (lane == (fj & 31)) {
+        if (!v_positive) {                               // run of rows whose first step is known (see above)
+            cur = known_first_step_run(cur, R, first_col, first_val, r4c_s, v_s, u_s, c4r_s, lane);
+            if (cur >= R) break;
 #pragma unroll
-                for (int q = 0; q < CPL; ++q)
-                    if (q == (fj >> 5)) ok = r4c[q] < 0 && v[q] == 0.0;
-            }
-            if (__ballot_sync(kFull, ok)) {
-                if (ok) {
-#pragma unroll
-                    for (int q = 0; q < CPL; ++q)
-                        if (q == (fj >> 5)) r4c[q] = cur;
-                }
-                if (lane == 0) { u_s[cur] = first_step_dual(first_val[cur]); c4r_s[cur] = fj; }
-                continue;
-            }
+            for (int q = 0; q < CPL; ++q)
+                if (lane + 32 * q < Cc) r4c[q] = r4c_s[lane + 32 * q];
         }
 #pragma unroll
         for (int q = 0; q < CPL; ++q) {
@@ -279,7 +308,9 @@ __device__ inline int solve_warp(const float* cost, int R, int Cc, int ld, doubl
         unsigned scanned = 0;                            // bit q: own column q scanned in this search
         int i = cur, n_todo = Cc, sink = -1;
         double minv = 0.0;
+        LSAP_STAT(1, 1);
         while (sink < 0) {
+            LSAP_STAT(2, 1);
             const double ui = u_s[i];
             const float* crow = cost + (size_t)i * ld;
             unsigned long long bk = ~0ull;
@@ -333,6 +364,7 @@ __device__ inline int solve_warp(const float* cost, int R, int Cc, int ld, doubl
                 const double delta = minv - dist[q];
                 if (r4c[q] >= 0) u_s[r4c[q]] += delta;
                 v[q] -= delta;
+                v_s[lane + 32 * q] = v[q];
                 vp = vp || v[q] > 0.0;
             }
         v_positive = v_positive || __any_sync(kFull, vp);
@@ -348,17 +380,15 @@ __device__ inline int solve_warp(const float* cost, int R, int Cc, int ld, doubl
 #pragma unroll
                 for (int q = 0; q < CPL; ++q)
                     if (q == (j >> 5)) r4c[q] = pi;
+                r4c_s[j] = pi;
             }
             int prev = 0;
             if (lane == 0) { prev = c4r_s[pi]; c4r_s[pi] = j; }
             j = __shfl_sync(kFull, prev, 0);
             if (pi == cur) break;
         }
-        __syncwarp();                                    // u_s updates visible before the next search
+        __syncwarp();                                    // u_s / v_s / r4c_s updates visible before the next search
     }
-#pragma unroll
-    for (int q = 0; q < CPL; ++q)
-        if (lane + 32 * q < Cc) r4c_s[lane + 32 * q] = r4c[q];
     __syncwarp();
     return B200_OK;
 }
@@ -389,17 +419,10 @@ __device__ inline int solve_regs(const float* cost, int R, int Cc, int ld, const
     group_sync(nt);
     int par = 0;
     for (int cur = 0;; ++cur) {
-        if (tid == 0) {                                   // run of rows with a known first step (see above)
+        if (wid == 0) {                                   // run of rows with a known first step (see above)
             int c = cur;
-            if (!w.red_un[0])
-                for (; c < R; ++c) {
-                    const int fj = first_col[c];
-                    if (fj < 0 || w.r4c[fj] >= 0 || w.v[fj] != 0.0) break;
-                    w.r4c[fj] = c;
-                    w.c4r[c] = fj;
-                    w.u[c] = first_step_dual(first_val[c]);
-                }
-            *w.flag = c;
+            if (!w.red_un[0]) c = known_first_step_run(cur, R, first_col, first_val, w.r4c, w.v, w.u, w.c4r, lane);
+            if (lane == 0) *w.flag = c;
         }
         group_sync(nt);
         cur = *w.flag;
@@ -416,7 +439,9 @@ __device__ inline int solve_regs(const float* cost, int R, int Cc, int ld, const
         unsigned scanned = 0;
         int i = cur, n_todo = Cc, sink = -1;
         double minv = 0.0;
+        if (tid == 0) LSAP_STAT(1, 1);
         while (sink < 0) {
+            if (tid == 0) LSAP_STAT(2, 1);
             const double ui = w.u[i];
             const float* crow = cost + (size_t)i * ld;
             unsigned long long bk = ~0ull;
@@ -500,6 +525,66 @@ __device__ inline int solve_regs(const float* cost, int R, int Cc, int ld, const
     return B200_OK;
 }
 
+// One pass over the matrix for solve_block: NaN / -inf check, optional copy to shared memory, and for every row
+// the column of its unique minimum (or -1).  A warp takes RB rows at a time and issues all their loads (LPR per
+// lane and row, 16 in flight) before touching any: the pass is a few global round trips per warp instead of
+// one per row.  NaN is detected through the row sum (a NaN makes it NaN; +inf with -inf does too, and -inf is
+// invalid anyway), -inf through the minimum.  Returns 1 on an invalid entry (this thread's view).
+template <int LPR>
+__device__ __forceinline__ int row_minima_pass(const float* cost, int R, int Cc, int ld, float* stage_or_null,
+                                               int* first_col, float* first_val) {
+    constexpr int RB = LPR >= 16 ? 1 : 16 / LPR;
+    const unsigned kFull = 0xffffffffu;
+    const float kPosInf = __int_as_float(0x7f800000);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    int bad = 0;
+    for (int i0 = wid * RB; i0 < R; i0 += nw * RB) {
+        float c[RB][LPR];
+#pragma unroll
+        for (int rb = 0; rb < RB; ++rb)
+#pragma unroll
+            for (int k = 0; k < LPR; ++k) {
+                const int i = i0 + rb, j = lane + 32 * k;
+                c[rb][k] = (i < R && j < Cc) ? cost[(size_t)i * ld + j] : kPosInf;
+            }
+#pragma unroll
+        for (int rb = 0; rb < RB; ++rb) {
+            const int i = i0 + rb;
+            if (i >= R) break;                                    // uniform across the warp
+            float m = kPosInf, sum = 0.0f;
+#pragma unroll
+            for (int k = 0; k < LPR; ++k) {
+                m = fminf(m, c[rb][k]);                           // fminf ignores NaN; the sum catches it
+                sum += c[rb][k];
+                if (stage_or_null && lane + 32 * k < Cc) stage_or_null[i * Cc + lane + 32 * k] = c[rb][k];
+            }
+            if (sum != sum || m == -kPosInf) bad = 1;
+            const unsigned bits = (unsigned)__float_as_int(m + 0.0f);                      // -0.0 ties with +0.0
+            const unsigned key = bits ^ ((unsigned)((int)bits >> 31) | 0x80000000u);      // order-preserving
+            const unsigned kmin = __reduce_min_sync(kFull, key);
+            const float wm = __int_as_float((int)(kmin ^ ((kmin >> 31) ? 0x80000000u : 0xffffffffu)));
+            int cnt = 0, kk = 0;
+#pragma unroll
+            for (int k = 0; k < LPR; ++k)
+                if (c[rb][k] == wm) { ++cnt; kk = k; }
+            const int total = __reduce_add_sync(kFull, cnt);
+            if (total == 1 && wm < kPosInf) {
+                if (cnt == 1) {
+                    float val = 0.0f;
+#pragma unroll
+                    for (int k = 0; k < LPR; ++k)
+                        if (k == kk) val = c[rb][k];
+                    first_col[i] = lane + 32 * kk;
+                    first_val[i] = val;
+                }
+            } else if (lane == 0) {
+                first_col[i] = -1;
+            }
+        }
+    }
+    return bad;
+}
+
 // Block-level driver shared by the operator kernel and the tracker: validates the matrix, optionally
 // stages it in shared memory and finds every row's unique minimum (all warps, a row each), then runs the
 // single-warp solver (Cc <= 128), the multi-warp register solver (up to 4 columns per thread) or, beyond
@@ -512,39 +597,50 @@ __device__ inline int solve_block(const float* cost, int R, int Cc, int ld, cons
     const float kNegInf = -__int_as_float(0x7f800000);
     int* first_col = w.seen_rows;                         // [R] column of the row's unique minimum, or -1
     float* first_val = reinterpret_cast<float*>(w.dist);  // [R] that minimum
-    // One pass over the matrix, a warp per row: NaN / -inf check, optional copy to shared memory, row minimum.
-    for (int i = tid >> 5; i < R; i += nthr >> 5) {
-        const float* row = cost + (size_t)i * ld;
-        float m = __int_as_float(0x7f800000);
-        int mj = -1, cnt = 0;
+    LSAP_CLK(0);
+    const int lpr = (Cc + 31) / 32;
+    bad = lpr <= 1    ? row_minima_pass<1>(cost, R, Cc, ld, stage_or_null, first_col, first_val)
+          : lpr <= 2  ? row_minima_pass<2>(cost, R, Cc, ld, stage_or_null, first_col, first_val)
+          : lpr <= 4  ? row_minima_pass<4>(cost, R, Cc, ld, stage_or_null, first_col, first_val)
+          : lpr <= 8  ? row_minima_pass<8>(cost, R, Cc, ld, stage_or_null, first_col, first_val)
+          : lpr <= 16 ? row_minima_pass<16>(cost, R, Cc, ld, stage_or_null, first_col, first_val)
+                      : -1;
+    if (bad < 0) {                                        // more than 512 columns: plain loop, a row per warp
+        bad = 0;
+        for (int i = tid >> 5; i < R; i += nthr >> 5) {
+            const float* row = cost + (size_t)i * ld;
+            float m = __int_as_float(0x7f800000);
+            int mj = -1, cnt = 0;
 #pragma unroll 4
-        for (int j = lane; j < Cc; j += 32) {
-            const float c = row[j];
-            if (c != c || c == kNegInf) bad = 1;
-            if (stage_or_null) stage_or_null[i * Cc + j] = c;
-            if (c < m) { m = c; mj = j; cnt = 1; }
-            else if (c == m) ++cnt;
+            for (int j = lane; j < Cc; j += 32) {
+                const float c = row[j];
+                if (c != c || c == kNegInf) bad = 1;
+                if (stage_or_null) stage_or_null[i * Cc + j] = c;
+                if (c < m) { m = c; mj = j; cnt = 1; }
+                else if (c == m) ++cnt;
+            }
+            const unsigned bits = (unsigned)__float_as_int(m + 0.0f);                      // -0.0 ties with +0.0
+            const unsigned key = bits ^ ((unsigned)((int)bits >> 31) | 0x80000000u);      // order-preserving
+            const unsigned kmin = __reduce_min_sync(0xffffffffu, key);
+            const unsigned eq = __ballot_sync(0xffffffffu, key == kmin && mj >= 0);
+            if (eq && lane == __ffs(eq) - 1) {
+                const bool unique = __popc(eq) == 1 && cnt == 1 && m < __int_as_float(0x7f800000);
+                first_col[i] = unique ? mj : -1;
+                first_val[i] = m;
+            }
+            if (!eq && lane == 0) first_col[i] = -1;
         }
-        const unsigned bits = (unsigned)__float_as_int(m + 0.0f);                      // -0.0 ties with +0.0
-        const unsigned key = bits ^ ((unsigned)((int)bits >> 31) | 0x80000000u);      // order-preserving
-        const unsigned kmin = __reduce_min_sync(0xffffffffu, key);
-        const unsigned eq = __ballot_sync(0xffffffffu, key == kmin && mj >= 0);
-        if (eq && lane == __ffs(eq) - 1) {
-            const bool unique = __popc(eq) == 1 && cnt == 1 && m < __int_as_float(0x7f800000);
-            first_col[i] = unique ? mj : -1;
-            first_val[i] = m;
-        }
-        if (!eq && lane == 0) first_col[i] = -1;
     }
     bad = __syncthreads_or(bad);
+    LSAP_CLK(1);
     if (bad) return B200_ENUMERIC;
     if (stage_or_null) { cost = stage_or_null; ld = Cc; }
     __shared__ int s_status;
     const int nt = nthr < kMaxThreads ? (nthr & ~31) : kMaxThreads;
     if (Cc <= kWarpSolverMaxCols) {
         if (tid < 32) {
-            const int rc = Cc <= 64 ? solve_warp<2>(cost, R, Cc, ld, w.u, w.c4r, w.r4c, first_col, first_val)
-                                    : solve_warp<4>(cost, R, Cc, ld, w.u, w.c4r, w.r4c, first_col, first_val);
+            const int rc = Cc <= 64 ? solve_warp<2>(cost, R, Cc, ld, w.u, w.c4r, w.r4c, w.v, first_col, first_val)
+                                    : solve_warp<4>(cost, R, Cc, ld, w.u, w.c4r, w.r4c, w.v, first_col, first_val);
             if (tid == 0) s_status = rc;
         }
     } else if (tid < nt) {
@@ -556,6 +652,7 @@ __device__ inline int solve_block(const float* cost, int R, int Cc, int ld, cons
         if (tid == 0) s_status = rc;
     }
     __syncthreads();
+    LSAP_CLK(2);
     return s_status;
 }
 

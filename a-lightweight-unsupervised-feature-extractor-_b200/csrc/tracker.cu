@@ -1107,6 +1107,19 @@ extern "C" int b200_tracker_export(b200_tracker* t, int stream_idx, int32_t* ids
 }
 
 #ifdef B200_TRK_TIMING
+#ifdef B200_TRK_TIMING
+extern "C" int b200_debug_lsap_stats(unsigned long long* out4, int reset) {
+    unsigned long long z[4] = {0, 0, 0, 0};
+    if (out4) cudaMemcpyFromSymbol(out4, b200::lsap::g_lsap_stats, sizeof(z));
+    if (reset) cudaMemcpyToSymbol(b200::lsap::g_lsap_stats, z, sizeof(z));
+    return 0;
+}
+extern "C" int b200_debug_lsap_clk(long long* out8) {
+    cudaMemcpyFromSymbol(out8, b200::lsap::g_lsap_clk, 8 * sizeof(long long));
+    return 0;
+}
+#endif
+
 extern "C" int b200_debug_timing(long long* out32) {
     return cudaMemcpyFromSymbol(out32, b200::trk::g_timing, sizeof(long long) * 32) == cudaSuccess ? 0 : -2;
 }
