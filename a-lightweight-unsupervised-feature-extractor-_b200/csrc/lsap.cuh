@@ -591,14 +591,26 @@ __device__ __forceinline__ int row_minima_pass(const float* cost, int R, int Cc,
 // that, the shared-memory one.  Measured on B200 (association step, one stream): 64 columns 135 us (warp) vs
 // 149 us (multi-warp); 128: 213 vs 220; 256: 752 vs 392; 512: 1 387 (shared-memory solver) vs 897.  Every thread of the CTA must call; the
 // status is returned on every thread and w.c4r / w.r4c hold the assignment.
-__device__ inline int solve_block(const float* cost, int R, int Cc, int ld, const Work& w, float* stage_or_null) {
+// pre_col / pre_val (optional, R entries in global memory): the producer of the matrix already knows every
+// row's unique minimum (column, or -1) and has checked the row (-2 = NaN / -inf): when the matrix is not to be
+// staged, the pass over it is skipped altogether.
+__device__ inline int solve_block(const float* cost, int R, int Cc, int ld, const Work& w, float* stage_or_null,
+                                  const int* pre_col = nullptr, const float* pre_val = nullptr) {
     const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31;
     int bad = 0;
     const float kNegInf = -__int_as_float(0x7f800000);
     int* first_col = w.seen_rows;                         // [R] column of the row's unique minimum, or -1
     float* first_val = reinterpret_cast<float*>(w.dist);  // [R] that minimum
     LSAP_CLK(0);
-    const int lpr = (Cc + 31) / 32;
+    const int lpr = (pre_col && !stage_or_null) ? 0 : (Cc + 31) / 32;
+    if (lpr == 0) {
+        for (int i = tid; i < R; i += nthr) {
+            const int fc = pre_col[i];
+            if (fc == -2) bad = 1;
+            first_col[i] = fc;
+            first_val[i] = pre_val[i];
+        }
+    } else
     bad = lpr <= 1    ? row_minima_pass<1>(cost, R, Cc, ld, stage_or_null, first_col, first_val)
           : lpr <= 2  ? row_minima_pass<2>(cost, R, Cc, ld, stage_or_null, first_col, first_val)
           : lpr <= 4  ? row_minima_pass<4>(cost, R, Cc, ld, stage_or_null, first_col, first_val)

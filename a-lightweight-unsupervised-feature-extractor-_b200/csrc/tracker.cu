@@ -63,6 +63,8 @@ struct Dev {
     // per-step scratch
     float *det_unit, *det_z, *det_boxf, *det_conff, *prev_boxf, *prev_conff, *C1, *C1T, *C2, *C2T;
     double* gate_SI;
+    int* row_fc;                     // stage 1, written by the cost kernel: column of each row's unique minimum (-1: none, -2: NaN / -inf in the row)
+    float* row_fv;                   //          that minimum
     int *rows_main, *rows_reid, *cnt, *ud1, *det_used, *m_row, *m_det, *m_app, *tmp;
     int2 *work1, *work2;             // (stream, row * 64 + detection tile) items of the two cost launches
     int* wcount;                     // [3] items queued for this step: cost1, cost2, updates
@@ -297,6 +299,34 @@ __global__ void __launch_bounds__(cost::kThreads) cost2_kernel(Dev d) {
     }
 }
 
+// Per-row summary of a stage-1 cost row for the assignment kernel's known-first-step rule (lsap.cuh): each lane
+// feeds the entries it wrote; finish() leaves the column of the row's unique minimum (-1 if the minimum is tied
+// or +inf, -2 if the row holds a NaN or -inf, which scipy rejects) and its value.
+struct RowMin {
+    float m = __builtin_huge_valf(), first = 0.0f;
+    int mj = -1, cnt = 0, bad = 0;
+    __device__ __forceinline__ void see(float c, int j) {
+        if (c != c || c == -__builtin_huge_valf()) bad = 1;
+        if (c < m) { m = c; mj = j; cnt = 1; first = c; }
+        else if (c == m) ++cnt;
+    }
+    __device__ __forceinline__ void finish(int* fc, float* fv, int lane) const {
+        const unsigned kFull = 0xffffffffu;
+        const unsigned bits = (unsigned)__float_as_int(m + 0.0f);                      // -0.0 ties with +0.0
+        const unsigned key = bits ^ ((unsigned)((int)bits >> 31) | 0x80000000u);
+        const unsigned kmin = __reduce_min_sync(kFull, key);
+        const unsigned eq = __ballot_sync(kFull, key == kmin && mj >= 0);
+        const bool any_bad = __any_sync(kFull, bad);
+        const int total = __reduce_add_sync(kFull, (key == kmin && mj >= 0) ? cnt : 0);
+        if (any_bad) { if (lane == 0) *fc = -2; return; }
+        if (eq && lane == __ffs(eq) - 1) {
+            *fc = (total == 1 && m < __builtin_huge_valf()) ? mj : -1;
+            *fv = first;
+        }
+        if (!eq && lane == 0) *fc = -1;
+    }
+};
+
 // ---- stage-1 cost, gate first -----------------------------------------------------------------------
 // apply_kalman_gating (:306-338) overwrites every pair with d2 > maha_thr by 1e9 AFTER the reference has
 // computed its full cost (:496-511).  The result does not depend on the order, and in steady state ~98 %
@@ -342,6 +372,7 @@ __global__ void __launch_bounds__(kCost1Warps * 32) cost1_sparse_kernel(Dev d) {
         const float pconf = d.prev_conff[slot];
         float inv0 = 0.0f, inv1 = 0.0f;           // 1 / (|bank_t| + 1e-12) of rows lane and lane + 32 (:188-189)
         bool have_norm = false;
+        RowMin rmin;
         for (int j0 = 0; j0 < N; j0 += 32) {
             const int j = j0 + lane;
             bool alive = false;
@@ -398,8 +429,10 @@ __global__ void __launch_bounds__(kCost1Warps * 32) cost1_sparse_kernel(Dev d) {
                     total_c = cost::pair_cost(pb, d.det_boxf + (db + j) * 4, pconf, d.det_conff[db + j], d.pw, c_app).total;
                 d.C1[(sb + r) * d.MD + j] = total_c;
                 d.C1T[(db + j) * d.MT + r] = total_c;
+                rmin.see(total_c, j);
             }
         }
+        rmin.finish(d.row_fc + sb + r, d.row_fv + sb + r, lane);
     }
 }
 
@@ -450,6 +483,7 @@ __global__ void __launch_bounds__(kCost1Warps * 32, 2) cost1_sparse32_kernel(Dev
         float4 bv[32];
         float inv = 0.0f;                          // 1 / (|bank_lane| + 1e-12), :188-189
         bool have_bank = false;
+        RowMin rmin;
         for (int j0 = 0; j0 < N; j0 += 32) {
             const int j = j0 + lane;
             bool alive = false;
@@ -501,8 +535,10 @@ __global__ void __launch_bounds__(kCost1Warps * 32, 2) cost1_sparse32_kernel(Dev
                     total_c = cost::pair_cost(pb, d.det_boxf + (db + j) * 4, pconf, d.det_conff[db + j], d.pw, c_app).total;
                 d.C1[(sb + r) * d.MD + j] = total_c;
                 d.C1T[(db + j) * d.MT + r] = total_c;
+                rmin.see(total_c, j);
             }
         }
+        rmin.finish(d.row_fc + sb + r, d.row_fv + sb + r, lane);
     }
 }
 
@@ -660,7 +696,10 @@ __global__ void __launch_bounds__(kThreads) assign_kernel(Dev d, int smem_matrix
         const lsap::Work w = lsap::carve(smem_raw, R, Cc);
         float* stage = (size_t)R * Cc <= (size_t)smem_matrix_floats
                            ? reinterpret_cast<float*>(smem_raw + lsap::work_bytes(R, Cc)) : nullptr;
-        const int rc = lsap::solve_block(costp, R, Cc, ld, w, stage);
+        // stage 1, rows = tracks: the cost kernel has already summarised every row (RowMin)
+        const bool pre = STAGE == 1 && !tall;
+        const int rc = lsap::solve_block(costp, R, Cc, ld, w, stage, pre ? d.row_fc + sb : nullptr,
+                                         pre ? d.row_fv + sb : nullptr);
         if (tid == 0) s_rc = rc;
         __syncthreads();
         if (STAGE == 1) TRK_STAMP(1);
@@ -879,6 +918,7 @@ extern "C" int b200_tracker_create(b200_tracker** out, int n_streams, int max_tr
     TAKE(det_conff, float, S * MD); TAKE(prev_boxf, float, S * MT * 4); TAKE(prev_conff, float, S * MT);
     TAKE(C1, float, S * MT * MD); TAKE(C1T, float, S * MT * MD); TAKE(C2, float, S * MT * MD);
     TAKE(C2T, float, S * MT * MD); TAKE(gate_SI, double, S * MT * 16);
+    TAKE(row_fc, int, S * MT); TAKE(row_fv, float, S * MT);
     TAKE(rows_main, int, S * MT); TAKE(rows_reid, int, S * MT); TAKE(cnt, int, S * trk::kHdr);
     TAKE(ud1, int, S * MD); TAKE(det_used, int, S * MD); TAKE(m_row, int, S * MT); TAKE(m_det, int, S * MT);
     TAKE(m_app, int, S * MT); TAKE(tmp, int, S * MT);
@@ -905,6 +945,7 @@ extern "C" int b200_tracker_create(b200_tracker** out, int n_streams, int max_tr
     PTR(miss, int); PTR(age, int); PTR(last_frame, int); PTR(order, int); PTR(free_list, int); PTR(hdr, int);
     PTR(det_unit, float); PTR(det_z, float); PTR(det_boxf, float); PTR(det_conff, float); PTR(prev_boxf, float);
     PTR(prev_conff, float); PTR(C1, float); PTR(C1T, float); PTR(C2, float); PTR(C2T, float); PTR(gate_SI, double);
+    PTR(row_fc, int); PTR(row_fv, float);
     PTR(rows_main, int); PTR(rows_reid, int); PTR(cnt, int); PTR(ud1, int); PTR(det_used, int); PTR(m_row, int);
     PTR(m_det, int); PTR(m_app, int); PTR(tmp, int); PTR(work1, int2); PTR(work2, int2); PTR(wcount, int);
     PTR(upd_slot, int); PTR(upd_det, int); PTR(upd_cost, float); PTR(upd_flag, uint8_t);

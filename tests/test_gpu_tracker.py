@@ -147,6 +147,26 @@ def test_tracker_queries_and_errors():
         small.update(synth.Scene(1, 12, 640, 640).step())     # 12 live + 12 new could exceed 16
 
 
+@pytest.mark.parametrize("n", [12, 300])
+def test_tracker_nan_embedding_raises_like_scipy(n):
+    """A NaN embedding on a detection that passes the gate puts NaN into the cost matrix; the reference dies in
+    scipy's linear_sum_assignment with ValueError (hung.py:28).  n = 12 takes the staged validation pass, n = 300
+    the row summaries written by the cost kernel."""
+    cfg = dict(SHIPPED_CONF)
+    ref = tracker_ref.TrackerRef(cfg)
+    trk = Tracking(conf=cfg, max_tracks=2 * n + 64, max_dets=n)
+    scene = synth.Scene(5, n, 1280, 1280)
+    for _ in range(4):
+        obj = scene.step()
+        assert trk.update(obj) == ref.update(obj)
+    obj = scene.step()
+    obj["embs"][n // 2] = np.full(128, np.nan, np.float32)
+    with pytest.raises(ValueError):
+        ref.update(obj)
+    with pytest.raises(ValueError):
+        trk.update(obj)
+
+
 def test_tracker_grows_like_the_unbounded_reference():
     """Start far too small: every capacity is outgrown mid-sequence and the outputs still match the oracle."""
     cfg = dict(SHIPPED_CONF, lost_reid_after=4, max_age=10)
