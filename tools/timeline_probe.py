@@ -7,7 +7,7 @@ import torch
 import bench
 from alufe_b200 import _lib
 
-S, W = 64, 40
+S, W = (int(sys.argv[1]) if len(sys.argv) > 1 else 64), 40
 dev = torch.device("cuda", 0)
 torch.cuda.set_device(0)
 lib = ctypes.CDLL(_lib.LIB_PATH)
