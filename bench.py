@@ -341,19 +341,30 @@ def main():
     # before the W warm-up steps, so the timed K steps always see the same workload.
     pre = max(0, 35 - W)
     grp = StreamGroup(S, pre + W + K, rank, dev)
-    gathered = torch.zeros((8, world, S, grp.trk.stride), dtype=torch.int32, device=dev) if world > 1 else None
+    # The only inter-GPU traffic: the per-stream result tables, all-gathered for the consumer of tracking.py:329.
+    # They are gathered GATHER_EVERY frames at a time ("optionally gather every K frames"):
+    # a NCCL kernel per step holds SM slots while it waits for the slowest rank, which cost 17 % at 8 GPUs.
+    GATHER_EVERY = 8
+    n_total = pre + W + K
+    gathered = (torch.zeros((2, world, GATHER_EVERY, S, grp.trk.stride), dtype=torch.int32, device=dev)
+                if world > 1 else None)
     pending = []
 
-    def gather(i):                                   # the only inter-GPU traffic: per-stream result tables
-        if world > 1:
-            pending.append(dist.all_gather_into_tensor(gathered[i % 8].view(-1), grp.results[i].view(-1), async_op=True))
-            if len(pending) > 6:
-                pending.pop(0).wait()
-
     def gather_after(i):
-        if world > 1:
-            torch.cuda.current_stream(dev).wait_stream(grp.sB)     # NCCL orders after the current stream
-            gather(i)
+        if world == 1:
+            return
+        full = (i + 1) % GATHER_EVERY == 0
+        if not (full or i == n_total - 1 or i == pre + W - 1):     # also flush at the end of each run() call
+            return
+        i0 = (i // GATHER_EVERY) * GATHER_EVERY
+        n = i + 1 - i0
+        torch.cuda.current_stream(dev).wait_stream(grp.sB)         # NCCL orders after the current stream
+        dst = gathered[(i // GATHER_EVERY) % 2][:, :n] if n == GATHER_EVERY else \
+            torch.empty((world, n, S, grp.trk.stride), dtype=torch.int32, device=dev)
+        pending.append(dist.all_gather_into_tensor(dst.reshape(-1) if n == GATHER_EVERY else dst.view(-1),
+                                                   grp.results[i0:i0 + n].reshape(-1), async_op=True))
+        if len(pending) > 1:
+            pending.pop(0).wait()
 
     grp.run(0, pre + W, after_step=gather_after)
     for h in pending:
@@ -491,6 +502,8 @@ def main():
                        "l2": "inputs larger than L2: each step reads %d maps (%.0f MB) and writes %.0f MB; %d map sets and %d "
                              "output buffers rotate" % (S, grp.map_b / 1e6, grp.out_b / 1e6, grp.nmap, grp.nout),
                        "pipeline": "ROI Align of frame t+1 (stream A) overlaps the association of frame t (stream B)",
+                       "gather": ("result tables of all ranks all-gathered with NCCL every %d frames" % GATHER_EVERY)
+                       if world > 1 else "single GPU: none",
                        "state_dtype": "f64 Kalman/assignment duals, f32 ROI/cost"},
             "clocks": sampler.summary(),
             "e2e": {"value": world * S * n_e2e / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
