@@ -35,7 +35,14 @@ def _worker(rank, world, port, n_streams, stride, q):
         work.wait()
         out2 = finish()
         ok = all(int(out[s, 0]) == 100 * s and int(out[s, stride - 1]) == 100 * s + stride - 1 for s in range(n_streams))
-        q.put((rank, ok and torch.equal(out, out2), tuple(out.shape)))
+        # three frames per collective (what bench.py does eight at a time): frame f adds 7 * f to every entry
+        frames = torch.stack([local + 7 * f for f in range(3)])
+        out3 = g.gather_frames(frames)
+        work, finish = g.gather_frames(frames, async_op=True)
+        work.wait()
+        ok3 = tuple(out3.shape) == (3, n_streams, stride) and torch.equal(out3, finish()) and \
+            all(torch.equal(out3[f], out + 7 * f) for f in range(3))
+        q.put((rank, ok and ok3 and torch.equal(out, out2), tuple(out.shape)))
     finally:
         dist.destroy_process_group()
 
