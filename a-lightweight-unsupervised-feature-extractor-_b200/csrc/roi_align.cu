@@ -21,6 +21,17 @@
 // instantiation, take exact but slower paths.  Sample coordinates are evaluated with
 // the same operation order as torchvision and without FMA contraction so that cell
 // selection agrees with the CPU op.
+//
+// Kernels, by launch size (launch_tile):
+//   roi_align_tile_kernel    fewer than 16 384 tiles: steps 1-4 fused, one tile per warp (single-stream latency);
+//   roi_prep_kernel          large launches: step 1 once per ROI instead of once per channel tile, then
+//   roi_align_multi_kernel     NCHW / half / 7x7: the tile body with a warp walking eight tiles (next ROI record
+//                              loaded during the current tile, bulk-store wait deferred), or
+//   roi_align_pipe_kernel      channels-last float32: software pipeline over tiles with two footprint buffers
+//                              (16-byte cp.async.cg copies of tile n+1 while tile n accumulates);
+//   roi_align_generic_kernel other output sizes: one thread per output element.
+// Output is NCHW like the reference's, or channels-last on request (b200_roi_align_fwd_ex): lane = channel then
+// stores whole lines straight from the accumulators.
 #include <cuda_fp16.h>
 
 #include "common.cuh"
