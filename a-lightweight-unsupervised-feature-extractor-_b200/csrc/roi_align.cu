@@ -51,6 +51,8 @@ constexpr int kCellCap = kFootCap * kFootCap;
 template <typename T> __device__ __forceinline__ float ldf(const T* p);
 template <> __device__ __forceinline__ float ldf<float>(const float* p) { return __ldg(p); }
 template <> __device__ __forceinline__ float ldf<__half>(const __half* p) { return __half2float(__ldg(p)); }
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(__half v) { return __half2float(v); }
 template <typename T> __device__ __forceinline__ T from_f(float v);
 template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
 template <> __device__ __forceinline__ __half from_f<__half>(float v) { return __float2half_rn(v); }
@@ -589,51 +591,60 @@ struct PipeSmem {
     static_assert(kFloatsPerWarp >= L::kFloatsPerWarp, "the fallback path needs an output tile + tables");
 };
 
-// Starts the copies of one tile of a channels-last map: V[cell][channel] (no skew needed: a cell's 32 channels are
-// one 128-byte line in both the map and the buffer) and the ROI's ready-made weight tables.  With a full,
-// 16-byte aligned tile, eight lanes move one cell (16 bytes each) and a warp instruction moves four cells.
-template <int PH, int PW>
-__device__ __forceinline__ void pipe_issue(const float* __restrict__ feat, int C, int H, int W, const int4 h0,
+// Starts the copies of one tile of a channels-last map: V[cell][channel] in the map's element type (no skew
+// needed: a cell's 32 channels are one 128-byte -- half: 64-byte -- line in both the map and the buffer) and the
+// ROI's ready-made weight tables.  With a full, 16-byte aligned tile, 16-byte copies move four (half: eight)
+// cells per warp instruction; the 4-byte fallback exists for float only (`pipe_can_stage`).
+template <int PH, int PW, typename T>
+__device__ __forceinline__ void pipe_issue(const T* __restrict__ feat, int C, int H, int W, const int4 h0,
                                            const int4 h1, long long k, int c0, int cn, bool vec16,
                                            const float* __restrict__ prep_tabs, unsigned sv, int lane) {
     using L = TileSmem<PH, PW>;
+    constexpr int kEs = (int)sizeof(T), kLpc = 32 * kEs / 16, kCpi = 32 / kLpc;     // lanes per cell, cells per instruction
     const int b = h0.x, ymin = h0.y, xmin = h0.z, FY = h0.w, FX = h1.x;
     const float* tsrc = prep_tabs + (size_t)k * L::kTabFloats;
     for (int i = lane; i < L::kTabFloats / 4; i += 32) cp_async16_s(sv + 4u * (kCellCap * 32) + 16u * i, tsrc + 4 * i);
     const int cells = FY * FX;
     if (vec16 && cn == 32) {
-        int m = lane >> 3, x = m, r = 0;
+        int m = lane / kLpc, x = m, r = 0;
         while (x >= FX && r < FY) { x -= FX; ++r; }
-        const float* src = feat + (((size_t)b * H + ymin + r) * W + xmin + x) * C + c0 + (lane & 7) * 4;
-        const size_t step = (size_t)4 * C, wrap = (size_t)(W - FX) * C;
-        unsigned dst = sv + 128u * m + 16u * (lane & 7);
-        for (; m < cells; m += 4, dst += 512u) {
+        const T* src = feat + (((size_t)b * H + ymin + r) * W + xmin + x) * C + c0 + (lane % kLpc) * (16 / kEs);
+        const size_t step = (size_t)kCpi * C, wrap = (size_t)(W - FX) * C;
+        unsigned dst = sv + (unsigned)(32 * kEs) * m + 16u * (lane % kLpc);
+        for (; m < cells; m += kCpi, dst += (unsigned)(32 * kEs * kCpi)) {
             cp_async16_s(dst, src);
-            x += 4;
+            x += kCpi;
             src += step;
             while (x >= FX) { x -= FX; src += wrap; }
         }
-    } else if (lane < cn) {
-        const float* row = feat + (((size_t)b * H + ymin) * W + xmin) * C + c0 + lane;
+    } else if (kEs == 4 && lane < cn) {
+        const T* row = feat + (((size_t)b * H + ymin) * W + xmin) * C + c0 + lane;
         unsigned dst = sv + 4u * lane;
         for (int r = 0; r < FY; ++r, row += (size_t)W * C) {
-            const float* src = row;
+            const T* src = row;
 #pragma unroll 4
             for (int x = 0; x < FX; ++x, src += C, dst += 128) cp_async4_s(dst, src);
         }
     }
 }
 
-template <int PH, int PW, bool OCL>
+// A tile can go through the pipeline if roi_prep_kernel staged its footprint and, for half maps, the 16-byte
+// copy applies (there is no 2-byte cp.async); other tiles take process_tile() between two pipeline flushes.
+template <typename T>
+__device__ __forceinline__ bool pipe_can_stage(const int4 rec1, bool vec16, int cn) {
+    return rec1.y != 0 && (sizeof(T) == 4 || (vec16 && cn == 32));
+}
+
+template <int PH, int PW, bool OCL, typename T>
 __global__ void __launch_bounds__(kPipeWarps * 32, (B200_ROI_MIN_CTAS * 2 + kPipeWarps - 1) / kPipeWarps)
-roi_align_pipe_kernel(const float* __restrict__ feat, int B, int C, int H, int W, const float* __restrict__ rois,
-                      long long K, float scale, int sr, int aligned, float* __restrict__ out, int ctiles,
+roi_align_pipe_kernel(const T* __restrict__ feat, int B, int C, int H, int W, const float* __restrict__ rois,
+                      long long K, float scale, int sr, int aligned, T* __restrict__ out, int ctiles,
                       const RoiPrep* __restrict__ prep, const float* __restrict__ prep_tabs, int group_warps,
                       int tiles_per_warp) {
     using L = TileSmem<PH, PW>;
     using P = PipeSmem<PH, PW>;
-    constexpr int PHP = L::kPHP, NB = PH * PW;
-    static_assert(OCL || NB % 4 == 0, "16-byte stores of a lane's output row");
+    constexpr int PHP = L::kPHP, NB = PH * PW, kEs = (int)sizeof(T);
+    static_assert(OCL || (NB * kEs) % (kEs == 4 ? 16 : 4) == 0, "vector stores of a lane's output row");
     extern __shared__ __align__(16) float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* base = smem + (size_t)warp * P::kFloatsPerWarp;
@@ -655,8 +666,9 @@ roi_align_pipe_kernel(const float* __restrict__ feat, int B, int C, int H, int W
     unsigned ka = t / (unsigned)ctiles;
     int ca = (int)(t - ka * (unsigned)ctiles) * 32;
     int4 a0 = reinterpret_cast<const int4*>(prep + ka)[0], a1 = reinterpret_cast<const int4*>(prep + ka)[1];
-    const bool vec16 = (C & 3) == 0 && (reinterpret_cast<uintptr_t>(feat) & 15) == 0;
-    if (a1.y) pipe_issue<PH, PW>(feat, C, H, W, a0, a1, ka, ca, min(32, C - ca), vec16, prep_tabs, sbase, lane);
+    const bool vec16 = ((C * kEs) & 15) == 0 && (reinterpret_cast<uintptr_t>(feat) & 15) == 0;
+    if (pipe_can_stage<T>(a1, vec16, min(32, C - ca)))
+        pipe_issue<PH, PW, T>(feat, C, H, W, a0, a1, ka, ca, min(32, C - ca), vec16, prep_tabs, sbase, lane);
     asm volatile("cp.async.commit_group;\n" ::: "memory");
     unsigned tn = t + stride, kn = 0;
     int cnx = 0;
@@ -671,65 +683,78 @@ roi_align_pipe_kernel(const float* __restrict__ feat, int B, int C, int H, int W
     for (;;) {
         const bool have_next = tn < total;
         const int cn = min(32, C - ca);
-        if (!a1.y) {            // footprint too large for a buffer: nothing is in flight, use the whole region
-            process_tile<PH, PW, true, float, false, OCL>(feat, B, C, H, W, rois, scale, sr, aligned, out, (long long)ka,
-                                                          ca, cn, nullptr, nullptr, base, base + L::kMainFloats, lane);
+        if (!pipe_can_stage<T>(a1, vec16, cn)) {           // footprint too large for a buffer (or no 16-byte copy): nothing is in flight, use the whole region
+            process_tile<PH, PW, true, T, false, OCL>(feat, B, C, H, W, rois, scale, sr, aligned, out, (long long)ka,
+                                                      ca, cn, nullptr, nullptr, base, base + L::kMainFloats, lane);
             __syncwarp();
         }
-        if (have_next && n1.y)
-            pipe_issue<PH, PW>(feat, C, H, W, n0, n1, kn, cnx, min(32, C - cnx), vec16, prep_tabs,
-                               sbase + 4u * (unsigned)((par ^ 1) * P::kBufFloats), lane);
+        if (have_next && pipe_can_stage<T>(n1, vec16, min(32, C - cnx)))
+            pipe_issue<PH, PW, T>(feat, C, H, W, n0, n1, kn, cnx, min(32, C - cnx), vec16, prep_tabs,
+                                  sbase + 4u * (unsigned)((par ^ 1) * P::kBufFloats), lane);
         asm volatile("cp.async.commit_group;\n" ::: "memory");
-        // record of the tile after next: in registers by the time this tile is done
+        // record of the tile after next: requested after the accumulation below (the accumulators leave no room for
+        // eight more live registers) and in registers by the time the copy-out is done
         const unsigned tm = tn + stride;
         unsigned km = 0;
         int cm = 0;
         int4 m0 = make_int4(0, 0, 0, 0), m1 = m0;
-        if (have_next && tm < total) {
-            km = tm / (unsigned)ctiles;
-            cm = (int)(tm - km * (unsigned)ctiles) * 32;
-            m0 = reinterpret_cast<const int4*>(prep + km)[0];
-            m1 = reinterpret_cast<const int4*>(prep + km)[1];
-        }
-        if (a1.y) {
+        auto load_after_next = [&]() {
+            if (have_next && tm < total) {
+                km = tm / (unsigned)ctiles;
+                cm = (int)(tm - km * (unsigned)ctiles) * 32;
+                m0 = reinterpret_cast<const int4*>(prep + km)[0];
+                m1 = reinterpret_cast<const int4*>(prep + km)[1];
+            }
+        };
+        if (pipe_can_stage<T>(a1, vec16, cn)) {
             asm volatile("cp.async.wait_group 1;\n" ::: "memory");
             __syncwarp();
-            const float* sV = base + par * P::kBufFloats;
-            const float* sWy = sV + kCellCap * 32;
+            const T* sV = reinterpret_cast<const T*>(base + par * P::kBufFloats);
+            const float* sWy = base + par * P::kBufFloats + kCellCap * 32;
             const int FY = a0.w, FX = a1.x;
             float acc[PH][PW];
 #pragma unroll
             for (int a = 0; a < PH; ++a)
 #pragma unroll
                 for (int bq = 0; bq < PW; ++bq) acc[a][bq] = 0.0f;
-            separable_accumulate<PH, PW>(acc, sWy, sWy + kFootCap * PHP, FY, FX,
-                                         [&](int r, int x) { return sV[(r * FX + x) * 32 + lane]; });
+            separable_accumulate<PH, PW>(acc, sWy, sWy + kFootCap * PHP, FY, FX, [&](int r, int x) {
+                return to_f32(sV[(r * FX + x) * 32 + lane]);
+            });
+            load_after_next();
             if (OCL) {          // channels-last result: full-line stores straight from the accumulators
-                float* gl = out + (size_t)ka * NB * C + ca + lane;
+                T* gl = out + (size_t)ka * NB * C + ca + lane;
                 if (lane < cn) {
 #pragma unroll
                     for (int a = 0; a < PH; ++a)
 #pragma unroll
-                        for (int bq = 0; bq < PW; ++bq) __stcs(gl + (size_t)(a * PW + bq) * C, acc[a][bq]);
+                        for (int bq = 0; bq < PW; ++bq) gl[(size_t)(a * PW + bq) * C] = from_f<T>(acc[a][bq]);
                 }
             }
             __syncwarp();       // V of this tile is dead: its buffer now stages the output, 16 channels at a time
-            float* so = base + par * P::kBufFloats;
+            T* so = reinterpret_cast<T*>(base + par * P::kBufFloats);
 #pragma unroll
             for (int h = 0; h < (OCL ? 0 : 2); ++h) {
                 if ((lane >> 4) == h) {
-                    float4* row = reinterpret_cast<float4*>(so + (lane & 15) * NB);
+                    if (kEs == 4) {
+                        float4* row = reinterpret_cast<float4*>(so + (lane & 15) * NB);
 #pragma unroll
-                    for (int q = 0; q < NB / 4; ++q)
-                        row[q] = make_float4(acc[(4 * q) / PW][(4 * q) % PW], acc[(4 * q + 1) / PW][(4 * q + 1) % PW],
-                                             acc[(4 * q + 2) / PW][(4 * q + 2) % PW], acc[(4 * q + 3) / PW][(4 * q + 3) % PW]);
+                        for (int q = 0; q < NB / 4; ++q)
+                            row[q] = make_float4(acc[(4 * q) / PW][(4 * q) % PW], acc[(4 * q + 1) / PW][(4 * q + 1) % PW],
+                                                 acc[(4 * q + 2) / PW][(4 * q + 2) % PW],
+                                                 acc[(4 * q + 3) / PW][(4 * q + 3) % PW]);
+                    } else {    // half: one rounding of the fp32 result
+                        __half2* row = reinterpret_cast<__half2*>(so + (lane & 15) * NB);
+#pragma unroll
+                        for (int q = 0; q < NB / 2; ++q)
+                            row[q] = __floats2half2_rn(acc[(2 * q) / PW][(2 * q) % PW], acc[(2 * q + 1) / PW][(2 * q + 1) % PW]);
+                    }
                 }
                 __syncwarp();
                 const int nch = min(16, cn - 16 * h);                 // contiguous [nch][PH*PW] block of the result
                 float4* g4 = reinterpret_cast<float4*>(out + ((size_t)ka * C + ca + 16 * h) * NB);
                 const float4* s4 = reinterpret_cast<const float4*>(so);
                 if (nch == 16) {                                      // loads in batches of four, then their stores
-                    constexpr int kN4 = 16 * (NB / 4), kIt = (kN4 + 31) / 32;
+                    constexpr int kN4 = 16 * NB * kEs / 16, kIt = (kN4 + 31) / 32;
 #pragma unroll
                     for (int i0 = 0; i0 < kIt; i0 += 4) {
                         float4 v[4];
@@ -742,12 +767,14 @@ roi_align_pipe_kernel(const float* __restrict__ feat, int B, int C, int H, int W
                             if (i0 + u < kIt && (32 * (i0 + u + 1) <= kN4 || lane + 32 * (i0 + u) < kN4))
                                 __stcs(g4 + lane + 32 * (i0 + u), v[u]);
                     }
-                } else {
-                    for (int i = lane; i < nch * (NB / 4); i += 32) __stcs(g4 + i, s4[i]);
+                } else {        // ragged last tile (float only: half tiles with cn < 32 are not staged)
+                    for (int i = lane; i < nch * NB * kEs / 16; i += 32) __stcs(g4 + i, s4[i]);
                 }
                 __syncwarp();
             }
             __syncwarp();       // every lane is done with this buffer before the next iteration refills it
+        } else {
+            load_after_next();
         }
         if (!have_next) break;
         t = tn; ka = kn; ca = cnx; a0 = n0; a1 = n1;
@@ -811,11 +838,12 @@ int launch_pipe(const T* feat, int B, int C, int H, int W, const float* rois, lo
     // Channels-last maps only: with NCHW maps the 4-byte plane-strided staging already keeps the LSU pipe ~40 %
     // busy, and the extra shared-memory pass of the copy-out makes the pipelined kernel slower than the tiled one
     // (g64 launch: 275 us vs 232 us); channels-last has the headroom (191 us vs 208 us).
-    if constexpr (NHWC && std::is_same<T, float>::value && (OCL || (PH * PW) % 4 == 0)) {
+    if constexpr (NHWC && (OCL || (PH * PW * sizeof(T)) % (sizeof(T) == 4 ? 16 : 4) == 0)) {
         using P = PipeSmem<PH, PW>;
-        if (!OCL && (reinterpret_cast<uintptr_t>(out) & 15)) return 1;
+        if (!OCL && ((reinterpret_cast<uintptr_t>(out) & 15) || (sizeof(T) == 2 && (C & 1)))) return 1;
+        if (sizeof(T) == 2 && ((C & 7) || (reinterpret_cast<uintptr_t>(feat) & 15))) return 1;   // half: 16-byte copies only
         static int resident_warps = 0;       // warps the device holds at once (per instantiation)
-        auto kern = roi_align_pipe_kernel<PH, PW, OCL>;
+        auto kern = roi_align_pipe_kernel<PH, PW, OCL, T>;
         if (!resident_warps) {
             int dev = 0, sms = 0, per_sm = 0;
             B200_CUDA(cudaGetDevice(&dev));

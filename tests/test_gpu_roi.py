@@ -230,3 +230,27 @@ def test_roi_device_boxes_hand_off():
     c = roi.roi_align_from_input_boxes(feat.contiguous(memory_format=torch.channels_last), det, (1280, 1280),
                                        out_size=(10, 10), out_channels_last=True)
     assert torch.equal(a, b) and torch.allclose(a, c.contiguous(), rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("out_cl", [False, True])
+@pytest.mark.parametrize("nhwc", [False, True])
+def test_roi_float16_large_launch_vs_oracle(nhwc, out_cl):
+    """Half storage at launch sizes that take the prep + multi-tile (NCHW) / pipelined (channels-last) kernels:
+    float32 sampling of the half-rounded map, one rounding at the end (within half an ulp of the float32 oracle).
+    C = 136 gives four full channel tiles and a ragged one."""
+    rng = np.random.default_rng(23)
+    Bm, C, Hf, Wf, n = 2, 136, 40, 48, 3400
+    feat16 = rng.standard_normal((Bm, C, Hf, Wf)).astype(np.float16)
+    boxes = synth.random_boxes(rng, n, 1280, 1536)
+    edge = synth.edge_case_boxes(1280, 1536)
+    boxes[:len(edge)] = edge
+    boxes[100:104] = [[0, 0, 1536, 1280]] * 4
+    boxes = boxes.astype(np.float16).astype(np.float64)
+    rois = np.concatenate([rng.integers(0, Bm, (n, 1)).astype(np.float64), boxes], 1).astype(np.float32)
+    f = torch.from_numpy(feat16).cuda()
+    if nhwc:
+        f = f.contiguous(memory_format=torch.channels_last)
+    got = roi.roi_align(f, torch.from_numpy(rois).cuda(), (10, 10), 40 / 1280.0, 2, True, out_channels_last=out_cl)
+    assert got.dtype == torch.float16
+    want = native.roi_align(feat16.astype(np.float32), rois, (10, 10), 40 / 1280.0, 2, True)
+    assert_close(got.contiguous().float().cpu().numpy(), want, rtol=1e-3, atol=2e-4, what="fp16 large nhwc=%s cl=%s" % (nhwc, out_cl))
