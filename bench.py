@@ -328,6 +328,17 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local)
+    # Run this rank's host side on the CPUs next to its GPU (NVML's ideal affinity): the e2e leg copies 212 MB per
+    # step from pinned host memory, and pinned pages allocated on the far socket halve that copy rate.
+    affinity0 = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
+    near_cpus = None
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local))
+        near_cpus = len(os.sched_getaffinity(0))
+    except Exception:                                               # noqa: BLE001
+        pass
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
@@ -485,6 +496,8 @@ def main():
     # ---- CPU baseline on this box's host cores (rank 0, N == 1 only) ---------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        if affinity0 is not None:
+            os.sched_setaffinity(0, affinity0)                       # the CPU baseline uses every host core
         cpu = cpu_group_fps(warm=30, max_frames=60, budget_s=12.0)
 
     if rank == 0:
@@ -507,7 +520,8 @@ def main():
                        "state_dtype": "f64 Kalman/assignment duals, f32 ROI/cost"},
             "clocks": sampler.summary(),
             "e2e": {"value": world * S * n_e2e / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": n_e2e, "api": "alufe_b200.roi_align + MultiStreamTracker.step (pinned host buffers)"},
+                    "steps": n_e2e, "api": "alufe_b200.roi_align + MultiStreamTracker.step (pinned host buffers)",
+                    "h2d_gbps": h2d * n_e2e / e2e_s / 1e9, "host_cpus_near_gpu": near_cpus},
             "gpu_launches": int(launches),
             "roofline": {"kernel": "roi_prep_kernel + roi_align_multi_kernel<10,10,NCHW> (one ROI Align launch)", "bound": "hbm",
                          "achieved": grp.roi_alg_bytes / roi_us_avg / 1e3, "peak": peak, "unit": "GB/s",
