@@ -68,3 +68,20 @@ def test_reference_arm_is_silent_on_nonzero_ranks():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2",
                         "--steps", "2", "--warmup", "3"], env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_reference_arm_prints_one_json_line_with_the_contract_keys():
+    """bench.py --impl reference on rank 0: exactly one JSON line on stdout with the keys the driver reads."""
+    import json
+    env = dict(os.environ, RANK="0", WORLD_SIZE="1", LOCAL_RANK="0")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "1",
+                        "--steps", "1", "--warmup", "3"], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "frames/s" and d["higher_is_better"] is True
+    assert d["steps"] == 1 and d["warmup"] == 3 and d["setup_steps"] == 27 and d["value"] > 0
+    assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
+    assert "workload" in d["config"] and d["metric"].startswith("tracked frames/sec")
