@@ -51,6 +51,8 @@ class BatchedKalman:
                                                    _lib.ptr(self.stage), _lib.stream_ptr(dev)))
 
     def predict(self, want_boxes=False):
+        """filterpy ``KalmanFilter.predict`` for every track (x <- Fx, P <- FPF' + Q) as ``predict_all`` uses it,
+        mainTracking.py:340-345; optionally also the predicted boxes (x_to_bbox_xyxy, KalmanFilter.py:19-33)."""
         pb = torch.empty((self.M, 4), dtype=torch.float64, device=self.device) if want_boxes else None
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().b200_kalman_predict(_lib.ptr(self.x), _lib.ptr(self.P), _lib.ptr(self.stage), self.M,
@@ -58,6 +60,8 @@ class BatchedKalman:
         return pb
 
     def update(self, det_of_track, meas, meas_is_z=False):
+        """filterpy ``KalmanFilter.update`` (Joseph form) of the tracks with a measurement, mainTracking.py:400;
+        ``meas`` holds boxes (converted with bbox_xyxy_to_z, KalmanFilter.py:5-16) or z vectors."""
         d = torch.as_tensor(np.asarray(det_of_track, dtype=np.int32)).to(self.device)
         m = torch.as_tensor(np.asarray(meas, dtype=np.float64).reshape(-1, 4)).to(self.device)
         with torch.cuda.device(self.device):

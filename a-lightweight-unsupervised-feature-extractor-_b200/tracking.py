@@ -108,6 +108,7 @@ class MultiStreamTracker:
         self.n_live[stream] = n
 
     def close(self):
+        """Frees the device state (b200_tracker_destroy)."""
         if getattr(self, "_h", None) is not None and self._h:
             _lib.lib().b200_tracker_destroy(self._h)
             self._h = ctypes.c_void_p()
@@ -119,12 +120,17 @@ class MultiStreamTracker:
             pass
 
     def reset(self):
+        """Back to the state of ``Tracking.__init__`` (mainTracking.py:45-96): no tracks, next id 0, every stream."""
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().b200_tracker_reset(self._h, _lib.stream_ptr(self.device)))
         self.n_live[:] = 0
 
     # -- one frame-step for every stream, host arrays in, host result table out -------------------
     def step(self, n_det, boxes, confs, embs, frame_ids) -> np.ndarray:
+        """One ``Tracking.update`` (mainTracking.py:450-610) for every stream from host arrays padded to ``max_dets``:
+        n_det [S], boxes [S,max_dets,4] float64 xyxy, confs [S,max_dets] float64, embs [S,max_dets,128] float32,
+        frame_ids [S].  Returns the int32 result table [S, stride] (``decode`` turns a row into the reference's
+        return value); raises ValueError where scipy would (NaN / infeasible cost matrix, hung.py:28)."""
         n_det = np.ascontiguousarray(n_det, dtype=np.int32).reshape(self.S)
         frame_ids = np.ascontiguousarray(frame_ids, dtype=np.int32).reshape(self.S)
         boxes = np.ascontiguousarray(boxes, dtype=np.float64).reshape(self.S, self.max_dets, 4)
@@ -155,6 +161,9 @@ class MultiStreamTracker:
     # -- device-resident inputs, asynchronous on the current stream (no read-back) ------------------
     def step_device(self, n_det: torch.Tensor, boxes: torch.Tensor, confs: torch.Tensor, embs: torch.Tensor,
                     frame_ids: torch.Tensor, result: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """The same step with device-resident inputs, asynchronous on the current stream, no read-back (SURVEY 8f-1:
+        the reference rebuilds host lists every frame, tracking.py:315-324).  The per-stream status is in column
+        R_STATUS of the returned table."""
         for t, dt in ((n_det, torch.int32), (boxes, torch.float64), (confs, torch.float64), (embs, torch.float32),
                       (frame_ids, torch.int32)):
             _lib.require_cuda(t, "input")
@@ -250,6 +259,9 @@ class Tracking:
 
     # -- the call the pipeline makes (tracking.py:326) ---------------------------------------------
     def update(self, obj: Dict):
+        """``Tracking.update`` (mainTracking.py:450-610): obj = {embs, bboxes, confs, input_hw, frame_id} ->
+        (matches [(track_id, det_idx)], unmatched track ids, unmatched det indices), same order, same ValueErrors
+        (:457-462, :267-268)."""
         det_embs = obj.get("embs", []) or []
         det_boxes = obj.get("bboxes", []) or []
         det_confs = obj.get("confs", []) or []
@@ -289,17 +301,21 @@ class Tracking:
 
     # -- state inspection ---------------------------------------------------------------------------
     def snapshot(self) -> Dict[str, np.ndarray]:
+        """Host copy of the live tracks in ascending id order: the fields of TrackMemory / TrackState
+        (mainTracking.py:15-42) plus the Kalman state."""
         if self._snap is None:
             self._snap = self._ms.export(0)
         return self._snap
 
     @property
     def tracks(self) -> Dict[int, TrackView]:
+        """Read-only view shaped like the reference's ``self.tracks`` dict (mainTracking.py:45-46, :15-42)."""
         s = self.snapshot()
         return {int(s["ids"][i]): TrackView(s, i) for i in range(len(s["ids"]))}
 
     @property
     def next_id(self) -> int:
+        """The id the next new track gets (mainTracking.py:371-372)."""
         return self.snapshot()["next_id"]
 
     def _rows(self, row_to_tid):
