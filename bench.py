@@ -309,6 +309,8 @@ def main():
     ap.add_argument("--streams", type=int, default=64, help="config-2 streams per GPU stepped together")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather-every", type=int, default=8,
+                    help="N > 1: all-gather the result tables every this many frames")
     ap.add_argument("--no-extra", action="store_true", help="skip the single-stream side measurement")
     args = ap.parse_args()
     quiet_stdout()
@@ -355,7 +357,7 @@ def main():
     # The only inter-GPU traffic: the per-stream result tables, all-gathered for the consumer of tracking.py:329.
     # They are gathered GATHER_EVERY frames at a time ("optionally gather every K frames"):
     # a NCCL kernel per step holds SM slots while it waits for the slowest rank, which cost 17 % at 8 GPUs.
-    GATHER_EVERY = 8
+    GATHER_EVERY = max(1, args.gather_every)
     n_total = pre + W + K
     gathered = (torch.zeros((2, world, GATHER_EVERY, S, grp.trk.stride), dtype=torch.int32, device=dev)
                 if world > 1 else None)
