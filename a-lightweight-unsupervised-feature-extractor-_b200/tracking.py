@@ -184,7 +184,7 @@ class MultiStreamTracker:
         m = row[R_HDR:R_HDR + 2 * nm].reshape(nm, 2)
         ut = row[R_HDR + 2 * MD:R_HDR + 2 * MD + nut]
         ud = row[R_HDR + 2 * MD + MT:R_HDR + 2 * MD + MT + nud]
-        return [(int(a), int(b)) for a, b in m], [int(v) for v in ut], [int(v) for v in ud]
+        return list(map(tuple, m.tolist())), ut.tolist(), ud.tolist()
 
     def export(self, stream: int = 0) -> Dict[str, np.ndarray]:
         """Copies one stream's live tracks (ascending track id) to host arrays."""
@@ -275,9 +275,13 @@ class Tracking:
             raise ValueError("Length mismatch: embs/bboxes/confs must have same length")
         N = len(det_boxes)
         if N:
-            e = np.stack([np.asarray(v, dtype=np.float32).reshape(-1) for v in det_embs], axis=0)
-            if e.shape[1] != 128:
-                raise ValueError(f"det_embs must be 128D, got {e.shape}")
+            try:                                   # equal-length vectors: one C-level conversion
+                e = np.asarray(det_embs, dtype=np.float32).reshape(N, -1)
+            except ValueError:                     # ragged input: per-vector conversion, then the reference's error
+                e = None
+            if e is None or e.shape[1] != 128:
+                shapes = sorted({np.asarray(v).size for v in det_embs})
+                raise ValueError(f"det_embs must be 128D, got sizes {shapes}")
             return self.update_arrays(np.asarray(det_boxes, dtype=np.float64), np.asarray(det_confs, dtype=np.float64),
                                       e, int(frame_id))
         return self.update_arrays(np.zeros((0, 4)), np.zeros((0,)), np.zeros((0, 128), np.float32), int(frame_id))
