@@ -7,6 +7,7 @@
 """
 from typing import List, Sequence, Tuple, Union
 
+import numpy as np
 import torch
 
 from . import _lib
@@ -89,7 +90,10 @@ def roi_align_from_input_boxes(feat: torch.Tensor, boxes_in, input_hw: Tuple[int
         b = boxes_in.reshape(-1, boxes_in.shape[-1])[:, :4].to(device=feat.device, dtype=torch.float32)
         rois = torch.cat([torch.zeros((b.shape[0], 1), dtype=torch.float32, device=feat.device), b], dim=1)
     else:
-        rois = torch.tensor([[0.0, b[0], b[1], b[2], b[3]] for b in boxes_in], dtype=torch.float32).reshape(-1, 5)
+        b = np.asarray(boxes_in, dtype=np.float32).reshape(-1, 4) if len(boxes_in) else np.zeros((0, 4), np.float32)
+        r = np.zeros((b.shape[0], 5), np.float32)                     # batch index 0 (tracking.py:209-213)
+        r[:, 1:] = b
+        rois = torch.from_numpy(r)
     return roi_align(feat, rois.to(feat.device), out_size, Hf / float(H_in), sampling_ratio, aligned,
                      out_channels_last=out_channels_last)
 
