@@ -461,9 +461,33 @@ def main():
     e2e_s = float(t.item())
     h2d = grp.map_b + S * NBOX * 20 + S * (8 + NBOX * (32 + 8 + 512))
     d2h = S * grp.trk.stride * 4
+    extra = {}
+    # ---- the same public-API loop with the maps already on the device (how the reference's CUDA deployment calls
+    # roi_align: the detector's map never leaves the GPU, only boxes / confidences / embeddings come from the host) ----
+    if rank == 0 and not args.no_extra:
+        try:
+            def api_step(i):
+                rois_dev[i & 1].copy_(pin_rois[i % len(pin_rois)], non_blocking=True)
+                patches = alufe_b200.roi_align(feat_dev[i & 1], rois_dev[i & 1], (PS, PS), scale, 2, True)
+                return patches, ms2.step(n_det, grp.boxes[i], grp.confs[i], grp.embs[i], np.full(S, i, np.int32))
+            torch.cuda.synchronize()
+            n_api = min(60, K - n_e2e)                 # the frames after those of the e2e leg
+            if n_api <= 0:
+                raise RuntimeError("needs --steps > %d" % n_e2e)
+            t0 = time.perf_counter()
+            for k in range(n_api):
+                _, res = api_step(pre + W + n_e2e + k)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            assert (res[:, 0] > 0).all()
+            extra["api_device_maps"] = {"value": S * n_api / dt, "unit": "frames/s", "ms_per_step": 1e3 * dt / n_api,
+                                        "h2d_bytes_per_step": S * NBOX * 20 + S * (8 + NBOX * (32 + 8 + 512)),
+                                        "note": "alufe_b200.roi_align + MultiStreamTracker.step with host boxes / "
+                                                "confidences / embeddings and device-resident maps"}
+        except Exception as exc:                                    # noqa: BLE001
+            extra["api_device_maps_error"] = repr(exc)
     del pin_maps, feat_dev
 
-    extra = {}
     # ---- single-stream latency mode (one frame in flight; the shape the reference runs) --------------
     if rank == 0 and not args.no_extra:
         try:
