@@ -2,7 +2,7 @@
 
 Inputs are the reference's host-side Python lists (or tensors); results are CUDA float32 tensors.
 """
-from typing import Any, Dict, List, Optional, Sequence, Tuple
+from typing import Any, Dict, List, Optional, Tuple
 
 import torch
 

@@ -4,7 +4,6 @@
 per-track helpers are kept as thin wrappers around it: ``init_kf_from_bbox`` returns a one-track
 ``KalmanState`` with ``predict()`` / ``update(z)`` like the filterpy object it replaces.
 """
-from typing import Sequence
 
 import numpy as np
 import torch

@@ -10,7 +10,7 @@ All state (Kalman filters, EMA embeddings, history banks, ages) lives on the dev
 one device->host copy of a small result table.  There is no CPU fallback.
 """
 import ctypes
-from typing import Any, Dict, List, Optional, Sequence, Tuple
+from typing import Any, Dict, List, Optional
 
 import numpy as np
 import torch

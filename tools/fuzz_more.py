@@ -4,8 +4,6 @@ import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-import numpy as np
-import torch
 import test_gpu_tracker as T
 import test_gpu_ops as O
 

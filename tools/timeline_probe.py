@@ -1,5 +1,5 @@
 """Debug (build with EXTRA=-DB200_TRK_TIMING): global-timer spans of every kernel over a few steady-state steps."""
-import ctypes, os, sys, json
+import ctypes, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np
