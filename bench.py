@@ -41,6 +41,21 @@ WORKLOAD = ("c2: 1280x1280 frame, map [1,512,40,40], 64 detections vs ~64 tracks
             "cost + gate + Kalman + assignment per frame")
 C, HF, WF, H_IN, W_IN, NBOX, PS = 512, 40, 40, 1280, 1280, 64, 10
 ROI_ALG_BYTES = NBOX * C * PS * PS * 4 + C * HF * WF * 4 + NBOX * 20
+WORKLOADS = {
+    # BASELINE.json configs[1]: the configuration the metric is quoted on (default)
+    "c2": (40, 40, 1280, 1280, 64, "c2: 1280x1280 frame, map [1,512,40,40], 64 detections vs ~64 tracks, roi_align 10x10 + "
+                                   "cost + gate + Kalman + assignment per frame"),
+    # BASELINE.json configs[4]: the streams of the multi-GPU configuration
+    "c5": (34, 60, 1088, 1920, 128, "c5: 1088x1920 frame, map [1,512,34,60], 128 detections vs ~128 tracks, roi_align "
+                                    "10x10 + cost + gate + Kalman + assignment per frame"),
+}
+
+
+def select_workload(name):
+    """Sets the module-level shape constants; everything below reads them at call time."""
+    global HF, WF, H_IN, W_IN, NBOX, WORKLOAD, ROI_ALG_BYTES
+    HF, WF, H_IN, W_IN, NBOX, WORKLOAD = WORKLOADS[name]
+    ROI_ALG_BYTES = NBOX * C * PS * PS * 4 + C * HF * WF * 4 + NBOX * 20
 
 
 def measured_peaks():
@@ -104,7 +119,8 @@ class ClockSampler(threading.Thread):
 
 def _cpu_worker(args):
     """One host process = one video stream through the reference path (module-level for spawn)."""
-    seed, warm, max_frames, budget_s = args
+    seed, warm, max_frames, budget_s, workload = args
+    select_workload(workload)                # spawned processes start from the defaults
     import torch
     torch.set_num_threads(1)
     import alufe_b200  # noqa: F401
@@ -145,15 +161,16 @@ def cpu_group_fps(warm, max_frames, budget_s, workers=None):
     workers = workers or max(1, os.cpu_count() or 1)
     ctx = mp.get_context("spawn")
     with ctx.Pool(workers) as pool:
-        out = pool.map(_cpu_worker, [(50000 + w, warm, max_frames, budget_s) for w in range(workers)])
+        name = [k for k, v in WORKLOADS.items() if v[5] == WORKLOAD][0]
+        out = pool.map(_cpu_worker, [(50000 + w, warm, max_frames, budget_s, name) for w in range(workers)])
     fps = sum(n / wall for n, _, _, wall, _ in out)
     n_tot = sum(o[0] for o in out)
     ms_roi = 1e3 * sum(o[1] for o in out) / n_tot
     ms_upd = 1e3 * sum(o[2] for o in out) / n_tot
     return {"value": fps, "unit": "frames/s", "cores": workers, "kind": "port",
-            "sample": "%d independent config-2 streams, one host process each (%d logical CPUs), %d frames in total after %d "
-                      "warm-up frames per stream: roi_align (%s CPU) %.1f ms + Tracking.update port %.1f ms per frame per "
-                      "core; the association step is single-threaded Python as in the reference"
+            "sample": ("%d independent " + name + " streams, one host process each (%d logical CPUs), %d frames in total "
+                       "after %d warm-up frames per stream: roi_align (%s CPU) %.1f ms + Tracking.update port %.1f ms per "
+                       "frame per core; the association step is single-threaded Python as in the reference")
                       % (workers, os.cpu_count() or 0, n_tot, warm, out[0][4], ms_roi, ms_upd)}
 
 
@@ -309,10 +326,13 @@ def main():
     ap.add_argument("--streams", type=int, default=64, help="config-2 streams per GPU stepped together")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="c2",
+                    help="per-stream frame shape: c2 (BASELINE configs[1], the headline) or c5 (configs[4])")
     ap.add_argument("--gather-every", type=int, default=8,
                     help="N > 1: all-gather the result tables every this many frames")
     ap.add_argument("--no-extra", action="store_true", help="skip the single-stream side measurement")
     args = ap.parse_args()
+    select_workload(args.workload)
     quiet_stdout()
     if args.impl == "reference":
         return run_reference(args)
