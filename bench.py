@@ -484,7 +484,7 @@ def main():
     extra = {}
     # ---- the same public-API loop with the maps already on the device (how the reference's CUDA deployment calls
     # roi_align: the detector's map never leaves the GPU, only boxes / confidences / embeddings come from the host) ----
-    if rank == 0 and not args.no_extra:
+    if rank == 0 and not args.no_extra and K - n_e2e > 0:          # needs frames beyond those of the e2e leg
         try:
             def api_step(i):
                 rois_dev[i & 1].copy_(pin_rois[i % len(pin_rois)], non_blocking=True)
@@ -492,8 +492,6 @@ def main():
                 return patches, ms2.step(n_det, grp.boxes[i], grp.confs[i], grp.embs[i], np.full(S, i, np.int32))
             torch.cuda.synchronize()
             n_api = min(60, K - n_e2e)                 # the frames after those of the e2e leg
-            if n_api <= 0:
-                raise RuntimeError("needs --steps > %d" % n_e2e)
             t0 = time.perf_counter()
             for k in range(n_api):
                 _, res = api_step(pre + W + n_e2e + k)
