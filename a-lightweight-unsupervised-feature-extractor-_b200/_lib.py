@@ -58,6 +58,7 @@ SIGNATURES = {
     "b200_tracker_destroy": (None, [_P]),
     "b200_tracker_reset": (_I, [_P, _P]),
     "b200_tracker_result_stride": (_I, [_P]),
+    "b200_tracker_live_counts": (_I, [_P, _P, _P, _P]),
     "b200_tracker_step": (_I, [_P, _P, _P, _P, _P, _P, _P, _P]),
     "b200_tracker_step_host": (_I, [_P, _P, _P, _P, _P, _P, _P, _P]),
     "b200_tracker_export": (_I, [_P, _I] + [_P] * 14),

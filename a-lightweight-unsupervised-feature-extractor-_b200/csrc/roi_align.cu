@@ -32,9 +32,11 @@
 //   roi_align_generic_kernel other output sizes: one thread per output element.
 // Output is NCHW like the reference's, or channels-last on request (b200_roi_align_fwd_ex): lane = channel then
 // stores whole lines straight from the accumulators.
+#include <cuda.h>
 #include <cuda_fp16.h>
 
 #include "common.cuh"
+#include <mutex>
 #include <type_traits>
 
 namespace b200 {
@@ -167,7 +169,8 @@ __device__ __forceinline__ void bulk_store_wait_read() {
 // weight-table computation (roi_prep_kernel) instead of repeating it.
 struct __align__(16) RoiPrep {
     int b, ymin, xmin, FY;
-    int FX, staged, pad0, pad1;     // staged = 0: footprint too large, the tile computes everything itself
+    int FX, staged, xmask, pad1;    // staged = 0: footprint too large, the tile computes everything itself;
+                                    // xmask: bit x set = footprint column x carries weight (all FX of them unless widened)
 };
 
 template <int PH, int PW>
@@ -246,7 +249,7 @@ __device__ __forceinline__ void build_tables(const Geom& g, float inv, int H, in
 template <int PH, int PW>
 __global__ void __launch_bounds__(128)
 roi_prep_kernel(const float* __restrict__ rois, long long K, int B, int H, int W, float scale, int sr, int aligned,
-                RoiPrep* __restrict__ prep, float* __restrict__ tabs) {
+                RoiPrep* __restrict__ prep, float* __restrict__ tabs, int xalign) {
     using L = TileSmem<PH, PW>;
     __shared__ __align__(16) float sTabs[4][L::kTabFloats];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -258,6 +261,15 @@ roi_prep_kernel(const float* __restrict__ rois, long long K, int B, int H, int W
     axis_footprint(g.sh, g.bh, PH, g.gh, H, &ymin, &FY);
     axis_footprint(g.sw, g.bw, PW, g.gw, W, &xmin, &FX);
     if (g.b < 0 || g.b >= B || FY == 0 || FX == 0) FY = FX = 0;
+    // TMA consumers (roi_align_tma_kernel) can only start a box on a 16-byte boundary of a map row: the footprint is
+    // widened to the left to the previous multiple of `xalign` cells; the added columns get zero weights and a clear
+    // bit in the column mask, so they are never multiplied.
+    int xoff = 0;
+    if (xalign > 1 && FX) {
+        xoff = xmin & (xalign - 1);
+        xmin -= xoff;
+        FX += xoff;
+    }
     const bool staged = FY <= kFootCap && FX <= kFootCap;
     if (staged) {
         float* t = sTabs[warp];
@@ -269,7 +281,9 @@ roi_prep_kernel(const float* __restrict__ rois, long long K, int B, int H, int W
     }
     if (lane == 0) {
         RoiPrep h;
-        h.b = g.b; h.ymin = ymin; h.xmin = xmin; h.FY = FY; h.FX = FX; h.staged = staged ? 1 : 0; h.pad0 = h.pad1 = 0;
+        h.b = g.b; h.ymin = ymin; h.xmin = xmin; h.FY = FY; h.FX = FX; h.staged = staged ? 1 : 0;
+        h.xmask = FX ? (((1 << (FX - xoff)) - 1) << xoff) : 0;
+        h.pad1 = 0;
         prep[k] = h;
     }
 }
@@ -784,6 +798,346 @@ roi_align_pipe_kernel(const T* __restrict__ feat, int B, int C, int H, int W, co
     B200_SPAN_END(span_slot);
 }
 
+
+// ---- TMA-staged pipelined kernel: large launches on NCHW maps --------------------------------------------
+// The plane-strided footprint of an NCHW map (FY rows x FX floats in each of 32 channel planes) is exactly a
+// box of a 4-D tensor (W, H, C, B): one cp.async.bulk.tensor (SASS UTMALDG) moves it with no LSU wavefronts and
+// no per-element address arithmetic, which were the two costs of the LDGSTS staging above.  The box is
+// {16 bytes, kTmaRows rows, 32 channels, 1 map} and lands in shared memory as V[channel][row][x], x fastest; with
+// an ODD row count the per-channel stride (kTmaRows * 16 B) is an odd multiple of 16 bytes, so the 128-bit read
+// of one footprint row by the 8 lanes of a quarter-warp (lane = channel) touches 8 different bank groups:
+// conflict-free, and one LDS.128 per row instead of FX 32-bit ones.  The contraction therefore runs row-outer:
+//   tx[pw] = sum_x Wx[x][pw] * V[r][x];   acc[ph][pw] += Wy[r][ph] * tx[pw]
+// (same FFMA count as the column-outer form of separable_accumulate).  A box can only start on a 16-byte boundary of a
+// map row (measured: an inner coordinate that is not a multiple of 16 bytes raises "illegal instruction",
+// tools/tma_probe.cu), so roi_prep_kernel widens the footprint to the left to a multiple of four cells and
+// records which columns really carry weight (RoiPrep::xmask); the others are skipped, not multiplied by zero.
+// Footprints wider than 16 bytes take a second box to the right, taller than kTmaRows a second box below (up to
+// the 8 x 8 cells of the staged path); coordinates beyond the map are zero-filled by the TMA unit.  The ROI's ready-made weight tables
+// arrive on the same mbarrier with one cp.async.bulk.  A warp walks `tiles_per_warp` tiles and keeps the
+// footprint of the NEXT tile in flight while it accumulates the current one (two table slots; the V region is
+// shared by the two tiles in flight, growing from both ends, and a tile that does not fit beside its
+// predecessor is simply requested after it has been consumed), stages its [32][PH*PW] result in a separate
+// output tile and hands that to the TMA engine as one bulk store whose completion is awaited only when the next
+// result is ready.  Tiles the prep kernel did not stage go through process_tile() with the output tile as
+// scratch.
+constexpr int kTmaRows = 5;
+constexpr int kTmaBoxBytes = 16 * kTmaRows * 32;          // one box: 16 B x kTmaRows rows x 32 channels
+constexpr int kTmaVBytes = 4 * kTmaBoxBytes;              // one 2 x 2-box tile, or two smaller tiles in flight
+#ifndef B200_ROI_TMA_WARPS
+#define B200_ROI_TMA_WARPS 3
+#endif
+#ifndef B200_ROI_TMA_CTAS
+#define B200_ROI_TMA_CTAS 3
+#endif
+#ifndef B200_ROI_TMA_TILES
+#define B200_ROI_TMA_TILES 8
+#endif
+constexpr int kTmaWarps = B200_ROI_TMA_WARPS;
+
+template <int PH, int PW>
+struct TmaSmem {
+    using L = TileSmem<PH, PW>;
+    static constexpr int kTabBytes = L::kTabFloats * 4;
+    static constexpr int kOutBytes = L::kMainFloats * 4;                  // output tile; process_tile()'s sMain on the fallback
+    static constexpr int kOffTab = kTmaVBytes, kOffOut = kOffTab + 2 * kTabBytes, kOffBar = kOffOut + kOutBytes;
+    static constexpr int kBytesPerWarp = (kOffBar + 16 + 127) & ~127;
+    static constexpr int kBytesPerCta = kBytesPerWarp * kTmaWarps;
+    static_assert(kTabBytes % 16 == 0 && kOffOut % 16 == 0 && kOffBar % 8 == 0, "bulk-copy alignment");
+};
+
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_box_4d(unsigned dst, const CUtensorMap* tm, int x, int y, int c, int b, unsigned bar) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];\n"
+                 ::"r"(dst), "l"(tm), "r"(x), "r"(y), "r"(c), "r"(b), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void bulk_load(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// Boxes of a staged tile (0 for a ROI that samples nothing) and the bytes they occupy in the V region.
+template <typename T>
+__device__ __forceinline__ int tma_tile_boxes(const int4 h0, const int4 h1) {
+    constexpr int BX = 16 / (int)sizeof(T);
+    const int FY = h0.w, FX = h1.x;
+    if (FY == 0 || FX == 0) return 0;
+    return (FY > kTmaRows ? 2 : 1) * (FX > BX ? 2 : 1);
+}
+
+// One lane requests everything tile (k, c0) needs: the weight tables of ROI k and the footprint boxes.
+template <int PH, int PW, typename T>
+__device__ __forceinline__ void tma_issue(const CUtensorMap* tm, const int4 h0, const int4 h1, long long k, int c0,
+                                          const float* __restrict__ prep_tabs, unsigned sv, unsigned stab, unsigned bar) {
+    using S = TmaSmem<PH, PW>;
+    constexpr int BX = 16 / (int)sizeof(T);
+    const int b = h0.x, ymin = h0.y, xmin = h0.z, FY = h0.w, FX = h1.x;
+    const int nb = tma_tile_boxes<T>(h0, h1);
+    const int nrb = FY > kTmaRows ? 2 : 1;
+    mbar_expect_tx(bar, (unsigned)(S::kTabBytes + nb * kTmaBoxBytes));
+    bulk_load(stab, prep_tabs + (size_t)k * S::L::kTabFloats, S::kTabBytes, bar);
+    if (nb) {
+        tma_box_4d(sv, tm, xmin, ymin, c0, b, bar);
+        if (nrb == 2) tma_box_4d(sv + kTmaBoxBytes, tm, xmin, ymin + kTmaRows, c0, b, bar);
+        if (FX > BX) {
+            tma_box_4d(sv + nrb * kTmaBoxBytes, tm, xmin + BX, ymin, c0, b, bar);
+            if (nrb == 2) tma_box_4d(sv + 3 * kTmaBoxBytes, tm, xmin + BX, ymin + kTmaRows, c0, b, bar);
+        }
+    }
+}
+
+// Row-outer separable contraction over V[channel][row][x] as the TMA boxes lay it out (see above).
+template <int PH, int PW, typename T>
+__device__ __forceinline__ void tma_accumulate(float (&acc)[PH][PW], const unsigned char* sV, const float* sWy,
+                                               const float* sWx, int FY, int FX, int xmask, int lane) {
+    constexpr int PHP = (PH + 3) & ~3, PWP = (PW + 3) & ~3, BX = 16 / (int)sizeof(T);
+    const int nrb = FY > kTmaRows ? 2 : 1;
+    const unsigned char* mine = sV + lane * (kTmaRows * 16);
+    for (int r = 0; r < FY; ++r) {
+        const int rb = r >= kTmaRows ? 1 : 0;
+        const unsigned char* row = mine + rb * kTmaBoxBytes + (r - rb * kTmaRows) * 16;
+        float v[8];
+        if (sizeof(T) == 4) {
+            const float4 a = *reinterpret_cast<const float4*>(row);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+            if (FX > BX) {
+                const float4 c = *reinterpret_cast<const float4*>(row + nrb * kTmaBoxBytes);
+                v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
+            } else {
+                v[4] = v[5] = v[6] = v[7] = 0.0f;
+            }
+        } else {
+            const uint4 a = *reinterpret_cast<const uint4*>(row);
+            const __half2* h = reinterpret_cast<const __half2*>(&a);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { const float2 f = __half22float2(h[q]); v[2 * q] = f.x; v[2 * q + 1] = f.y; }
+        }
+        float tx[PW];
+#pragma unroll
+        for (int bq = 0; bq < PW; ++bq) tx[bq] = 0.0f;
+#pragma unroll
+        for (int x = 0; x < 8; ++x) {
+            if ((xmask >> x) & 1) {                                   // uniform: cells outside the footprint are never touched
+                const float4* w4 = reinterpret_cast<const float4*>(sWx + x * PWP);
+#pragma unroll
+                for (int q = 0; q < PWP / 4; ++q) {
+                    const float4 w = w4[q];
+                    if (4 * q + 0 < PW) tx[4 * q + 0] = fmaf(w.x, v[x], tx[4 * q + 0]);
+                    if (4 * q + 1 < PW) tx[4 * q + 1] = fmaf(w.y, v[x], tx[4 * q + 1]);
+                    if (4 * q + 2 < PW) tx[4 * q + 2] = fmaf(w.z, v[x], tx[4 * q + 2]);
+                    if (4 * q + 3 < PW) tx[4 * q + 3] = fmaf(w.w, v[x], tx[4 * q + 3]);
+                }
+            }
+        }
+        const float4* w4 = reinterpret_cast<const float4*>(sWy + r * PHP);
+#pragma unroll
+        for (int q = 0; q < PHP / 4; ++q) {
+            const float4 w = w4[q];
+            const float wv[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (4 * q + e < PH) {
+#pragma unroll
+                    for (int bq = 0; bq < PW; ++bq) acc[4 * q + e][bq] = fmaf(wv[e], tx[bq], acc[4 * q + e][bq]);
+                }
+        }
+    }
+}
+
+template <int PH, int PW, typename T, bool OCL>
+__global__ void __launch_bounds__(kTmaWarps * 32, B200_ROI_TMA_CTAS)
+roi_align_tma_kernel(const __grid_constant__ CUtensorMap tmap, const T* __restrict__ feat, int B, int C, int H, int W,
+                     const float* __restrict__ rois, long long K, float scale, int sr, int aligned, T* __restrict__ out,
+                     int ctiles, const RoiPrep* __restrict__ prep, const float* __restrict__ prep_tabs, int group_warps,
+                     int tiles_per_warp) {
+    using L = TileSmem<PH, PW>;
+    using S = TmaSmem<PH, PW>;
+    constexpr int PHP = L::kPHP, NB = PH * PW;
+    extern __shared__ __align__(128) unsigned char smem_tma[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char* base = smem_tma + (size_t)warp * S::kBytesPerWarp;
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(base);
+    const unsigned sbar = sbase + S::kOffBar;
+    float* sOut = reinterpret_cast<float*>(base + S::kOffOut);
+    const unsigned gw = blockIdx.x * kTmaWarps + warp, grp = gw / (unsigned)group_warps;
+    const unsigned stride = (unsigned)group_warps, window = stride * (unsigned)tiles_per_warp;
+    unsigned t = grp * window + (gw - grp * stride);
+    const unsigned total = (unsigned)min((long long)(grp + 1) * window, K * ctiles);
+    if (t >= total) return;
+    const int span_slot = (int)((reinterpret_cast<uintptr_t>(rois) / (size_t)(K * 20)) & 7);   // debug: step index mod 8
+    B200_SPAN_BEGIN(span_slot);
+    if (lane == 0) {
+        mbar_init(sbar, 1);
+        mbar_init(sbar + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tmap) : "memory");
+    }
+    __syncwarp();
+
+    // current tile (a*), next tile (n*): ROI index, first channel, prep record
+    unsigned ka = t / (unsigned)ctiles;
+    int ca = (int)(t - ka * (unsigned)ctiles) * 32;
+    int4 a0 = reinterpret_cast<const int4*>(prep + ka)[0], a1 = reinterpret_cast<const int4*>(prep + ka)[1];
+    unsigned tn = t + stride, kn = 0;
+    int cnx = 0;
+    int4 n0 = make_int4(0, 0, 0, 0), n1 = n0;
+    if (tn < total) {
+        kn = tn / (unsigned)ctiles;
+        cnx = (int)(tn - kn * (unsigned)ctiles) * 32;
+        n0 = reinterpret_cast<const int4*>(prep + kn)[0];
+        n1 = reinterpret_cast<const int4*>(prep + kn)[1];
+    }
+    int par = 0;                       // slot of the current tile: table slot, mbarrier, end of the V region it grows from
+    unsigned phase = 0;                // bit p = parity the next wait on mbarrier p expects
+    bool pending = false;              // the bulk store of the previous result may still be reading sOut
+    bool cur_issued = false;
+    // V offset of a tile with `nb` boxes in slot p: slot 0 grows up from the start, slot 1 down from the end
+    auto v_off = [&](int p, int nb) { return p ? (unsigned)(kTmaVBytes - nb * kTmaBoxBytes) : 0u; };
+    if (a1.y) {
+        if (lane == 0)
+            tma_issue<PH, PW, T>(&tmap, a0, a1, ka, ca, prep_tabs, sbase + v_off(0, tma_tile_boxes<T>(a0, a1)),
+                                 sbase + S::kOffTab, sbar);
+        cur_issued = true;
+    }
+    for (;;) {
+        const bool have_next = tn < total;
+        const int cn = min(32, C - ca);
+        const int nba = a1.y ? tma_tile_boxes<T>(a0, a1) : 0;
+        const int nbn = (have_next && n1.y) ? tma_tile_boxes<T>(n0, n1) : 0;
+        // the next tile's footprint is requested now if it fits beside the current one, else once that is consumed
+        bool next_issued = false;
+        if (have_next && n1.y && (nba + nbn) * kTmaBoxBytes <= kTmaVBytes) {
+            if (lane == 0)
+                tma_issue<PH, PW, T>(&tmap, n0, n1, kn, cnx, prep_tabs, sbase + v_off(par ^ 1, nbn),
+                                     sbase + S::kOffTab + (par ^ 1) * S::kTabBytes, sbar + 8 * (par ^ 1));
+            next_issued = true;
+        }
+        // record of the tile after next: requested after the accumulation (register pressure), see roi_align_pipe_kernel
+        const unsigned tm = tn + stride;
+        unsigned km = 0;
+        int cm = 0;
+        int4 m0 = make_int4(0, 0, 0, 0), m1 = m0;
+        auto load_after_next = [&]() {
+            if (have_next && tm < total) {
+                km = tm / (unsigned)ctiles;
+                cm = (int)(tm - km * (unsigned)ctiles) * 32;
+                m0 = reinterpret_cast<const int4*>(prep + km)[0];
+                m1 = reinterpret_cast<const int4*>(prep + km)[1];
+            }
+        };
+        if (a1.y) {
+            if (!cur_issued) {         // only when the previous iteration could not fit it beside its own tile
+                if (lane == 0)
+                    tma_issue<PH, PW, T>(&tmap, a0, a1, ka, ca, prep_tabs, sbase + v_off(par, nba),
+                                         sbase + S::kOffTab + par * S::kTabBytes, sbar + 8 * par);
+            }
+            mbar_wait(sbar + 8 * par, (phase >> par) & 1u);
+            phase ^= 1u << par;
+            const float* sWy = reinterpret_cast<const float*>(base + S::kOffTab + par * S::kTabBytes);
+            const int FY = a0.w, FX = a1.x;
+            float acc[PH][PW];
+#pragma unroll
+            for (int a = 0; a < PH; ++a)
+#pragma unroll
+                for (int bq = 0; bq < PW; ++bq) acc[a][bq] = 0.0f;
+            if (nba) tma_accumulate<PH, PW, T>(acc, base + v_off(par, nba), sWy, sWy + kFootCap * PHP, FY, FX, a1.z, lane);
+            load_after_next();
+            __syncwarp();              // V and the tables of this slot are dead
+            if (have_next && n1.y && !next_issued && nbn * kTmaBoxBytes <= kTmaVBytes) {
+                if (lane == 0)
+                    tma_issue<PH, PW, T>(&tmap, n0, n1, kn, cnx, prep_tabs, sbase + v_off(par ^ 1, nbn),
+                                         sbase + S::kOffTab + (par ^ 1) * S::kTabBytes, sbar + 8 * (par ^ 1));
+                next_issued = true;
+            }
+            if (OCL) {                 // channels-last result: full-line stores straight from the accumulators
+                T* gl = out + (size_t)ka * NB * C + ca + lane;
+                if (lane < cn) {
+#pragma unroll
+                    for (int a = 0; a < PH; ++a)
+#pragma unroll
+                        for (int bq = 0; bq < PW; ++bq) gl[(size_t)(a * PW + bq) * C] = from_f<T>(acc[a][bq]);
+                }
+            } else {
+                if (pending && lane == 0) bulk_store_wait_read();
+                pending = false;
+                __syncwarp();
+                if (sizeof(T) == 4) {
+                    float* myrow = sOut + lane * NB;
+                    if ((NB & 3) == 0) {
+#pragma unroll
+                        for (int q = 0; q < NB / 4; ++q)
+                            reinterpret_cast<float4*>(myrow)[q] =
+                                make_float4(acc[(4 * q) / PW][(4 * q) % PW], acc[(4 * q + 1) / PW][(4 * q + 1) % PW],
+                                            acc[(4 * q + 2) / PW][(4 * q + 2) % PW], acc[(4 * q + 3) / PW][(4 * q + 3) % PW]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < NB; ++i) myrow[i] = acc[i / PW][i % PW];
+                    }
+                } else {
+                    __half* myrow = reinterpret_cast<__half*>(sOut) + lane * NB;
+                    if ((NB & 1) == 0) {
+#pragma unroll
+                        for (int q = 0; q < NB / 2; ++q)
+                            reinterpret_cast<__half2*>(myrow)[q] = __floats2half2_rn(acc[(2 * q) / PW][(2 * q) % PW],
+                                                                                     acc[(2 * q + 1) / PW][(2 * q + 1) % PW]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < NB; ++i) myrow[i] = __float2half_rn(acc[i / PW][i % PW]);
+                    }
+                }
+                T* gdst = out + ((size_t)ka * C + ca) * NB;
+                const unsigned bytes = (unsigned)cn * NB * (unsigned)sizeof(T);
+                if (((reinterpret_cast<uintptr_t>(gdst) & 15) == 0) && (bytes & 15u) == 0) {
+                    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) bulk_store_issue(gdst, sOut, bytes);
+                    pending = true;
+                } else {
+                    __syncwarp();
+                    const T* tile = reinterpret_cast<const T*>(sOut);
+                    for (int i = lane; i < cn * NB; i += 32) gdst[i] = tile[i];
+                    __syncwarp();
+                }
+            }
+        } else {
+            // footprint larger than the staged path: everything through the generic tile body, the output tile as scratch
+            process_tile<PH, PW, false, T, true, OCL, true>(feat, B, C, H, W, rois, scale, sr, aligned, out, (long long)ka, ca,
+                                                            cn, prep, prep_tabs, sOut,
+                                                            reinterpret_cast<float*>(base + S::kOffTab + par * S::kTabBytes),
+                                                            lane, a0, a1, &pending);
+            load_after_next();
+            __syncwarp();
+            if (have_next && n1.y && !next_issued && nbn * kTmaBoxBytes <= kTmaVBytes) {
+                if (lane == 0)
+                    tma_issue<PH, PW, T>(&tmap, n0, n1, kn, cnx, prep_tabs, sbase + v_off(par ^ 1, nbn),
+                                         sbase + S::kOffTab + (par ^ 1) * S::kTabBytes, sbar + 8 * (par ^ 1));
+                next_issued = true;
+            }
+        }
+        if (!have_next) break;
+        t = tn; ka = kn; ca = cnx; a0 = n0; a1 = n1;
+        tn = tm; kn = km; cnx = cm; n0 = m0; n1 = m1;
+        cur_issued = next_issued;
+        par ^= 1;
+    }
+    if (pending && lane == 0) bulk_store_wait_read();
+    B200_SPAN_END(span_slot);
+}
+
 // Any output size / any parameters: one thread per output element, direct sampling.
 template <bool NHWC, typename T>
 __global__ void __launch_bounds__(256)
@@ -824,6 +1178,124 @@ roi_align_generic_kernel(const T* __restrict__ feat, int B, int C, int H, int W,
     }
 }
 
+
+// ---- per-device launch state ---------------------------------------------------------------------------
+// Function attributes (the dynamic shared-memory opt-in), occupancy and the scratch pool belong to a device,
+// not to the process: a host application may drive several GPUs from one process.  Each kernel instantiation
+// keeps one slot per device ordinal; a race between two host threads writes the same values twice.
+constexpr int kMaxDevices = 64;
+
+inline int device_ordinal() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) dev = 0;
+    return dev;
+}
+
+// Warps of `kern` the current device holds at once (and the shared-memory opt-in, once per device).
+template <typename Kern>
+int resident_warps_of(Kern kern, int (&cache)[kMaxDevices], int warps_per_cta, int smem_bytes, int* out) {
+    const int dev = device_ordinal();
+    if (!cache[dev]) {
+        int sms = 0, per_sm = 0;
+        B200_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps_per_cta * 32, smem_bytes));
+        cache[dev] = sms * (per_sm > 0 ? per_sm : 1) * warps_per_cta;
+    }
+    *out = cache[dev];
+    return B200_OK;
+}
+
+// Stream-ordered scratch (per-ROI records and weight tables of the two-kernel path) comes from a PRIVATE pool per
+// device that keeps freed blocks cached; the application's default pool and its release threshold are not touched.
+struct ScratchPool {
+    std::mutex mu;
+    cudaMemPool_t pool = nullptr;
+};
+ScratchPool g_scratch[kMaxDevices];
+
+int scratch_pool(cudaMemPool_t* out) {
+    const int dev = device_ordinal();
+    ScratchPool& sp = g_scratch[dev];
+    std::lock_guard<std::mutex> lock(sp.mu);
+    if (!sp.pool) {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = dev;
+        cudaMemPool_t pool = nullptr;
+        B200_CUDA(cudaMemPoolCreate(&pool, &props));
+        unsigned long long keep = ~0ull;
+        B200_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        sp.pool = pool;
+    }
+    *out = sp.pool;
+    return B200_OK;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+    static std::atomic<void*> cached{nullptr};
+    void* fn = cached.load(std::memory_order_acquire);
+    if (!fn) {
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            fn = nullptr;
+        cached.store(fn, std::memory_order_release);
+    }
+    return reinterpret_cast<EncodeTiledFn>(fn);
+}
+
+// Launches the TMA-staged kernel when it applies: NCHW map whose rows are a multiple of 16 bytes (the tensor map's
+// stride rule), 16-byte aligned base, dimensions inside the descriptor's limits.  Returns 1 when it does not.
+// The TMA-staged kernel applies to float32 NCHW maps whose rows are a multiple of 16 bytes (the tensor map's stride
+// rule) with a 16-byte aligned base and dimensions inside the descriptor's limits.  (Half maps would need a
+// 16-column window: not built, they stay on the multi-tile kernel.)
+template <typename T>
+bool tma_applies(const T* feat, int C, int H, int W) {
+    if (sizeof(T) != 4) return false;
+    if (((size_t)W * sizeof(T)) % 16 || (reinterpret_cast<uintptr_t>(feat) & 15)) return false;
+    if ((unsigned long long)C * H * W * sizeof(T) >= (1ull << 40)) return false;
+    return encode_tiled_fn() != nullptr;
+}
+constexpr int kTmaXAlign = 4;                    // cells per 16 bytes of a float32 map row
+
+template <int PH, int PW, bool OCL, typename T>
+int launch_tma(const T* feat, int B, int C, int H, int W, const float* rois, long long K, float scale, int sr, int aligned,
+               T* out, int ctiles, const RoiPrep* prep, const float* tabs, long long tiles, cudaStream_t st) {
+    using S = TmaSmem<PH, PW>;
+    constexpr int kEs = (int)sizeof(T);
+    if (reinterpret_cast<uintptr_t>(tabs) & 15) return 1;
+    EncodeTiledFn encode = encode_tiled_fn();
+    if (!encode) return 1;
+    CUtensorMap tmap;
+    const cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)C, (cuuint64_t)B};
+    const cuuint64_t strides[3] = {(cuuint64_t)W * kEs, (cuuint64_t)H * W * kEs, (cuuint64_t)C * H * W * kEs};
+    const cuuint32_t box[4] = {(cuuint32_t)(16 / kEs), (cuuint32_t)kTmaRows, 32u, 1u};
+    const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+    const CUresult r = encode(&tmap, kEs == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4,
+                              const_cast<T*>(feat), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return 1;
+    static int cache[kMaxDevices];               // per instantiation and device
+    auto kern = roi_align_tma_kernel<PH, PW, T, OCL>;
+    int resident = 0;
+    const int rc = resident_warps_of(kern, cache, kTmaWarps, S::kBytesPerCta, &resident);
+    if (rc) return rc;
+    const long long window = (long long)resident * B200_ROI_TMA_TILES;
+    const long long groups = (tiles + window - 1) / window;
+    const long long last = tiles - (groups - 1) * window;
+    const long long warps = (groups - 1) * resident + (last < resident ? last : resident);
+    kern<<<(unsigned)((warps + kTmaWarps - 1) / kTmaWarps), kTmaWarps * 32, S::kBytesPerCta, st>>>(
+        tmap, feat, B, C, H, W, rois, K, scale, sr, aligned, out, ctiles, prep, tabs, resident, B200_ROI_TMA_TILES);
+    return check_launch("roi_align_tma_kernel");
+}
+
 // Below this many tiles one fused kernel is faster (the prep kernel costs a dependent launch); above it the
 // per-ROI work is done once by roi_prep_kernel and shared by the ROI's channel tiles.
 constexpr long long kPrepMinTiles = 16384;
@@ -842,16 +1314,11 @@ int launch_pipe(const T* feat, int B, int C, int H, int W, const float* rois, lo
         using P = PipeSmem<PH, PW>;
         if (!OCL && ((reinterpret_cast<uintptr_t>(out) & 15) || (sizeof(T) == 2 && (C & 1)))) return 1;
         if (sizeof(T) == 2 && ((C & 7) || (reinterpret_cast<uintptr_t>(feat) & 15))) return 1;   // half: 16-byte copies only
-        static int resident_warps = 0;       // warps the device holds at once (per instantiation)
+        static int cache[kMaxDevices];       // warps the device holds at once (per instantiation and device)
         auto kern = roi_align_pipe_kernel<PH, PW, OCL, T>;
-        if (!resident_warps) {
-            int dev = 0, sms = 0, per_sm = 0;
-            B200_CUDA(cudaGetDevice(&dev));
-            B200_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-            B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P::kBytesPerCta));
-            B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kPipeWarps * 32, P::kBytesPerCta));
-            resident_warps = sms * (per_sm > 0 ? per_sm : 1) * kPipeWarps;
-        }
+        int resident_warps = 0;
+        const int rcw = resident_warps_of(kern, cache, kPipeWarps, P::kBytesPerCta, &resident_warps);
+        if (rcw) return rcw;
         const long long window = (long long)resident_warps * kPipeTilesPerWarp;
         const long long groups = (tiles + window - 1) / window;
         const long long last = tiles - (groups - 1) * window;                 // tiles in the last window
@@ -868,11 +1335,12 @@ template <int PH, int PW, bool NHWC, bool OCL, typename T>
 int launch_tile(const T* feat, int B, int C, int H, int W, const float* rois, long long K,
                 float scale, int sr, int aligned, T* out, cudaStream_t st) {
     using L = TileSmem<PH, PW>;
-    static bool configured = false;          // per instantiation; the attribute is idempotent
+    static bool configured[kMaxDevices];     // per instantiation and device; the attribute is idempotent
     auto fused = roi_align_tile_kernel<PH, PW, NHWC, T, false, OCL>;
-    if (!configured) {
+    const int dev = device_ordinal();
+    if (!configured[dev]) {
         B200_CUDA(cudaFuncSetAttribute(fused, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kBytesPerCta));
-        configured = true;
+        configured[dev] = true;
     }
     const int ctiles = (C + 31) / 32;
     const long long warps = K * ctiles;
@@ -883,46 +1351,39 @@ int launch_tile(const T* feat, int B, int C, int H, int W, const float* rois, lo
                                                                             aligned, out, ctiles, nullptr, nullptr);
         return check_launch("roi_align_tile_kernel");
     }
-    static bool pool_ready = false;          // keep freed scratch cached in the device's default pool: by default
-    if (!pool_ready) {                       // the pool hands memory back at every synchronisation point
-        int dev = 0;
-        cudaMemPool_t pool;
-        B200_CUDA(cudaGetDevice(&dev));
-        B200_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
-        unsigned long long keep = ~0ull, cur = 0;
-        B200_CUDA(cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &cur));
-        if (cur < (64ull << 20)) B200_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-        pool_ready = true;
-    }
+    cudaMemPool_t pool = nullptr;
+    int rc = scratch_pool(&pool);
+    if (rc) return rc;
     char* ws = nullptr;                      // stream-ordered scratch: K records + K tables
     const size_t rec = (size_t)K * sizeof(RoiPrep), tab = (size_t)K * L::kTabFloats * sizeof(float);
-    B200_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ws), rec + tab, st));
+    B200_CUDA(cudaMallocFromPoolAsync(reinterpret_cast<void**>(&ws), rec + tab, pool, st));
     RoiPrep* prep = reinterpret_cast<RoiPrep*>(ws);
     float* tabs = reinterpret_cast<float*>(ws + rec);
-    roi_prep_kernel<PH, PW><<<(unsigned)((K + 3) / 4), 128, 0, st>>>(rois, K, B, H, W, scale, sr, aligned, prep, tabs);
-    int rc = check_launch("roi_prep_kernel");
+    bool use_tma = false;
+    if constexpr (!NHWC && sizeof(T) == 4) use_tma = tma_applies(feat, C, H, W);
+    roi_prep_kernel<PH, PW><<<(unsigned)((K + 3) / 4), 128, 0, st>>>(rois, K, B, H, W, scale, sr, aligned, prep, tabs,
+                                                                     use_tma ? kTmaXAlign : 1);
+    rc = check_launch("roi_prep_kernel");
     if (rc == B200_OK) {
-        rc = launch_pipe<PH, PW, NHWC, OCL>(feat, B, C, H, W, rois, K, scale, sr, aligned, out, ctiles, prep, tabs, warps, st);
-        if (rc == 1) {                       // no pipelined kernel for this layout / type / size / alignment
-            static int resident_warps = 0;   // per instantiation
+        rc = 1;
+        if constexpr (!NHWC && sizeof(T) == 4)
+            if (use_tma) rc = launch_tma<PH, PW, OCL>(feat, B, C, H, W, rois, K, scale, sr, aligned, out, ctiles, prep, tabs, warps, st);
+        if (rc == 1) rc = launch_pipe<PH, PW, NHWC, OCL>(feat, B, C, H, W, rois, K, scale, sr, aligned, out, ctiles, prep, tabs, warps, st);
+        if (rc == 1) {                       // no TMA / pipelined kernel for this layout / type / size / alignment
+            static int cache[kMaxDevices];   // per instantiation and device
             auto multi = roi_align_multi_kernel<PH, PW, NHWC, T, OCL>;
-            if (!resident_warps) {
-                int dev = 0, sms = 0, per_sm = 0;
-                B200_CUDA(cudaGetDevice(&dev));
-                B200_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-                B200_CUDA(cudaFuncSetAttribute(multi, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kBytesPerCta));
-                B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, multi, kWarpsPerCta * 32,
-                                                                        L::kBytesPerCta));
-                resident_warps = sms * (per_sm > 0 ? per_sm : 1) * kWarpsPerCta;
+            int resident_warps = 0;
+            rc = resident_warps_of(multi, cache, kWarpsPerCta, L::kBytesPerCta, &resident_warps);
+            if (rc == B200_OK) {
+                const long long window = (long long)resident_warps * B200_ROI_MULTI_TILES;
+                const long long groups = (warps + window - 1) / window;
+                const long long last = warps - (groups - 1) * window;
+                const long long nw = (groups - 1) * resident_warps + (last < resident_warps ? last : resident_warps);
+                multi<<<(unsigned)((nw + kWarpsPerCta - 1) / kWarpsPerCta), kWarpsPerCta * 32, L::kBytesPerCta, st>>>(
+                    feat, B, C, H, W, rois, K, scale, sr, aligned, out, ctiles, prep, tabs, resident_warps,
+                    B200_ROI_MULTI_TILES);
+                rc = check_launch("roi_align_multi_kernel");
             }
-            const long long window = (long long)resident_warps * B200_ROI_MULTI_TILES;
-            const long long groups = (warps + window - 1) / window;
-            const long long last = warps - (groups - 1) * window;
-            const long long nw = (groups - 1) * resident_warps + (last < resident_warps ? last : resident_warps);
-            multi<<<(unsigned)((nw + kWarpsPerCta - 1) / kWarpsPerCta), kWarpsPerCta * 32, L::kBytesPerCta, st>>>(
-                feat, B, C, H, W, rois, K, scale, sr, aligned, out, ctiles, prep, tabs, resident_warps,
-                B200_ROI_MULTI_TILES);
-            rc = check_launch("roi_align_multi_kernel");
         }
     }
     B200_CUDA(cudaFreeAsync(ws, st));

@@ -13,6 +13,7 @@
 // State never leaves the device.  Tracks live in fixed physical slots (banks are never moved);
 // `order` lists the live slots by ascending track id, which is the row order the reference uses
 // (sorted(rows_main), :486-487) because ids are handed out monotonically (:371-372).
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -50,7 +51,7 @@ constexpr int kThreads = 256;
 constexpr int kHdr = 8;                 // ints per stream in hdr / cnt
 enum { H_NLIVE = 0, H_NEXT = 1, H_NFREE = 2 };
 enum { C_M1 = 0, C_M2 = 1, C_NU = 2, C_MODE = 3, C_NMATCH = 4, C_NUT = 5, C_STATUS = 6 };
-enum { MODE_SKIP = 0, MODE_EMPTY = 1, MODE_NORMAL = 2 };
+enum { MODE_SKIP = 0, MODE_EMPTY = 1, MODE_NORMAL = 2, MODE_FAILED = 3 };   // FAILED: scipy would have raised in stage 1
 enum { R_NMATCH = 0, R_NUT = 1, R_NUD = 2, R_NLIVE = 3, R_NEXT = 4, R_STATUS = 5, R_M1 = 6, R_M2 = 7, R_HDR = 8 };
 
 struct Dev {
@@ -66,6 +67,7 @@ struct Dev {
     int* row_fc;                     // stage 1, written by the cost kernel: column of each row's unique minimum (-1: none, -2: NaN / -inf in the row)
     float* row_fv;                   //          that minimum
     int *rows_main, *rows_reid, *cnt, *ud1, *det_used, *m_row, *m_det, *m_app, *tmp;
+    int* born;                       // [S, MD] detection index of each birth of the step, in order
     int2 *work1, *work2;             // (stream, row * 64 + detection tile) items of the two cost launches
     int* wcount;                     // [3] items queued for this step: cost1, cost2, updates
     int *upd_slot, *upd_det;         // update queue: global slot / detection index of every match
@@ -671,9 +673,19 @@ __global__ void __launch_bounds__(kThreads) assign_kernel(Dev d, int smem_matrix
     int* cnt = d.cnt + s * kHdr;
     // both cost launches of this step are done: clear their queues for the next step
     if (STAGE == 2 && s == 0 && tid == 0) { d.wcount[0] = 0; d.wcount[1] = 0; }
-    if (cnt[C_MODE] != MODE_NORMAL) return;
     int* hdr = d.hdr + s * kHdr;
     int* res = d.result + (size_t)s * d.res_stride;
+    if (STAGE == 2 && cnt[C_MODE] == MODE_FAILED) {
+        // Stage 1 hit a NaN / infeasible matrix: the reference raises inside hungarian_assign (hung.py:28) before
+        // any mark_missed / update_matched / birth / purge, so the stream's state stays "predict only".
+        if (tid == 0) {
+            res[R_NMATCH] = res[R_NUT] = res[R_NUD] = 0;
+            res[R_NLIVE] = hdr[H_NLIVE]; res[R_NEXT] = hdr[H_NEXT]; res[R_STATUS] = cnt[C_STATUS];
+            res[R_M1] = cnt[C_M1]; res[R_M2] = cnt[C_M2];
+        }
+        return;
+    }
+    if (cnt[C_MODE] != MODE_NORMAL) return;
     const size_t sb = (size_t)s * d.MT, db = (size_t)s * d.MD;
     const int M = STAGE == 1 ? cnt[C_M1] : cnt[C_M2];
     const int N = STAGE == 1 ? d.n_det[s] : cnt[C_NU];
@@ -686,6 +698,7 @@ __global__ void __launch_bounds__(kThreads) assign_kernel(Dev d, int smem_matrix
     int* out_ut = res_ut(d, res);
     int* m_col = d.tmp + sb;                        // column (local det index) of each match
     int n_match = 0, n_ut = 0, n_left = N;
+    bool failed = false;                            // uniform across the CTA
     if (STAGE == 1) TRK_STAMP(0);
 
     if (M > 0 && N > 0) {
@@ -704,7 +717,8 @@ __global__ void __launch_bounds__(kThreads) assign_kernel(Dev d, int smem_matrix
         __syncthreads();
         if (STAGE == 1) TRK_STAMP(1);
         if (s_rc != B200_OK) {                      // NaN / infeasible: scipy would raise
-            if (tid == 0) cnt[C_STATUS] = s_rc;
+            failed = true;
+            if (tid == 0) { cnt[C_STATUS] = s_rc; if (STAGE == 1) cnt[C_MODE] = MODE_FAILED; }
         } else {
             const int* col = tall ? w.r4c : w.c4r;  // assigned column of row r (-1: unassigned)
             auto is_match = [&](int r) {
@@ -739,6 +753,10 @@ __global__ void __launch_bounds__(kThreads) assign_kernel(Dev d, int smem_matrix
     }
 
     if (STAGE == 1) {
+        if (failed) {                               // nothing else happens to this stream in this step
+            if (tid == 0) { cnt[C_NU] = 0; cnt[C_NMATCH] = 0; cnt[C_NUT] = 0; }
+            return;
+        }
         // leftover detections, ascending (hung.py:43)
         n_left = block_compact(N, [&](int j) { return d.det_used[db + j] == 0; },
                                [&](int pos, int j) { d.ud1[db + pos] = j; }, scratch);
@@ -748,6 +766,15 @@ __global__ void __launch_bounds__(kThreads) assign_kernel(Dev d, int smem_matrix
         return;
     }
 
+    if (failed) {
+        // The ReID-stage assignment raised (:560): stage 1's updates and misses stand, no births, no purge.
+        if (tid == 0) {
+            res[R_NMATCH] = match0; res[R_NUT] = ut0; res[R_NUD] = 0;
+            res[R_NLIVE] = hdr[H_NLIVE]; res[R_NEXT] = hdr[H_NEXT]; res[R_STATUS] = cnt[C_STATUS];
+            res[R_M1] = cnt[C_M1]; res[R_M2] = cnt[C_M2];
+        }
+        return;
+    }
     // ---- stage 2 tail: leftover dets, births (:362-373), purge (:357-360), result table ------------
     int* out_ud = res_ud(d, res);
     n_left = block_compact(N, [&](int jl) { return d.det_used[db + d.ud1[db + jl]] == 0; },
@@ -755,7 +782,7 @@ __global__ void __launch_bounds__(kThreads) assign_kernel(Dev d, int smem_matrix
     const int nl = hdr[H_NLIVE], nfree = hdr[H_NFREE], next_id = hdr[H_NEXT];
     int* order = d.order + sb;
     const int* fl = d.free_list + sb;
-    int* born = d.m_row + sb;                       // det index of each birth, in order
+    int* born = d.born + db;                        // det index of each birth, in order
     const int want = block_compact(n_left, [&](int k) { return !(d.confs[db + out_ud[k]] < d.init_conf_min); },
                                    [&](int pos, int k) { born[pos] = out_ud[k]; }, scratch);
     const int nb = min(want, nfree);
@@ -921,7 +948,7 @@ extern "C" int b200_tracker_create(b200_tracker** out, int n_streams, int max_tr
     TAKE(row_fc, int, S * MT); TAKE(row_fv, float, S * MT);
     TAKE(rows_main, int, S * MT); TAKE(rows_reid, int, S * MT); TAKE(cnt, int, S * trk::kHdr);
     TAKE(ud1, int, S * MD); TAKE(det_used, int, S * MD); TAKE(m_row, int, S * MT); TAKE(m_det, int, S * MT);
-    TAKE(m_app, int, S * MT); TAKE(tmp, int, S * MT);
+    TAKE(m_app, int, S * MT); TAKE(tmp, int, S * MT); TAKE(born, int, S * MD);
     const size_t tiles_max = (MD + cost::kTileN - 1) / cost::kTileN;
     TAKE(work1, int2, S * MT * tiles_max); TAKE(work2, int2, S * MT * tiles_max); TAKE(wcount, int, 4);
     TAKE(upd_slot, int, S * MT); TAKE(upd_det, int, S * MT); TAKE(upd_cost, float, S * MT); TAKE(upd_flag, uint8_t, S * MT);
@@ -947,7 +974,7 @@ extern "C" int b200_tracker_create(b200_tracker** out, int n_streams, int max_tr
     PTR(prev_conff, float); PTR(C1, float); PTR(C1T, float); PTR(C2, float); PTR(C2T, float); PTR(gate_SI, double);
     PTR(row_fc, int); PTR(row_fv, float);
     PTR(rows_main, int); PTR(rows_reid, int); PTR(cnt, int); PTR(ud1, int); PTR(det_used, int); PTR(m_row, int);
-    PTR(m_det, int); PTR(m_app, int); PTR(tmp, int); PTR(work1, int2); PTR(work2, int2); PTR(wcount, int);
+    PTR(m_det, int); PTR(m_app, int); PTR(tmp, int); PTR(born, int); PTR(work1, int2); PTR(work2, int2); PTR(wcount, int);
     PTR(upd_slot, int); PTR(upd_det, int); PTR(upd_cost, float); PTR(upd_flag, uint8_t);
 #undef PTR
     t->in_ndet = reinterpret_cast<int*>(base + o_in_ndet);
@@ -987,8 +1014,10 @@ extern "C" int b200_tracker_create(b200_tracker** out, int n_streams, int max_tr
     if (max_tracks <= 256 && max_dets <= 256 && mat > 32 * 1024) mat = 32 * 1024;
     t->smem_matrix_floats = (int)(mat / sizeof(float));
     t->assign_smem = wb + mat;
-    cudaFuncSetAttribute(trk::assign_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t->assign_smem);
-    cudaFuncSetAttribute(trk::assign_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t->assign_smem);
+    // The opt-in belongs to the kernel function (per device), not to this handle: always the full budget, so
+    // handles of different capacities can be stepped in any order.
+    cudaFuncSetAttribute(trk::assign_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
+    cudaFuncSetAttribute(trk::assign_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
     cudaFuncSetAttribute(trk::cost2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cost::smem_bytes(cost::kMaxBank));
     trk::reset_kernel<<<n_streams, 128>>>(d);
     e = cudaDeviceSynchronize();
@@ -1030,6 +1059,26 @@ extern "C" int b200_tracker_reset(b200_tracker* t, void* stream) {
 }
 
 extern "C" int b200_tracker_result_stride(const b200_tracker* t) { return t ? t->d.res_stride : 0; }
+
+extern "C" int b200_tracker_live_counts(b200_tracker* t, int32_t* n_live_host, int32_t* next_id_host, void* stream) {
+    B200_REQUIRE(t, "tracker_live_counts: null handle");
+    cudaStream_t st = as_stream(stream);
+    const int S = t->d.S;
+    int* h = static_cast<int*>(malloc(sizeof(int) * trk::kHdr * (size_t)S));
+    B200_REQUIRE(h, "tracker_live_counts: out of host memory");
+    cudaError_t e = cudaMemcpyAsync(h, t->d.hdr, sizeof(int) * trk::kHdr * (size_t)S, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) {
+        free(h);
+        return fail(B200_ECUDA, "tracker_live_counts: %s", cudaGetErrorString(e));
+    }
+    for (int s = 0; s < S; ++s) {
+        if (n_live_host) n_live_host[s] = h[s * trk::kHdr + trk::H_NLIVE];
+        if (next_id_host) next_id_host[s] = h[s * trk::kHdr + trk::H_NEXT];
+    }
+    free(h);
+    return B200_OK;
+}
 
 extern "C" int b200_tracker_step(b200_tracker* t, const int32_t* n_det, const double* boxes, const double* confs,
                                  const float* embs, const int32_t* frame_id, int32_t* result, void* stream) {

@@ -75,6 +75,18 @@ class MultiStreamTracker:
         self._h = ctypes.c_void_p()
         self._create(int(max_tracks), int(max_dets))
         self.n_live = np.zeros(self.S, dtype=np.int64)
+        self._n_live_stale = False                 # set by step_device: the host copy of the live counts is out of date
+
+    def n_live_now(self) -> np.ndarray:
+        """Live tracks per stream as of the work queued so far (re-read from the device after device-side steps)."""
+        if self._n_live_stale:
+            n = np.zeros(self.S, np.int32)
+            with torch.cuda.device(self.device):
+                _lib.check(_lib.lib().b200_tracker_live_counts(self._h, n.ctypes.data_as(ctypes.c_void_p), None,
+                                                               _lib.stream_ptr(self.device)))
+            self.n_live[:] = n
+            self._n_live_stale = False
+        return self.n_live
 
     def _create(self, max_tracks, max_dets):
         h = ctypes.c_void_p()
@@ -136,7 +148,7 @@ class MultiStreamTracker:
         boxes = np.ascontiguousarray(boxes, dtype=np.float64).reshape(self.S, self.max_dets, 4)
         confs = np.ascontiguousarray(confs, dtype=np.float64).reshape(self.S, self.max_dets)
         embs = np.ascontiguousarray(embs, dtype=np.float32).reshape(self.S, self.max_dets, 128)
-        need = int((self.n_live + np.maximum(n_det, 0)).max())
+        need = int((self.n_live_now() + np.maximum(n_det, 0)).max())
         if need > self.max_tracks:                     # the reference is unbounded: migrate to a larger handle
             if not self.auto_grow:
                 raise _lib.B200Error("tracker capacity: live tracks + detections could exceed max_tracks=%d; "
@@ -148,6 +160,9 @@ class MultiStreamTracker:
                                                    p(self._res), _lib.stream_ptr(self.device))
         _lib.check(rc)
         self.n_live[:] = self._res[:, R_NLIVE]
+        # A failing stream does not lose the others: the table (self.last_result) is complete before anything is raised,
+        # and the failing stream's state is what the reference leaves behind when scipy raises (predict only).
+        self.last_result = self._res
         bad = np.nonzero(self._res[:, R_STATUS])[0]
         if len(bad):
             st = int(self._res[bad[0], R_STATUS])
@@ -155,6 +170,10 @@ class MultiStreamTracker:
                 raise ValueError("matrix contains invalid numeric entries (stream %d)" % bad[0])
             if st == _lib.EINFEASIBLE:
                 raise ValueError("cost matrix is infeasible (stream %d)" % bad[0])
+            if st == _lib.ECAPACITY:
+                raise _lib.B200Error("tracker capacity exceeded on stream %d: births were dropped because live tracks + "
+                                     "detections exceeded max_tracks=%d (device-side steps do not grow the handle; "
+                                     "call grow() or construct with a larger max_tracks)" % (bad[0], self.max_tracks))
             raise _lib.B200Error("tracker step failed on stream %d with status %d" % (bad[0], st))
         return self._res
 
@@ -175,6 +194,7 @@ class MultiStreamTracker:
             rc = _lib.lib().b200_tracker_step(self._h, _lib.ptr(n_det), _lib.ptr(boxes), _lib.ptr(confs), _lib.ptr(embs),
                                               _lib.ptr(frame_ids), _lib.ptr(result), _lib.stream_ptr(self.device))
         _lib.check(rc)
+        self._n_live_stale = True
         return result
 
     def decode(self, row: np.ndarray):

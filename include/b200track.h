@@ -151,9 +151,15 @@ int  b200_tracker_reset(b200_tracker* t, void* stream);
  *   then matches (tid, det) x max_dets, unmatched track ids x max_tracks,
  *   unmatched det indices x max_dets -- in the order Tracking.update returns them (:607-610). */
 int  b200_tracker_result_stride(const b200_tracker* t);
+/* Live-track count and next track id of every stream as of the work queued on `stream` so far (copies 8 ints per
+ * stream and synchronises the stream).  Callers that step with device-resident inputs (b200_tracker_step) use it
+ * to learn how full the handle is; either pointer may be NULL. */
+int  b200_tracker_live_counts(b200_tracker* t, int32_t* n_live_host, int32_t* next_id_host, void* stream);
 /* Device-resident inputs: n_det[S] (-1 = stream idle this step, 0 = empty frame, :467-471),
  * boxes [S,max_dets,4] float64 xyxy, confs [S,max_dets] float64, embs [S,max_dets,128]
- * float32, frame_id[S].  result: device int32 [S, stride]. */
+ * float32, frame_id[S].  result: device int32 [S, stride].
+ * Capacity precondition: for every stream n_live + n_det <= max_tracks (a birth that finds no free slot is
+ * dropped and reported as B200_ECAPACITY in the stream's status column; b200_tracker_live_counts tells n_live). */
 int  b200_tracker_step(b200_tracker* t, const int32_t* n_det, const double* boxes,
                        const double* confs, const float* embs, const int32_t* frame_id,
                        int32_t* result, void* stream);

@@ -60,3 +60,26 @@ def new_tracking():
     ref = load()
     with _cwd(REFERENCE_ROOT):
         return ref.mainTracking.Tracking()
+
+
+def load_roi_wrappers():
+    """The reference's two ROI Align call conventions as unbound functions (both ignore ``self``):
+    ``MainInfer.roi_align_from_input_boxes`` (tracking.py:193-221) and ``PreProcess._preprocess_roi``
+    (trainingCard.py:24-79).  trainingCard.py:9 imports the YOLOv7 wrapper, which drags in matplotlib /
+    seaborn (absent): a dummy ``model.yolov7.yoloDetects2`` stands in, it is never called."""
+    if not available():
+        raise RuntimeError("reference tree not mounted at %s" % REFERENCE_ROOT)
+    _install_stubs()
+    import model  # noqa: F401  (the reference's top-level package)
+    for name in ("model.yolov7", "model.yolov7.yoloDetects2"):
+        if name not in sys.modules:
+            stub = types.ModuleType(name)
+            stub.__path__ = []
+            sys.modules[name] = stub
+    sys.modules["model.yolov7.yoloDetects2"].YoloDetects = type("YoloDetects", (), {})
+    sys.modules["model.yolov7"].yoloDetects2 = sys.modules["model.yolov7.yoloDetects2"]
+    sys.modules["model"].yolov7 = sys.modules["model.yolov7"]
+    import tracking as live
+    import model.utils.trainingScr.trainingCard as tc
+    return types.SimpleNamespace(roi_align_from_input_boxes=live.MainInfer.roi_align_from_input_boxes,
+                                 preprocess_roi=tc.PreProcess._preprocess_roi)

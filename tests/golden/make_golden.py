@@ -200,8 +200,39 @@ def run_roi_cases():
     print("roi: ok")
 
 
+def run_roi_wrapper_cases():
+    """The reference's own ROI call conventions, called unbound (both methods ignore ``self``):
+    MainInfer.roi_align_from_input_boxes (tracking.py:193-221) and PreProcess._preprocess_roi
+    (trainingCard.py:24-79), on square and non-square maps, with inverted / out-of-image / sub-pixel boxes."""
+    import torch
+    w = reference_loader.load_roi_wrappers()
+    out = {}
+    for tag, (C, Hf, Wf, H_in, W_in) in {"sq": (32, 20, 20, 640, 640), "wide": (24, 34, 60, 1088, 1920)}.items():
+        feat = synth.feature_map(3, 1, C, Hf, Wf)
+        boxes = np.concatenate([synth.random_boxes(np.random.default_rng(4), 9, H_in, W_in),
+                                synth.edge_case_boxes(H_in, W_in)]).astype(np.float64)
+        out[tag + "_feat"], out[tag + "_boxes"] = feat, boxes
+        out[tag + "_hw"] = np.array([H_in, W_in], dtype=np.int64)
+        f = torch.from_numpy(feat)
+        for ps in ((7, 7), (10, 10)):
+            y = w.roi_align_from_input_boxes(None, f, boxes.tolist(), (H_in, W_in), out_size=ps)
+            out["%s_r1_%d" % (tag, ps[0])] = y.numpy()
+        y = w.roi_align_from_input_boxes(None, f, boxes.tolist(), (H_in, W_in))          # default 7x7
+        assert np.array_equal(y.numpy(), out[tag + "_r1_7"])
+        out[tag + "_r2_10"] = w.preprocess_roi(None, f, torch.from_numpy(boxes), (H_in, W_in)).numpy()
+        out[tag + "_r2_7_nomin"] = w.preprocess_roi(None, f, torch.from_numpy(boxes), (H_in, W_in), output_size=(7, 7),
+                                                    sampling_ratio=2, aligned=True, enforce_min_size=0.0).numpy()
+    np.savez_compressed(os.path.join(OUT, "roi_wrappers.npz"), **out)
+    print("roi_wrappers: ok")
+
+
 if __name__ == "__main__":
     assert reference_loader.available(), "mount the reference at /root/reference"
+    if len(sys.argv) > 1:                      # regenerate only the named fixtures, e.g. `make_golden.py roi_wrappers`
+        for name in sys.argv[1:]:
+            globals()["run_%s_cases" % name]()
+        sys.exit(0)
+    run_roi_wrapper_cases()
     run_roi_cases()
     run_lsap_cases()
     run_kalman_cases()

@@ -107,6 +107,46 @@ def test_roi_wrappers_match_reference_call_conventions():
         roi.preprocess_roi(torch.zeros(2, 4, 5, 5).cuda(), torch.zeros(1, 4), (10, 10))
 
 
+def test_roi_wrappers_vs_reference_golden():
+    """roi_align_from_input_boxes / preprocess_roi against fixtures recorded from the reference's OWN methods
+    (tracking.py:193-221, trainingCard.py:24-79; tests/golden/make_golden.py::run_roi_wrapper_cases)."""
+    g = load_golden("roi_wrappers")
+    for tag in ("sq", "wide"):
+        boxes, hw = g[tag + "_boxes"], tuple(int(v) for v in g[tag + "_hw"])
+        f = torch.from_numpy(g[tag + "_feat"]).cuda()
+        for ps in (7, 10):
+            got = roi.roi_align_from_input_boxes(f, boxes.tolist(), hw, out_size=(ps, ps))
+            assert_close(got.cpu().numpy(), g["%s_r1_%d" % (tag, ps)], what="%s r1 %d" % (tag, ps))
+        got = roi.roi_align_from_input_boxes(f, torch.from_numpy(boxes).cuda(), hw)          # device boxes, default 7x7
+        assert_close(got.cpu().numpy(), g[tag + "_r1_7"], what=tag + " r1 device boxes")
+        got = roi.preprocess_roi(f, torch.from_numpy(boxes), hw)
+        assert_close(got.cpu().numpy(), g[tag + "_r2_10"], what=tag + " r2")
+        got = roi.preprocess_roi(f, torch.from_numpy(boxes).cuda(), hw, output_size=(7, 7), enforce_min_size=0.0)
+        assert_close(got.cpu().numpy(), g[tag + "_r2_7_nomin"], what=tag + " r2 nomin")
+
+
+@pytest.mark.parametrize("nhwc", [False, True])
+def test_roi_c5_full_width_vs_oracle(nhwc):
+    """BASELINE config 5 at full width: 64 maps [512,34,60], 128 boxes each = 8 192 ROIs in ONE launch (the prep +
+    multi-tile / TMA / pipelined kernels), every ROI against the oracle."""
+    S, C, Hf, Wf, H_in, W_in, n = 64, 512, 34, 60, 1088, 1920, 128
+    rng = np.random.default_rng(17)
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    f = torch.randn((S, C, Hf, Wf), device="cuda", generator=gen)
+    boxes = np.concatenate([synth.random_boxes(rng, n, H_in, W_in) for _ in range(S)])
+    edge = synth.edge_case_boxes(H_in, W_in)
+    boxes[:len(edge)] = edge
+    rois = np.concatenate([np.repeat(np.arange(S), n)[:, None].astype(np.float64), boxes], 1).astype(np.float32)
+    fin = f.contiguous(memory_format=torch.channels_last) if nhwc else f
+    got = roi.roi_align(fin, torch.from_numpy(rois).cuda(), (10, 10), Hf / float(H_in), 2, True)
+    assert got.shape == (S * n, C, 10, 10)
+    for s0 in range(0, S, 8):                                        # eight maps at a time keeps host memory modest
+        sub = rois[s0 * n:(s0 + 8) * n].copy()
+        sub[:, 0] -= s0
+        want = native.roi_align(f[s0:s0 + 8].cpu().numpy(), sub, (10, 10), Hf / float(H_in), 2, True)
+        assert_close(got[s0 * n:(s0 + 8) * n].cpu().numpy(), want, rtol=1e-5, atol=2e-6, what="c5 maps %d.." % s0)
+
+
 def test_roi_full_size_properties():
     """BASELINE config 3 size ([4096,512,10,10]): size-independent checks only.
     (i) a constant map gives the constant for fully-inside boxes; (ii) linearity in the map;

@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 from conftest import assert_close, load_golden
-from oracle import cost_ref, kalman_ref, lsap_ref, native, tracker_ref
+from oracle import cost_ref, kalman_ref, lsap_ref, native, roi_wrappers_ref, tracker_ref
 
 
 def test_roi_oracle_vs_golden():
@@ -13,6 +13,20 @@ def test_roi_oracle_vs_golden():
         ph, pw, sr, al = (int(v) for v in g["arg_" + tag])
         got = native.roi_align(g["feat"], g["rois"], (ph, pw), 20 / 640.0, sr, bool(al))
         assert_close(got, g["out_" + tag], what="roi " + tag)
+
+
+def test_roi_wrapper_oracle_vs_golden():
+    """tracking.py:193-221 and trainingCard.py:24-79 restated, against fixtures recorded from the reference's own
+    methods (make_golden.py::run_roi_wrapper_cases)."""
+    g = load_golden("roi_wrappers")
+    for tag in ("sq", "wide"):
+        feat, boxes, hw = g[tag + "_feat"], g[tag + "_boxes"], tuple(int(v) for v in g[tag + "_hw"])
+        for ps in (7, 10):
+            got = roi_wrappers_ref.roi_align_from_input_boxes(feat, boxes.tolist(), hw, out_size=(ps, ps))
+            assert_close(got, g["%s_r1_%d" % (tag, ps)], what="%s r1 %d" % (tag, ps))
+        assert_close(roi_wrappers_ref.preprocess_roi(feat, boxes, hw), g[tag + "_r2_10"], what=tag + " r2")
+        assert_close(roi_wrappers_ref.preprocess_roi(feat, boxes, hw, output_size=(7, 7), enforce_min_size=0.0),
+                     g[tag + "_r2_7_nomin"], what=tag + " r2 nomin")
 
 
 def test_roi_oracle_vs_installed_torchvision():
