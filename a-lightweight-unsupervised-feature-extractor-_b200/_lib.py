@@ -8,7 +8,8 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200track.so")
+# B200TRACK_LIB: load another build of the same library (kernel experiments, tools/build_variants.sh); unset = the product
+LIB_PATH = os.environ.get("B200TRACK_LIB") or os.path.join(_HERE, "libb200track.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 OK, EINVAL, ECUDA, ECAPACITY, ENUMERIC, EINFEASIBLE = 0, -1, -2, -3, -4, -5
@@ -61,6 +62,11 @@ SIGNATURES = {
     "b200_tracker_live_counts": (_I, [_P, _P, _P, _P]),
     "b200_tracker_step": (_I, [_P, _P, _P, _P, _P, _P, _P, _P]),
     "b200_tracker_step_host": (_I, [_P, _P, _P, _P, _P, _P, _P, _P]),
+    "b200_tracker_predict_all": (_I, [_P, _I, _P]),
+    "b200_tracker_mark_missed": (_I, [_P, _I, _P, _I, _P]),
+    "b200_tracker_purge_dead": (_I, [_P, _I, _P]),
+    "b200_tracker_create_tracks": (_I, [_P, _I, _P, _I, _P, _P, _P, _I, _I, _P]),
+    "b200_tracker_update_matched": (_I, [_P, _I, _P, _P, _P, _I, _P, _P, _P, _I, _I, _D, _D, _D, _D, _P]),
     "b200_tracker_export": (_I, [_P, _I] + [_P] * 14),
     "b200_tracker_import": (_I, [_P, _I, _I] + [_P] * 12 + [_I, _P]),
 }

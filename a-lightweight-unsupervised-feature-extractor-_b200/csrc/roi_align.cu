@@ -825,13 +825,16 @@ constexpr int kTmaRows = 5;
 constexpr int kTmaBoxBytes = 16 * kTmaRows * 32;          // one box: 16 B x kTmaRows rows x 32 channels
 constexpr int kTmaVBytes = 4 * kTmaBoxBytes;              // one 2 x 2-box tile, or two smaller tiles in flight
 #ifndef B200_ROI_TMA_WARPS
-#define B200_ROI_TMA_WARPS 3
+#define B200_ROI_TMA_WARPS 2
 #endif
 #ifndef B200_ROI_TMA_CTAS
 #define B200_ROI_TMA_CTAS 3
 #endif
 #ifndef B200_ROI_TMA_TILES
-#define B200_ROI_TMA_TILES 8
+#define B200_ROI_TMA_TILES 16
+#endif
+#ifndef B200_ROI_TMA_REGS
+#define B200_ROI_TMA_REGS 216
 #endif
 constexpr int kTmaWarps = B200_ROI_TMA_WARPS;
 
@@ -879,87 +882,114 @@ __device__ __forceinline__ int tma_tile_boxes(const int4 h0, const int4 h1) {
     return (FY > kTmaRows ? 2 : 1) * (FX > BX ? 2 : 1);
 }
 
-// One lane requests everything tile (k, c0) needs: the weight tables of ROI k and the footprint boxes.
+__device__ __forceinline__ bool elect_one() {
+    unsigned p;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(p)::"memory");
+    return p != 0;
+}
+__device__ __forceinline__ int bcast0(int v) { return __shfl_sync(0xffffffffu, v, 0); }
+
+// One elected lane requests everything tile (k, c0) needs: the weight tables of ROI k and the footprint boxes.  Called by
+// the whole (converged) warp; the operands are broadcast from lane 0 first so that they are provably warp-uniform and
+// go to the TMA instructions through uniform registers directly (with per-lane values ptxas wraps every UTMALDG /
+// UBLKCP in an ELECT / R2UR.BROADCAST loop, which showed up as 11 % of all stall samples).
 template <int PH, int PW, typename T>
-__device__ __forceinline__ void tma_issue(const CUtensorMap* tm, const int4 h0, const int4 h1, long long k, int c0,
+__device__ __forceinline__ void tma_issue(const CUtensorMap* tm, const int4 h0, const int4 h1, unsigned k, int c0,
                                           const float* __restrict__ prep_tabs, unsigned sv, unsigned stab, unsigned bar) {
     using S = TmaSmem<PH, PW>;
     constexpr int BX = 16 / (int)sizeof(T);
-    const int b = h0.x, ymin = h0.y, xmin = h0.z, FY = h0.w, FX = h1.x;
-    const int nb = tma_tile_boxes<T>(h0, h1);
+    const int b = bcast0(h0.x), ymin = bcast0(h0.y), xmin = bcast0(h0.z), FY = bcast0(h0.w), FX = bcast0(h1.x);
+    const unsigned ku = (unsigned)bcast0((int)k);
+    const int cu = bcast0(c0);
+    const unsigned svu = (unsigned)bcast0((int)sv), stabu = (unsigned)bcast0((int)stab), baru = (unsigned)bcast0((int)bar);
     const int nrb = FY > kTmaRows ? 2 : 1;
-    mbar_expect_tx(bar, (unsigned)(S::kTabBytes + nb * kTmaBoxBytes));
-    bulk_load(stab, prep_tabs + (size_t)k * S::L::kTabFloats, S::kTabBytes, bar);
-    if (nb) {
-        tma_box_4d(sv, tm, xmin, ymin, c0, b, bar);
-        if (nrb == 2) tma_box_4d(sv + kTmaBoxBytes, tm, xmin, ymin + kTmaRows, c0, b, bar);
-        if (FX > BX) {
-            tma_box_4d(sv + nrb * kTmaBoxBytes, tm, xmin + BX, ymin, c0, b, bar);
-            if (nrb == 2) tma_box_4d(sv + 3 * kTmaBoxBytes, tm, xmin + BX, ymin + kTmaRows, c0, b, bar);
+    const int nb = (FY == 0 || FX == 0) ? 0 : nrb * (FX > BX ? 2 : 1);
+    if (elect_one()) {
+#ifdef B200_ROI_TMA_NOLOAD                       // timing experiment only (results are wrong): no footprint traffic
+        mbar_expect_tx(baru, (unsigned)S::kTabBytes);
+        bulk_load(stabu, prep_tabs + (size_t)ku * S::L::kTabFloats, S::kTabBytes, baru);
+        if (false) {
+#else
+        mbar_expect_tx(baru, (unsigned)(S::kTabBytes + nb * kTmaBoxBytes));
+        bulk_load(stabu, prep_tabs + (size_t)ku * S::L::kTabFloats, S::kTabBytes, baru);
+        if (nb) {
+#endif
+            tma_box_4d(svu, tm, xmin, ymin, cu, b, baru);
+            if (nrb == 2) tma_box_4d(svu + kTmaBoxBytes, tm, xmin, ymin + kTmaRows, cu, b, baru);
+            if (FX > BX) {
+                tma_box_4d(svu + nrb * kTmaBoxBytes, tm, xmin + BX, ymin, cu, b, baru);
+                if (nrb == 2) tma_box_4d(svu + 3 * kTmaBoxBytes, tm, xmin + BX, ymin + kTmaRows, cu, b, baru);
+            }
         }
     }
+    __syncwarp();
 }
 
-// Row-outer separable contraction over V[channel][row][x] as the TMA boxes lay it out (see above).
+// Separable contraction over V[channel][row][x] as the TMA boxes lay it out (see above).  Per box (kTmaRows rows x four
+// columns of this lane's channel) the rows are read once as 128-bit values into registers (rows beyond the footprint
+// as zeros, never as map data); then, column-outer like separable_accumulate: for every column that carries weight
+// (one uniform test per column and box, not per row), ty[ph] = sum_r Wy[r][ph] * V[r][x] and
+// acc[ph][pw] += Wx[x][pw] * ty[ph].
 template <int PH, int PW, typename T>
 __device__ __forceinline__ void tma_accumulate(float (&acc)[PH][PW], const unsigned char* sV, const float* sWy,
                                                const float* sWx, int FY, int FX, int xmask, int lane) {
-    constexpr int PHP = (PH + 3) & ~3, PWP = (PW + 3) & ~3, BX = 16 / (int)sizeof(T);
-    const int nrb = FY > kTmaRows ? 2 : 1;
+    static_assert(sizeof(T) == 4, "float32 maps only");
+    constexpr int PHP = (PH + 3) & ~3, PWP = (PW + 3) & ~3;
+    const int nrb = FY > kTmaRows ? 2 : 1, ncb = FX > 4 ? 2 : 1;
     const unsigned char* mine = sV + lane * (kTmaRows * 16);
-    for (int r = 0; r < FY; ++r) {
-        const int rb = r >= kTmaRows ? 1 : 0;
-        const unsigned char* row = mine + rb * kTmaBoxBytes + (r - rb * kTmaRows) * 16;
-        float v[8];
-        if (sizeof(T) == 4) {
-            const float4 a = *reinterpret_cast<const float4*>(row);
-            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
-            if (FX > BX) {
-                const float4 c = *reinterpret_cast<const float4*>(row + nrb * kTmaBoxBytes);
-                v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
-            } else {
-                v[4] = v[5] = v[6] = v[7] = 0.0f;
+    for (int cb = 0; cb < ncb; ++cb) {
+        for (int rb = 0; rb < nrb; ++rb) {
+            const unsigned char* box = mine + (cb * nrb + rb) * kTmaBoxBytes;
+            const int rows = FY - rb * kTmaRows;                      // rows of the footprint in this box (may exceed kTmaRows)
+            float v[kTmaRows][4];
+#pragma unroll
+            for (int i = 0; i < kTmaRows; ++i) {
+                float4 q = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                if (i < rows) q = *reinterpret_cast<const float4*>(box + i * 16);
+                v[i][0] = q.x; v[i][1] = q.y; v[i][2] = q.z; v[i][3] = q.w;
             }
-        } else {
-            const uint4 a = *reinterpret_cast<const uint4*>(row);
-            const __half2* h = reinterpret_cast<const __half2*>(&a);
+            const float* wy0 = sWy + rb * kTmaRows * PHP;
+            const int bits = (xmask >> (4 * cb)) & 15;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) { const float2 f = __half22float2(h[q]); v[2 * q] = f.x; v[2 * q + 1] = f.y; }
-        }
-        float tx[PW];
+            for (int xi = 0; xi < 4; ++xi) {
+                if ((bits >> xi) & 1) {                               // uniform
+                    float ty[PH];
 #pragma unroll
-        for (int bq = 0; bq < PW; ++bq) tx[bq] = 0.0f;
+                    for (int a = 0; a < PH; ++a) ty[a] = 0.0f;
 #pragma unroll
-        for (int x = 0; x < 8; ++x) {
-            if ((xmask >> x) & 1) {                                   // uniform: cells outside the footprint are never touched
-                const float4* w4 = reinterpret_cast<const float4*>(sWx + x * PWP);
+                    for (int i = 0; i < kTmaRows; ++i) {
+                        // rows past the table (only possible in the second row box) have no weights: their data is zero
+                        const int r = (rb * kTmaRows + i < kFootCap) ? i : 0;
+                        const float4* w4 = reinterpret_cast<const float4*>(wy0 + r * PHP);
 #pragma unroll
-                for (int q = 0; q < PWP / 4; ++q) {
-                    const float4 w = w4[q];
-                    if (4 * q + 0 < PW) tx[4 * q + 0] = fmaf(w.x, v[x], tx[4 * q + 0]);
-                    if (4 * q + 1 < PW) tx[4 * q + 1] = fmaf(w.y, v[x], tx[4 * q + 1]);
-                    if (4 * q + 2 < PW) tx[4 * q + 2] = fmaf(w.z, v[x], tx[4 * q + 2]);
-                    if (4 * q + 3 < PW) tx[4 * q + 3] = fmaf(w.w, v[x], tx[4 * q + 3]);
+                        for (int q = 0; q < PHP / 4; ++q) {
+                            const float4 w = w4[q];
+                            if (4 * q + 0 < PH) ty[4 * q + 0] = fmaf(w.x, v[i][xi], ty[4 * q + 0]);
+                            if (4 * q + 1 < PH) ty[4 * q + 1] = fmaf(w.y, v[i][xi], ty[4 * q + 1]);
+                            if (4 * q + 2 < PH) ty[4 * q + 2] = fmaf(w.z, v[i][xi], ty[4 * q + 2]);
+                            if (4 * q + 3 < PH) ty[4 * q + 3] = fmaf(w.w, v[i][xi], ty[4 * q + 3]);
+                        }
+                    }
+                    const float4* w4 = reinterpret_cast<const float4*>(sWx + (4 * cb + xi) * PWP);
+#pragma unroll
+                    for (int q = 0; q < PWP / 4; ++q) {
+                        const float4 w = w4[q];
+                        const float wv[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            if (4 * q + e < PW) {
+#pragma unroll
+                                for (int a2 = 0; a2 < PH; ++a2) acc[a2][4 * q + e] = fmaf(wv[e], ty[a2], acc[a2][4 * q + e]);
+                            }
+                    }
                 }
             }
-        }
-        const float4* w4 = reinterpret_cast<const float4*>(sWy + r * PHP);
-#pragma unroll
-        for (int q = 0; q < PHP / 4; ++q) {
-            const float4 w = w4[q];
-            const float wv[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-                if (4 * q + e < PH) {
-#pragma unroll
-                    for (int bq = 0; bq < PW; ++bq) acc[4 * q + e][bq] = fmaf(wv[e], tx[bq], acc[4 * q + e][bq]);
-                }
         }
     }
 }
 
 template <int PH, int PW, typename T, bool OCL>
-__global__ void __launch_bounds__(kTmaWarps * 32, B200_ROI_TMA_CTAS)
+__global__ void __maxnreg__(B200_ROI_TMA_REGS)
 roi_align_tma_kernel(const __grid_constant__ CUtensorMap tmap, const T* __restrict__ feat, int B, int C, int H, int W,
                      const float* __restrict__ rois, long long K, float scale, int sr, int aligned, T* __restrict__ out,
                      int ctiles, const RoiPrep* __restrict__ prep, const float* __restrict__ prep_tabs, int group_warps,
@@ -968,7 +998,7 @@ roi_align_tma_kernel(const __grid_constant__ CUtensorMap tmap, const T* __restri
     using S = TmaSmem<PH, PW>;
     constexpr int PHP = L::kPHP, NB = PH * PW;
     extern __shared__ __align__(128) unsigned char smem_tma[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform
     unsigned char* base = smem_tma + (size_t)warp * S::kBytesPerWarp;
     const unsigned sbase = (unsigned)__cvta_generic_to_shared(base);
     const unsigned sbar = sbase + S::kOffBar;
@@ -984,7 +1014,6 @@ roi_align_tma_kernel(const __grid_constant__ CUtensorMap tmap, const T* __restri
         mbar_init(sbar, 1);
         mbar_init(sbar + 8, 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-        asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tmap) : "memory");
     }
     __syncwarp();
 
@@ -1008,9 +1037,8 @@ roi_align_tma_kernel(const __grid_constant__ CUtensorMap tmap, const T* __restri
     // V offset of a tile with `nb` boxes in slot p: slot 0 grows up from the start, slot 1 down from the end
     auto v_off = [&](int p, int nb) { return p ? (unsigned)(kTmaVBytes - nb * kTmaBoxBytes) : 0u; };
     if (a1.y) {
-        if (lane == 0)
-            tma_issue<PH, PW, T>(&tmap, a0, a1, ka, ca, prep_tabs, sbase + v_off(0, tma_tile_boxes<T>(a0, a1)),
-                                 sbase + S::kOffTab, sbar);
+        tma_issue<PH, PW, T>(&tmap, a0, a1, ka, ca, prep_tabs, sbase + v_off(0, tma_tile_boxes<T>(a0, a1)),
+                             sbase + S::kOffTab, sbar);
         cur_issued = true;
     }
     for (;;) {
@@ -1021,9 +1049,8 @@ roi_align_tma_kernel(const __grid_constant__ CUtensorMap tmap, const T* __restri
         // the next tile's footprint is requested now if it fits beside the current one, else once that is consumed
         bool next_issued = false;
         if (have_next && n1.y && (nba + nbn) * kTmaBoxBytes <= kTmaVBytes) {
-            if (lane == 0)
-                tma_issue<PH, PW, T>(&tmap, n0, n1, kn, cnx, prep_tabs, sbase + v_off(par ^ 1, nbn),
-                                     sbase + S::kOffTab + (par ^ 1) * S::kTabBytes, sbar + 8 * (par ^ 1));
+            tma_issue<PH, PW, T>(&tmap, n0, n1, kn, cnx, prep_tabs, sbase + v_off(par ^ 1, nbn),
+                                 sbase + S::kOffTab + (par ^ 1) * S::kTabBytes, sbar + 8 * (par ^ 1));
             next_issued = true;
         }
         // record of the tile after next: requested after the accumulation (register pressure), see roi_align_pipe_kernel
@@ -1041,9 +1068,8 @@ roi_align_tma_kernel(const __grid_constant__ CUtensorMap tmap, const T* __restri
         };
         if (a1.y) {
             if (!cur_issued) {         // only when the previous iteration could not fit it beside its own tile
-                if (lane == 0)
-                    tma_issue<PH, PW, T>(&tmap, a0, a1, ka, ca, prep_tabs, sbase + v_off(par, nba),
-                                         sbase + S::kOffTab + par * S::kTabBytes, sbar + 8 * par);
+                tma_issue<PH, PW, T>(&tmap, a0, a1, ka, ca, prep_tabs, sbase + v_off(par, nba),
+                                     sbase + S::kOffTab + par * S::kTabBytes, sbar + 8 * par);
             }
             mbar_wait(sbar + 8 * par, (phase >> par) & 1u);
             phase ^= 1u << par;
@@ -1058,9 +1084,8 @@ roi_align_tma_kernel(const __grid_constant__ CUtensorMap tmap, const T* __restri
             load_after_next();
             __syncwarp();              // V and the tables of this slot are dead
             if (have_next && n1.y && !next_issued && nbn * kTmaBoxBytes <= kTmaVBytes) {
-                if (lane == 0)
-                    tma_issue<PH, PW, T>(&tmap, n0, n1, kn, cnx, prep_tabs, sbase + v_off(par ^ 1, nbn),
-                                         sbase + S::kOffTab + (par ^ 1) * S::kTabBytes, sbar + 8 * (par ^ 1));
+                tma_issue<PH, PW, T>(&tmap, n0, n1, kn, cnx, prep_tabs, sbase + v_off(par ^ 1, nbn),
+                                     sbase + S::kOffTab + (par ^ 1) * S::kTabBytes, sbar + 8 * (par ^ 1));
                 next_issued = true;
             }
             if (OCL) {                 // channels-last result: full-line stores straight from the accumulators
@@ -1122,9 +1147,8 @@ roi_align_tma_kernel(const __grid_constant__ CUtensorMap tmap, const T* __restri
             load_after_next();
             __syncwarp();
             if (have_next && n1.y && !next_issued && nbn * kTmaBoxBytes <= kTmaVBytes) {
-                if (lane == 0)
-                    tma_issue<PH, PW, T>(&tmap, n0, n1, kn, cnx, prep_tabs, sbase + v_off(par ^ 1, nbn),
-                                         sbase + S::kOffTab + (par ^ 1) * S::kTabBytes, sbar + 8 * (par ^ 1));
+                tma_issue<PH, PW, T>(&tmap, n0, n1, kn, cnx, prep_tabs, sbase + v_off(par ^ 1, nbn),
+                                     sbase + S::kOffTab + (par ^ 1) * S::kTabBytes, sbar + 8 * (par ^ 1));
                 next_issued = true;
             }
         }

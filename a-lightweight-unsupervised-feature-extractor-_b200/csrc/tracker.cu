@@ -161,6 +161,47 @@ __device__ inline void enqueue_cost_work(int2* work, int* counter, int s, int M,
     for (int i = threadIdx.x; i < total; i += blockDim.x) work[base + i] = make_int2(s, (i / tiles) * 64 + i % tiles);
 }
 
+// ---- detections: unit embeddings (:167-168), z (KalmanFilter.py:5-16), float32 boxes/confs (all threads of a CTA) ----
+__device__ inline void prep_detections(const Dev& d, int s, int n) {
+    const size_t db = (size_t)s * d.MD;
+    const int tid = threadIdx.x;
+    for (int j = tid >> 5; j < n; j += blockDim.x >> 5) {
+        const float4 v = reinterpret_cast<const float4*>(d.embs + (db + j) * cost::kD)[tid & 31];
+        reinterpret_cast<float4*>(d.det_unit + (db + j) * cost::kD)[tid & 31] = cost::unit_row(v);
+    }
+    for (int j = tid; j < n; j += blockDim.x) {
+        double b[4];
+        float z[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { b[k] = d.boxes[(db + j) * 4 + k]; d.det_boxf[(db + j) * 4 + k] = (float)b[k]; }
+        kf::box_to_z(b, z);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) d.det_z[(db + j) * 4 + k] = z[k];
+        d.det_conff[db + j] = (float)d.confs[db + j];
+        d.det_used[db + j] = 0;
+    }
+}
+
+// predict_all (:340-345) for one track + the per-track inputs of the stage-1 cost (by slot): predicted box and
+// confidence as float32, inverse innovation covariance for the gate.
+__device__ inline void predict_slot(const Dev& d, size_t slot) {
+    const float q[8] = {1.f, 1.f, 1.f, 1.f, 100.f, 100.f, 100.f, 100.f};    // KalmanFilter.py:91-95
+    const float rdiag[4] = {1.f, 1.f, 1.f, 1.f};                           // KalmanFilter.py:98-99
+    double x[8], P[64], b[4];
+    load_kf(d, slot, x, P);
+    const int st = d.kf_stage[slot];
+    kf::predict(x, P, st, q);
+    store_kf(d, slot, x, P);
+    kf::x_to_box(x, b);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { d.last_bbox[slot * 4 + k] = b[k]; d.prev_boxf[slot * 4 + k] = (float)b[k]; }
+    d.prev_conff[slot] = (float)d.last_conf[slot];
+    kf::Gate g;
+    kf::gate_prepare(x, P, st, rdiag, &g);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) d.gate_SI[slot * 16 + k] = g.SI[k];
+}
+
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) begin_kernel(Dev d) {
     Span span((d.frame_id[0] & 7) * 6 + 0);
@@ -174,22 +215,7 @@ __global__ void __launch_bounds__(kThreads) begin_kernel(Dev d) {
     int* order = d.order + sb;
     if (blockIdx.y == 1) {                         // second CTA of the stream: detection prep only
         if (n <= 0) return;
-    // ---- detections: unit embeddings (:167-168), z (KalmanFilter.py:5-16), float32 boxes/confs ----
-        for (int j = tid >> 5; j < n; j += blockDim.x >> 5) {
-            const float4 v = reinterpret_cast<const float4*>(d.embs + (db + j) * cost::kD)[tid & 31];
-            reinterpret_cast<float4*>(d.det_unit + (db + j) * cost::kD)[tid & 31] = cost::unit_row(v);
-        }
-        for (int j = tid; j < n; j += blockDim.x) {
-            double b[4];
-            float z[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) { b[k] = d.boxes[(db + j) * 4 + k]; d.det_boxf[(db + j) * 4 + k] = (float)b[k]; }
-            kf::box_to_z(b, z);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) d.det_z[(db + j) * 4 + k] = z[k];
-            d.det_conff[db + j] = (float)d.confs[db + j];
-            d.det_used[db + j] = 0;
-        }
+        prep_detections(d, s, n);
         return;
     }
     if (s == 0 && tid == 0) d.wcount[2] = 0;       // last step's update_kernel is done; nothing queued yet
@@ -221,24 +247,7 @@ __global__ void __launch_bounds__(kThreads) begin_kernel(Dev d) {
     }
     // ---- predict_all (:340-345) + per-track inputs of the stage-1 cost (by slot): predicted box and
     // confidence as float32, inverse innovation covariance for the gate -------------------------------
-    const float q[8] = {1.f, 1.f, 1.f, 1.f, 100.f, 100.f, 100.f, 100.f};    // KalmanFilter.py:91-95
-    const float rdiag[4] = {1.f, 1.f, 1.f, 1.f};                           // KalmanFilter.py:98-99
-    for (int p = tid; p < nl; p += blockDim.x) {
-        const size_t slot = sb + order[p];
-        double x[8], P[64], b[4];
-        load_kf(d, slot, x, P);
-        const int st = d.kf_stage[slot];
-        kf::predict(x, P, st, q);
-        store_kf(d, slot, x, P);
-        kf::x_to_box(x, b);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { d.last_bbox[slot * 4 + k] = b[k]; d.prev_boxf[slot * 4 + k] = (float)b[k]; }
-        d.prev_conff[slot] = (float)d.last_conf[slot];
-        kf::Gate g;
-        kf::gate_prepare(x, P, st, rdiag, &g);
-#pragma unroll
-        for (int k = 0; k < 16; ++k) d.gate_SI[slot * 16 + k] = g.SI[k];
-    }
+    for (int p = tid; p < nl; p += blockDim.x) predict_slot(d, sb + order[p]);
     // ---- rows_main / rows_reid in ascending track-id order (:478-487) -----------------------------
     int* rm = d.rows_main + sb;
     int* rr = d.rows_reid + sb;
@@ -660,6 +669,58 @@ __global__ void __launch_bounds__(kUpdWarps * 32) update_kernel(Dev d) {
     }
 }
 
+// create_new_tracks (:362-373) for the detections listed in born[0..want) (already filtered by init_conf_min, in
+// order): free slots, Kalman initial state, creat_item (:98-139), ids next_id, next_id + 1, ...  All threads of the
+// CTA must call; returns the number of tracks created (fewer than `want` only when the handle is full, which is
+// reported as B200_ECAPACITY in the stream's status).
+__device__ inline int spawn_tracks(const Dev& d, int s, const int* born, int want) {
+    const int tid = threadIdx.x;
+    int* hdr = d.hdr + s * kHdr;
+    int* cnt = d.cnt + s * kHdr;
+    const size_t sb = (size_t)s * d.MT, db = (size_t)s * d.MD;
+    const int nl = hdr[H_NLIVE], nfree = hdr[H_NFREE], next_id = hdr[H_NEXT];
+    int* order = d.order + sb;
+    const int* fl = d.free_list + sb;
+    const int nb = min(want, nfree);
+    const int frame = d.frame_id[s];
+    __syncthreads();
+    for (int b = tid; b < nb; b += blockDim.x) {
+        const int j = born[b], sl = fl[nfree - 1 - b];
+        const size_t slot = sb + sl;
+        double x[8], P[64], box[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { box[k] = d.boxes[(db + j) * 4 + k]; d.last_bbox[slot * 4 + k] = box[k]; }
+        kf::init_state(box, x, P);
+        store_kf(d, slot, x, P);
+        d.kf_stage[slot] = 0;
+        d.last_conf[slot] = d.confs[db + j];
+        d.last_cost[slot] = __longlong_as_double(0x7ff8000000000000LL);      // None
+        d.last_frame[slot] = frame;
+        d.tid[slot] = next_id + b;
+        d.miss[slot] = 0;
+        d.age[slot] = 1;
+        d.bank_len[slot] = 1;
+        d.bank_head[slot] = 0;
+        order[nl + b] = sl;
+    }
+    for (int i = tid; i < nb * (cost::kD / 4); i += blockDim.x) {              // creat_item :98-139
+        const int b = i / (cost::kD / 4), k = i % (cost::kD / 4);
+        const size_t slot = sb + fl[nfree - 1 - b];
+        const float4 e = reinterpret_cast<const float4*>(d.det_unit + (db + born[b]) * cost::kD)[k];
+        reinterpret_cast<float4*>(d.ema + slot * cost::kD)[k] = e;
+        reinterpret_cast<float4*>(d.bank + slot * d.HIST * cost::kD)[k] = e;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        hdr[H_NLIVE] = nl + nb;
+        hdr[H_NFREE] = nfree - nb;
+        hdr[H_NEXT] = next_id + nb;
+        if (want > nb && cnt[C_STATUS] == 0) cnt[C_STATUS] = B200_ECAPACITY;
+    }
+    __syncthreads();
+    return nb;
+}
+
 // hungarian_assign (hung.py:5-45) for this stream's matrix; fills m_row/m_det, marks misses.
 // Returns the number of matches; *n_unmatched_rows is the count appended to the unmatched list.
 template <int STAGE>
@@ -779,48 +840,11 @@ __global__ void __launch_bounds__(kThreads) assign_kernel(Dev d, int smem_matrix
     int* out_ud = res_ud(d, res);
     n_left = block_compact(N, [&](int jl) { return d.det_used[db + d.ud1[db + jl]] == 0; },
                            [&](int pos, int jl) { out_ud[pos] = d.ud1[db + jl]; }, scratch);
-    const int nl = hdr[H_NLIVE], nfree = hdr[H_NFREE], next_id = hdr[H_NEXT];
-    int* order = d.order + sb;
-    const int* fl = d.free_list + sb;
     int* born = d.born + db;                        // det index of each birth, in order
     const int want = block_compact(n_left, [&](int k) { return !(d.confs[db + out_ud[k]] < d.init_conf_min); },
                                    [&](int pos, int k) { born[pos] = out_ud[k]; }, scratch);
-    const int nb = min(want, nfree);
-    const int frame = d.frame_id[s];
-    for (int b = tid; b < nb; b += blockDim.x) {
-        const int j = born[b], sl = fl[nfree - 1 - b];
-        const size_t slot = sb + sl;
-        double x[8], P[64], box[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { box[k] = d.boxes[(db + j) * 4 + k]; d.last_bbox[slot * 4 + k] = box[k]; }
-        kf::init_state(box, x, P);
-        store_kf(d, slot, x, P);
-        d.kf_stage[slot] = 0;
-        d.last_conf[slot] = d.confs[db + j];
-        d.last_cost[slot] = __longlong_as_double(0x7ff8000000000000LL);      // None
-        d.last_frame[slot] = frame;
-        d.tid[slot] = next_id + b;
-        d.miss[slot] = 0;
-        d.age[slot] = 1;
-        d.bank_len[slot] = 1;
-        d.bank_head[slot] = 0;
-        order[nl + b] = sl;
-    }
-    for (int i = tid; i < nb * (cost::kD / 4); i += blockDim.x) {              // creat_item :98-139
-        const int b = i / (cost::kD / 4), k = i % (cost::kD / 4);
-        const size_t slot = sb + fl[nfree - 1 - b];
-        const float4 e = reinterpret_cast<const float4*>(d.det_unit + (db + born[b]) * cost::kD)[k];
-        reinterpret_cast<float4*>(d.ema + slot * cost::kD)[k] = e;
-        reinterpret_cast<float4*>(d.bank + slot * d.HIST * cost::kD)[k] = e;
-    }
-    __syncthreads();
-    if (tid == 0) {
-        hdr[H_NLIVE] = nl + nb;
-        hdr[H_NFREE] = nfree - nb;
-        hdr[H_NEXT] = next_id + nb;
-        if (want > nb && cnt[C_STATUS] == 0) cnt[C_STATUS] = B200_ECAPACITY;
-    }
-    __syncthreads();
+    const int nl = hdr[H_NLIVE];
+    const int nb = spawn_tracks(d, s, born, want);
     purge(d, s, nl + nb, scratch);
     if (tid == 0) {
         res[R_NMATCH] = match0 + n_match;
@@ -832,6 +856,91 @@ __global__ void __launch_bounds__(kThreads) assign_kernel(Dev d, int smem_matrix
         res[R_M1] = cnt[C_M1];
         res[R_M2] = cnt[C_M2];
     }
+}
+
+// ---- the pieces of Tracking.update as separate operations on one stream of a handle (mainTracking.py:340-448) ----
+// One CTA each; they exist so that a caller that drives the association step by step, like the reference's own
+// methods allow, finds the same methods on the device state.  The fused step (b200_tracker_step) does not use them.
+__device__ inline int find_slot(const Dev& d, int s, int nl, int track_id) {       // live slot of a track id, -1 if none
+    const size_t sb = (size_t)s * d.MT;
+    int lo = 0, hi = nl - 1;                                                         // `order` is ascending in track id
+    while (lo <= hi) {
+        const int mid = (lo + hi) >> 1, sl = d.order[sb + mid], t = d.tid[sb + sl];
+        if (t == track_id) return sl;
+        if (t < track_id) lo = mid + 1; else hi = mid - 1;
+    }
+    return -1;
+}
+
+__global__ void __launch_bounds__(kThreads) op_predict_kernel(Dev d, int s) {        // predict_all :340-345
+    const size_t sb = (size_t)s * d.MT;
+    const int nl = d.hdr[s * kHdr + H_NLIVE];
+    for (int p = threadIdx.x; p < nl; p += blockDim.x) predict_slot(d, sb + d.order[sb + p]);
+}
+
+__global__ void __launch_bounds__(kThreads) op_mark_missed_kernel(Dev d, int s, const int* tids, int n) {   // :347-355
+    const size_t sb = (size_t)s * d.MT;
+    const int nl = d.hdr[s * kHdr + H_NLIVE];
+    if (threadIdx.x == 0)                       // serial: the reference increments once per list entry, duplicates included
+        for (int i = 0; i < n; ++i) {
+            const int sl = find_slot(d, s, nl, tids[i]);
+            if (sl >= 0) d.miss[sb + sl] += 1;   // unknown ids are skipped (:350-351)
+        }
+}
+
+__global__ void __launch_bounds__(kThreads) op_purge_kernel(Dev d, int s) {          // purge_dead :357-360
+    __shared__ int scratch[kThreads / 32];
+    purge(d, s, d.hdr[s * kHdr + H_NLIVE], scratch);
+}
+
+// create_new_tracks (:362-373): det_ids in the caller's order, filtered by init_conf_min; d.boxes / confs / embs hold the
+// frame's detections of stream s.  out[0] = tracks created, out[1] = status.
+__global__ void __launch_bounds__(kThreads) op_create_kernel(Dev d, int s, const int* det_ids, int n_ids, int n_det, int* out) {
+    __shared__ int scratch[kThreads / 32];
+    const size_t db = (size_t)s * d.MD;
+    if (threadIdx.x == 0) d.cnt[s * kHdr + C_STATUS] = 0;
+    prep_detections(d, s, n_det);
+    __syncthreads();
+    int* born = d.born + db;
+    const int want = block_compact(n_ids, [&](int k) { return !(d.confs[db + det_ids[k]] < d.init_conf_min); },
+                                   [&](int pos, int k) { born[pos] = det_ids[k]; }, scratch);
+    const int nb = spawn_tracks(d, s, born, want);
+    if (threadIdx.x == 0) { out[0] = nb; out[1] = d.cnt[s * kHdr + C_STATUS]; }
+}
+
+// update_matched (:375-448), bookkeeping half: (track id, detection, cost) triples -> the update queue of update_kernel.
+// out[1] = B200_EINVAL if a track id is not live (the reference raises KeyError at :390).
+__global__ void __launch_bounds__(kThreads) op_queue_matches_kernel(Dev d, int s, const int* tids, const int* dets,
+                                                                     const float* costs, int n, int n_det, int* out) {
+    const size_t sb = (size_t)s * d.MT, db = (size_t)s * d.MD;
+    const int nl = d.hdr[s * kHdr + H_NLIVE], frame = d.frame_id[s];
+    __shared__ int bad;
+    if (threadIdx.x == 0) bad = 0;
+    prep_detections(d, s, n_det);
+    __syncthreads();
+    for (int q = threadIdx.x; q < n; q += blockDim.x)
+        if (find_slot(d, s, nl, tids[q]) < 0 || dets[q] < 0 || dets[q] >= n_det) bad = 1;
+    __syncthreads();
+    if (bad) {
+        if (threadIdx.x == 0) { out[1] = B200_EINVAL; d.wcount[2] = 0; }
+        return;
+    }
+    for (int q = threadIdx.x; q < n; q += blockDim.x) {
+        const size_t slot = sb + find_slot(d, s, nl, tids[q]);
+        const int j = dets[q];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) d.last_bbox[slot * 4 + k] = d.boxes[(db + j) * 4 + k];
+        d.last_conf[slot] = d.confs[db + j];
+        d.last_frame[slot] = frame;
+        d.age[slot] += 1;
+        d.miss[slot] = 0;
+        d.last_cost[slot] = (double)costs[q];
+        d.upd_slot[q] = (int)slot;
+        d.upd_det[q] = (int)(db + j);
+        d.upd_cost[q] = costs[q];
+        d.upd_flag[q] = 0;
+    }
+    if (threadIdx.x == 0) { out[1] = 0; d.wcount[2] = n; }
 }
 
 // Packs one stream's live tracks, ascending track id, for b200_tracker_export.
@@ -1153,6 +1262,137 @@ extern "C" int b200_tracker_step_host(b200_tracker* t, const int32_t* n_det_host
     B200_CUDA(cudaMemcpyAsync(h_res, t->dev_result, t->res_bytes, cudaMemcpyDeviceToHost, st));
     B200_CUDA(cudaStreamSynchronize(st));
     memcpy(result_host, h_res, t->res_bytes);
+    return B200_OK;
+}
+
+// ---- step-by-step operations (host arrays in, synchronous) ----------------------------------------------------------
+namespace {
+
+// Uploads one stream's detections of a frame into the handle's input block (stream s's slices) and points a Dev copy at it.
+int stage_stream_inputs(b200_tracker* t, int s, int n_det, const double* boxes_host, const double* confs_host,
+                        const float* embs_host, int frame_id, cudaStream_t st, trk::Dev* d) {
+    *d = t->d;
+    B200_REQUIRE(n_det >= 0 && n_det <= d->MD, "tracker op: %d detections, capacity %d", n_det, d->MD);
+    const size_t MD = d->MD;
+    if (n_det > 0) {
+        B200_REQUIRE(boxes_host && confs_host && embs_host, "tracker op: null detection arrays");
+        B200_CUDA(cudaMemcpyAsync(t->in_boxes + (size_t)s * MD * 4, boxes_host, sizeof(double) * 4 * n_det, cudaMemcpyHostToDevice, st));
+        B200_CUDA(cudaMemcpyAsync(t->in_confs + (size_t)s * MD, confs_host, sizeof(double) * n_det, cudaMemcpyHostToDevice, st));
+        B200_CUDA(cudaMemcpyAsync(t->in_embs + (size_t)s * MD * 128, embs_host, sizeof(float) * 128 * n_det, cudaMemcpyHostToDevice, st));
+    }
+    B200_CUDA(cudaMemcpyAsync(t->in_frame + s, &frame_id, sizeof(int), cudaMemcpyHostToDevice, st));
+    d->n_det = t->in_ndet; d->boxes = t->in_boxes; d->confs = t->in_confs; d->embs = t->in_embs; d->frame_id = t->in_frame;
+    d->result = t->dev_result;
+    return B200_OK;
+}
+
+int upload_ints(const int32_t* host, int n, int** dev, cudaStream_t st) {
+    *dev = nullptr;
+    if (n <= 0) return B200_OK;
+    B200_CUDA(cudaMallocAsync(reinterpret_cast<void**>(dev), sizeof(int) * (size_t)n, st));
+    B200_CUDA(cudaMemcpyAsync(*dev, host, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, st));
+    return B200_OK;
+}
+
+}  // namespace
+
+#define B200_STREAM_ARG(fn)                                                                                  \
+    B200_REQUIRE(t, fn ": null handle");                                                                     \
+    B200_REQUIRE(stream_idx >= 0 && stream_idx < t->d.S, fn ": stream %d out of range", stream_idx);         \
+    cudaStream_t st = as_stream(stream)
+
+extern "C" int b200_tracker_predict_all(b200_tracker* t, int stream_idx, void* stream) {
+    B200_STREAM_ARG("tracker_predict_all");
+    trk::op_predict_kernel<<<1, trk::kThreads, 0, st>>>(t->d, stream_idx);
+    int rc = check_launch("trk op_predict_kernel");
+    if (rc) return rc;
+    B200_CUDA(cudaStreamSynchronize(st));
+    return B200_OK;
+}
+
+extern "C" int b200_tracker_mark_missed(b200_tracker* t, int stream_idx, const int32_t* track_ids_host, int n, void* stream) {
+    B200_STREAM_ARG("tracker_mark_missed");
+    B200_REQUIRE(n >= 0 && (n == 0 || track_ids_host), "tracker_mark_missed: bad id list");
+    if (n == 0) return B200_OK;
+    int* ids = nullptr;
+    int rc = upload_ints(track_ids_host, n, &ids, st);
+    if (rc) return rc;
+    trk::op_mark_missed_kernel<<<1, trk::kThreads, 0, st>>>(t->d, stream_idx, ids, n);
+    rc = check_launch("trk op_mark_missed_kernel");
+    cudaFreeAsync(ids, st);
+    if (rc) return rc;
+    B200_CUDA(cudaStreamSynchronize(st));
+    return B200_OK;
+}
+
+extern "C" int b200_tracker_purge_dead(b200_tracker* t, int stream_idx, void* stream) {
+    B200_STREAM_ARG("tracker_purge_dead");
+    trk::op_purge_kernel<<<1, trk::kThreads, 0, st>>>(t->d, stream_idx);
+    int rc = check_launch("trk op_purge_kernel");
+    if (rc) return rc;
+    B200_CUDA(cudaStreamSynchronize(st));
+    return B200_OK;
+}
+
+extern "C" int b200_tracker_create_tracks(b200_tracker* t, int stream_idx, const int32_t* det_ids_host, int n_ids,
+                                          const double* boxes_host, const double* confs_host, const float* embs_host,
+                                          int n_det, int frame_id, void* stream) {
+    B200_STREAM_ARG("tracker_create_tracks");
+    B200_REQUIRE(n_ids >= 0 && (n_ids == 0 || det_ids_host), "tracker_create_tracks: bad id list");
+    for (int i = 0; i < n_ids; ++i)
+        B200_REQUIRE(det_ids_host[i] >= 0 && det_ids_host[i] < n_det, "tracker_create_tracks: detection index %d out of range", det_ids_host[i]);
+    if (n_ids == 0) return 0;
+    B200_REQUIRE(n_ids <= t->d.MD, "tracker_create_tracks: %d ids, capacity %d", n_ids, t->d.MD);
+    trk::Dev d;
+    int rc = stage_stream_inputs(t, stream_idx, n_det, boxes_host, confs_host, embs_host, frame_id, st, &d);
+    if (rc) return rc;
+    int* ids = nullptr;
+    if ((rc = upload_ints(det_ids_host, n_ids + 2, &ids, st))) return rc;     // two extra ints: the kernel's output
+    trk::op_create_kernel<<<1, trk::kThreads, 0, st>>>(d, stream_idx, ids, n_ids, n_det, ids + n_ids);
+    rc = check_launch("trk op_create_kernel");
+    int out[2] = {0, 0};
+    if (rc == B200_OK && cudaMemcpyAsync(out, ids + n_ids, sizeof(out), cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = B200_ECUDA;
+    if (rc == B200_OK && cudaStreamSynchronize(st) != cudaSuccess) rc = B200_ECUDA;
+    cudaFreeAsync(ids, st);
+    if (rc) return rc == B200_ECUDA ? fail(B200_ECUDA, "tracker_create_tracks: %s", cudaGetErrorString(cudaGetLastError())) : rc;
+    if (out[1] == B200_ECAPACITY) return fail(B200_ECAPACITY, "tracker_create_tracks: the handle is full (max_tracks %d)", t->d.MT);
+    return out[0];
+}
+
+extern "C" int b200_tracker_update_matched(b200_tracker* t, int stream_idx, const int32_t* match_tid_host,
+                                           const int32_t* match_det_host, const float* match_cost_host, int n_matches,
+                                           const double* boxes_host, const double* confs_host, const float* embs_host,
+                                           int n_det, int frame_id, double ema_alpha, double conf_update_min,
+                                           double cost_update_max, double maha_thr, void* stream) {
+    B200_STREAM_ARG("tracker_update_matched");
+    B200_REQUIRE(n_matches >= 0 && n_matches <= t->d.MT, "tracker_update_matched: %d matches, capacity %d", n_matches, t->d.MT);
+    if (n_matches == 0) return B200_OK;
+    B200_REQUIRE(match_tid_host && match_det_host && match_cost_host, "tracker_update_matched: null match arrays");
+    trk::Dev d;
+    int rc = stage_stream_inputs(t, stream_idx, n_det, boxes_host, confs_host, embs_host, frame_id, st, &d);
+    if (rc) return rc;
+    d.ema_a = (float)ema_alpha;
+    d.ema_b = (float)(1.0 - ema_alpha);
+    d.conf_update_min = conf_update_min; d.cost_update_max = cost_update_max; d.maha_thr = maha_thr;
+    int* buf = nullptr;                              // tids | dets | costs | out[2]
+    const size_t n = (size_t)n_matches;
+    B200_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&buf), sizeof(int) * (3 * n + 2), st));
+    cudaMemcpyAsync(buf, match_tid_host, sizeof(int) * n, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(buf + n, match_det_host, sizeof(int) * n, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(buf + 2 * n, match_cost_host, sizeof(float) * n, cudaMemcpyHostToDevice, st);
+    trk::op_queue_matches_kernel<<<1, trk::kThreads, 0, st>>>(d, stream_idx, buf, buf + n, reinterpret_cast<const float*>(buf + 2 * n),
+                                                              n_matches, n_det, buf + 3 * n);
+    rc = check_launch("trk op_queue_matches_kernel");
+    if (rc == B200_OK) {
+        trk::update_kernel<<<t->upd_grid, trk::kUpdWarps * 32, 0, st>>>(d);
+        rc = check_launch("trk update_kernel");
+    }
+    int out[2] = {0, 0};
+    if (rc == B200_OK && cudaMemcpyAsync(out, buf + 3 * n, sizeof(out), cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = B200_ECUDA;
+    if (rc == B200_OK && cudaStreamSynchronize(st) != cudaSuccess) rc = B200_ECUDA;
+    cudaFreeAsync(buf, st);
+    if (rc) return rc == B200_ECUDA ? fail(B200_ECUDA, "tracker_update_matched: %s", cudaGetErrorString(cudaGetLastError())) : rc;
+    if (out[1]) return fail(B200_EINVAL, "tracker_update_matched: a match names a track id that is not live or a detection index out of range");
     return B200_OK;
 }
 

@@ -323,6 +323,78 @@ class Tracking:
         self._snap = None
         return self._ms.decode(res[0])
 
+    # -- the reference's methods one by one (mainTracking.py:340-448), on the device state -----------
+    def _dets(self, det_embs, det_boxes, det_confs):
+        n = len(det_boxes)
+        if not (len(det_embs) == n == len(det_confs)):
+            raise ValueError("Length mismatch: embs/bboxes/confs must have same length")
+        if n > self._ms.max_dets:
+            self._ms.grow(max_dets=max(n, 2 * self._ms.max_dets))
+        e = np.zeros((n, 128), np.float32)
+        for j, v in enumerate(det_embs):
+            v = np.asarray(v, dtype=np.float32).reshape(-1)
+            if v.shape[0] != 128:
+                raise ValueError(f"emb must be shape (128,), got {v.shape}")
+            e[j] = v
+        return (n, np.ascontiguousarray(np.asarray(det_boxes, dtype=np.float64).reshape(n, 4)),
+                np.ascontiguousarray(np.asarray(det_confs, dtype=np.float64).reshape(n)), e)
+
+    def _op(self, name, *args):
+        p = lambda a: a.ctypes.data_as(ctypes.c_void_p) if isinstance(a, np.ndarray) else a  # noqa: E731
+        with torch.cuda.device(self.device):
+            rc = getattr(_lib.lib(), name)(self._ms._h, 0, *[p(a) for a in args], _lib.stream_ptr(self.device))
+        self._snap = None
+        self._ms._n_live_stale = True
+        return rc
+
+    def predict_all(self):
+        """mainTracking.py:340-345: Kalman predict of every track; ``last_bbox`` becomes the predicted box."""
+        _lib.check(self._op("b200_tracker_predict_all"))
+
+    def mark_missed(self, track_ids: List[int]):
+        """mainTracking.py:347-355 (ids that are not live are skipped)."""
+        ids = np.ascontiguousarray(np.asarray(list(track_ids), dtype=np.int32))
+        _lib.check(self._op("b200_tracker_mark_missed", ids, len(ids)))
+
+    def purge_dead(self):
+        """mainTracking.py:357-360: drops tracks whose miss_count exceeds max_age."""
+        _lib.check(self._op("b200_tracker_purge_dead"))
+
+    def create_new_tracks(self, det_ids, det_embs, det_boxes, det_confs, frame_id):
+        """mainTracking.py:362-373: one new track per listed detection with conf >= init_conf_min, ids in list order."""
+        ids = np.ascontiguousarray(np.asarray(list(det_ids), dtype=np.int32))
+        if len(ids) == 0:
+            return
+        n, boxes, confs, embs = self._dets(det_embs, det_boxes, det_confs)
+        if int((confs[ids] >= self.init_conf_min).sum()) + int(self._ms.n_live_now()[0]) > self._ms.max_tracks:
+            self._ms.grow(max_tracks=2 * self._ms.max_tracks + len(ids))
+        rc = self._op("b200_tracker_create_tracks", ids, len(ids), boxes, confs, embs, n, int(frame_id))
+        if rc < 0:
+            _lib.check(rc)
+
+    def update_matched(self, matches, row_to_tid, det_embs, det_boxes, det_confs, frame_id, C_total_np, *,
+                       ema_alpha=0.9, conf_update_min=0.55, cost_update_max=50.0, maha_thr=9.49):
+        """mainTracking.py:375-448: Kalman update + bookkeeping for every (row, det) match and, behind the
+        confidence / cost / posterior-Mahalanobis gates, the EMA embedding and history-bank update."""
+        matches = list(matches)
+        if not matches:
+            return
+        try:
+            tids = np.array([row_to_tid[r] for r, _ in matches], dtype=np.int32)
+        except IndexError as exc:
+            raise IndexError("update_matched: match row outside row_to_tid") from exc
+        dets = np.array([j for _, j in matches], dtype=np.int32)
+        C = np.asarray(C_total_np)
+        costs = np.ascontiguousarray(np.array([C[r, j] for r, j in matches], dtype=np.float64).astype(np.float32))
+        if not np.array_equal(costs.astype(np.float64), np.array([float(C[r, j]) for r, j in matches])):
+            raise TypeError("update_matched: C_total_np must hold float32-representable costs (the reference passes float32)")
+        n, boxes, confs, embs = self._dets(det_embs, det_boxes, det_confs)
+        if len(dets) and (dets.min() < 0 or dets.max() >= n):
+            raise IndexError("update_matched: detection index out of range")       # the reference: det_boxes[det_j] at :393
+        rc = self._op("b200_tracker_update_matched", tids, dets, costs, len(matches), boxes, confs, embs, n, int(frame_id),
+                      float(ema_alpha), float(conf_update_min), float(cost_update_max), float(maha_thr))
+        _lib.check(rc, {_lib.EINVAL: KeyError})             # a track id that is not live: self.tracks[tid] at :390
+
     # -- state inspection ---------------------------------------------------------------------------
     def snapshot(self) -> Dict[str, np.ndarray]:
         """Host copy of the live tracks in ascending id order: the fields of TrackMemory / TrackState

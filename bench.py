@@ -8,22 +8,31 @@ The frame is BASELINE.json config 2 (the config the metric is quoted on): ROI Al
 assignment, update, births/purge) for 64 detections against ~64 tracks.  A GPU owns a GROUP of
 --streams independent video streams (BASELINE.json north_star: "one stream group per GPU") and one
 step advances every stream of the group by one frame with batched launches, so frames per step =
-streams.  extra.single_stream reports the same path with a single stream (one frame in flight).
-Synthetic inputs follow SURVEY.md section 8d.  Prints ONE JSON line (rank 0).
+streams.  Synthetic inputs follow SURVEY.md section 8d.  Prints ONE JSON line (rank 0).
 
 * value     : frames/s with every input already in HBM (device-resident maps, rois, detections),
-              timed with CUDA events over exactly K steps, max over ranks.
+              timed with CUDA events over exactly K steps, max over ranks.  Nothing else runs inside the
+              timed region (the roofline probe is a separate pass); `step_ms` is the distribution of the
+              per-step times inside it.
 * e2e       : frames/s through the public Python API with HOST (pinned) buffers: per step the map,
               rois and detections are copied up and the match table is copied back.
-* roofline  : ROI Align, algorithmic bytes / average launch duration measured with CUDA events
-              inside the timed region, against the measured copy bandwidth (MEASURED_PEAKS.json).
+* roofline  : ROI Align, algorithmic bytes / average launch duration measured with CUDA events on the
+              launching stream in a separate pass right after the timed region (same buffers, nothing
+              else on the GPU), against the measured copy bandwidth (MEASURED_PEAKS.json).
 * cpu_baseline : the oracle port of the reference path (torchvision CPU roi_align +
               Tracking.update restated, single-threaded Python like the reference) on a bounded
-              sample of the same frames, on this box's host cores.
---impl reference times that CPU path alone.  N > 1 (torchrun): one stream group per GPU (weak
-scaling), per-step NCCL all-gather of the result tables, value = total frames / max time.
+              sample of the same frames, on this box's host cores.  The same leg checks a fresh
+              device-side run of 40 frames, row by row, against that oracle.
+* extra     : the other BASELINE configs, each a short device-timed run: c1 (single 640x640 stream), c3
+              (256-map ROI extraction), c4 (512 x 512 association), c5 (64 1088x1920 streams), the
+              single-stream latency mode, channels-last maps, the public API with device-resident maps.
+--impl reference times the CPU path alone.  N > 1 (torchrun): one stream group per GPU (weak
+scaling), result tables all-gathered with NCCL (one-CTA collectives on a side stream, 16 frames at
+a time), value = total frames / max time; extra.c5_strong is BASELINE configs[4] as written: 64 c5
+streams in total, 64/N per GPU (strong scaling).
 """
 import argparse
+import collections
 import ctypes
 import json
 import os
@@ -37,25 +46,25 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "tracked frames/sec at N=64 boxes; ROIAlign achieved HBM GB/s vs B200 peak"
-WORKLOAD = ("c2: 1280x1280 frame, map [1,512,40,40], 64 detections vs ~64 tracks, roi_align 10x10 + "
-            "cost + gate + Kalman + assignment per frame")
-C, HF, WF, H_IN, W_IN, NBOX, PS = 512, 40, 40, 1280, 1280, 64, 10
-ROI_ALG_BYTES = NBOX * C * PS * PS * 4 + C * HF * WF * 4 + NBOX * 20
+C, PS = 512, 10
+Shape = collections.namedtuple("Shape", "name HF WF H_IN W_IN NBOX desc")
 WORKLOADS = {
+    # BASELINE.json configs[0]: the reference's own CPU-runnable case (tracking.py shapes)
+    "c1": Shape("c1", 20, 20, 640, 640, 8, "c1: 640x640 frame, map [1,512,20,20], 8 detections vs ~8 tracks, roi_align 10x10 + "
+                                           "cost + gate + Kalman + assignment per frame"),
     # BASELINE.json configs[1]: the configuration the metric is quoted on (default)
-    "c2": (40, 40, 1280, 1280, 64, "c2: 1280x1280 frame, map [1,512,40,40], 64 detections vs ~64 tracks, roi_align 10x10 + "
-                                   "cost + gate + Kalman + assignment per frame"),
+    "c2": Shape("c2", 40, 40, 1280, 1280, 64, "c2: 1280x1280 frame, map [1,512,40,40], 64 detections vs ~64 tracks, roi_align 10x10 + "
+                                              "cost + gate + Kalman + assignment per frame"),
     # BASELINE.json configs[4]: the streams of the multi-GPU configuration
-    "c5": (34, 60, 1088, 1920, 128, "c5: 1088x1920 frame, map [1,512,34,60], 128 detections vs ~128 tracks, roi_align "
-                                    "10x10 + cost + gate + Kalman + assignment per frame"),
+    "c5": Shape("c5", 34, 60, 1088, 1920, 128, "c5: 1088x1920 frame, map [1,512,34,60], 128 detections vs ~128 tracks, roi_align "
+                                               "10x10 + cost + gate + Kalman + assignment per frame"),
 }
+SETUP_FRAMES = 35          # history banks full (hist_max = 30) and Kalman dtypes in steady state
 
 
-def select_workload(name):
-    """Sets the module-level shape constants; everything below reads them at call time."""
-    global HF, WF, H_IN, W_IN, NBOX, WORKLOAD, ROI_ALG_BYTES
-    HF, WF, H_IN, W_IN, NBOX, WORKLOAD = WORKLOADS[name]
-    ROI_ALG_BYTES = NBOX * C * PS * PS * 4 + C * HF * WF * 4 + NBOX * 20
+def roi_alg_bytes(sh, n_maps=1):
+    """output written + every map read once + the roi records."""
+    return n_maps * (sh.NBOX * C * PS * PS * 4 + C * sh.HF * sh.WF * 4 + sh.NBOX * 20)
 
 
 def measured_peaks():
@@ -65,15 +74,15 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def make_frames(seed, n_frames):
+def make_frames(sh, seed, n_frames):
     """Detections of n_frames consecutive frames as dense arrays + the reference's obj dicts."""
     from alufe_b200 import synth
-    scene = synth.Scene(seed, NBOX, H_IN, W_IN)
+    scene = synth.Scene(seed, sh.NBOX, sh.H_IN, sh.W_IN)
     objs = [scene.step() for _ in range(n_frames)]
     boxes = np.array([o["bboxes"] for o in objs], dtype=np.float64)
     confs = np.array([o["confs"] for o in objs], dtype=np.float64)
     embs = np.array([np.stack(o["embs"]) for o in objs], dtype=np.float32)
-    rois = np.concatenate([np.zeros((n_frames, NBOX, 1)), boxes], axis=2).astype(np.float32)
+    rois = np.concatenate([np.zeros((n_frames, sh.NBOX, 1)), boxes], axis=2).astype(np.float32)
     return objs, boxes, confs, embs, rois
 
 
@@ -110,7 +119,7 @@ class ClockSampler(threading.Thread):
     def run(self):
         while not self.stop_flag:
             self.sample()
-            time.sleep(0.01)
+            time.sleep(0.002)
 
     def summary(self):
         med = float(np.median(self.sm)) if self.sm else None
@@ -120,7 +129,7 @@ class ClockSampler(threading.Thread):
 def _cpu_worker(args):
     """One host process = one video stream through the reference path (module-level for spawn)."""
     seed, warm, max_frames, budget_s, workload = args
-    select_workload(workload)                # spawned processes start from the defaults
+    sh = WORKLOADS[workload]
     import torch
     torch.set_num_threads(1)
     import alufe_b200  # noqa: F401
@@ -130,8 +139,8 @@ def _cpu_worker(args):
         from torchvision.ops import roi_align as tv_roi
     except Exception:                                              # noqa: BLE001
         tv_roi = None
-    objs, *_ = make_frames(seed, warm + max_frames)
-    feat_cpu = synth.feature_map(seed, 1, C, HF, WF)
+    objs, *_ = make_frames(sh, seed, warm + max_frames)
+    feat_cpu = synth.feature_map(seed, 1, C, sh.HF, sh.WF)
     f_t = torch.from_numpy(feat_cpu)
     ref = tracker_ref.TrackerRef(tracker_ref.SHIPPED_CONF)
     for obj in objs[:warm]:
@@ -141,9 +150,9 @@ def _cpu_worker(args):
         t0 = time.perf_counter()
         rois = np.array([[0.0] + list(b) for b in obj["bboxes"]], dtype=np.float32)
         if tv_roi is not None:
-            tv_roi(f_t, torch.from_numpy(rois), (PS, PS), HF / float(H_IN), 2, True)
+            tv_roi(f_t, torch.from_numpy(rois), (PS, PS), sh.HF / float(sh.H_IN), 2, True)
         else:
-            native.roi_align(feat_cpu, rois, (PS, PS), HF / float(H_IN), 2, True)
+            native.roi_align(feat_cpu, rois, (PS, PS), sh.HF / float(sh.H_IN), 2, True)
         t1 = time.perf_counter()
         ref.update(obj)
         t2 = time.perf_counter()
@@ -153,7 +162,7 @@ def _cpu_worker(args):
     return n, t_roi, t_upd, time.perf_counter() - t_start, ("torchvision" if tv_roi else "oracle C")
 
 
-def cpu_group_fps(warm, max_frames, budget_s, workers=None):
+def cpu_group_fps(sh, warm, max_frames, budget_s, workers=None):
     """The reference path on the host cores: the reference is single-threaded Python per stream
     (torchvision's CPU roi_align does not scale with threads either), so independent
     streams are spread over one process per core.  Returns a cpu_baseline dict."""
@@ -161,14 +170,13 @@ def cpu_group_fps(warm, max_frames, budget_s, workers=None):
     workers = workers or max(1, os.cpu_count() or 1)
     ctx = mp.get_context("spawn")
     with ctx.Pool(workers) as pool:
-        name = [k for k, v in WORKLOADS.items() if v[5] == WORKLOAD][0]
-        out = pool.map(_cpu_worker, [(50000 + w, warm, max_frames, budget_s, name) for w in range(workers)])
+        out = pool.map(_cpu_worker, [(50000 + w, warm, max_frames, budget_s, sh.name) for w in range(workers)])
     fps = sum(n / wall for n, _, _, wall, _ in out)
     n_tot = sum(o[0] for o in out)
     ms_roi = 1e3 * sum(o[1] for o in out) / n_tot
     ms_upd = 1e3 * sum(o[2] for o in out) / n_tot
     return {"value": fps, "unit": "frames/s", "cores": workers, "kind": "port",
-            "sample": ("%d independent " + name + " streams, one host process each (%d logical CPUs), %d frames in total "
+            "sample": ("%d independent " + sh.name + " streams, one host process each (%d logical CPUs), %d frames in total "
                        "after %d warm-up frames per stream: roi_align (%s CPU) %.1f ms + Tracking.update port %.1f ms per "
                        "frame per core; the association step is single-threaded Python as in the reference")
                       % (workers, os.cpu_count() or 0, n_tot, warm, out[0][4], ms_roi, ms_upd)}
@@ -200,19 +208,20 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    sh = WORKLOADS[args.workload]
     # like the GPU arm: the workload is defined with full history banks (30 frames); warm-up steps the caller
     # did not ask for run as untimed set-up before the W warm-up steps
     setup = max(0, 30 - args.warmup)
     warm = setup + args.warmup
     frames = max(1, min(args.steps, 400))
-    cpu = cpu_group_fps(warm, frames, budget_s=120.0)
+    cpu = cpu_group_fps(sh, warm, frames, budget_s=120.0)
     fps = cpu["value"]
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": frames,
         "warmup": args.warmup, "setup_steps": setup, "ms_per_step": 1e3 * cpu["cores"] / fps, "higher_is_better": True,
         "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "%d independent streams (one per host core), each " % cpu["cores"] + WORKLOAD,
+        "config": {"workload": "%d independent streams (one per host core), each " % cpu["cores"] + sh.desc,
                    "frames_per_step": cpu["cores"]},
         "cpu_baseline": cpu,
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -221,101 +230,153 @@ def run_reference(args):
 
 
 class StreamGroup:
-    """S independent config-2 streams on one GPU with every input resident in HBM.
+    """S independent streams of one workload shape on one GPU with every input resident in HBM.
 
-    One step = one frame of every stream: a single ROI Align launch over the S maps (K = 64*S ROIs,
+    One step = one frame of every stream: a single ROI Align launch over the S maps (K = NBOX*S ROIs,
     batch index = stream) on stream A, and one MultiStreamTracker step on stream B that waits for
     that frame's ROI launch (in the real pipeline the encoder sits between them), so ROI Align of
     frame t+1 overlaps the association of frame t."""
 
-    def __init__(self, S, n_frames, rank, dev, channels_last=False):
+    def __init__(self, sh, S, n_frames, seed_base, dev, channels_last=False, with_roi=True, max_tracks=None):
         import torch
         import alufe_b200
         from alufe_b200 import _lib
-        self.torch, self.lib, self._lib, self.S, self.F, self.dev = torch, _lib.lib(), _lib, S, n_frames, dev
-        per = [make_frames(1000 * rank + s, n_frames) for s in range(S)]
+        self.torch, self.lib, self._lib, self.S, self.F, self.dev, self.sh = torch, _lib.lib(), _lib, S, n_frames, dev, sh
+        NB = sh.NBOX
+        per = [make_frames(sh, 1000 * seed_base + s, n_frames) for s in range(S)]
         self.objs0 = per[0][0]
-        self.boxes = np.stack([p[1] for p in per], axis=1)          # [F, S, 64, 4]
+        self.boxes = np.stack([p[1] for p in per], axis=1)          # [F, S, NB, 4]
         self.confs = np.stack([p[2] for p in per], axis=1)
         self.embs = np.stack([p[3] for p in per], axis=1)
-        rois = np.stack([p[4] for p in per], axis=1)                # [F, S, 64, 5]
+        rois = np.stack([p[4] for p in per], axis=1)                # [F, S, NB, 5]
         rois[..., 0] = np.arange(S, dtype=np.float32)[None, :, None]
-        self.rois = rois.reshape(n_frames, S * NBOX, 5)
+        self.rois = rois.reshape(n_frames, S * NB, 5)
         self.d_boxes, self.d_confs = torch.from_numpy(self.boxes).to(dev), torch.from_numpy(self.confs).to(dev)
         self.d_embs, self.d_rois = torch.from_numpy(self.embs).to(dev), torch.from_numpy(self.rois).to(dev)
-        self.d_ndet = torch.full((n_frames, S), NBOX, dtype=torch.int32, device=dev)
+        self.d_ndet = torch.full((n_frames, S), NB, dtype=torch.int32, device=dev)
         self.d_frame = torch.arange(n_frames, dtype=torch.int32, device=dev)[:, None].repeat(1, S).contiguous()
-        # enough distinct maps / output buffers that nothing is served from the 126 MB L2
-        self.nmap = max(2, -(-160 // max(1, (S * C * HF * WF * 4) // 1000000)))
-        self.nout = max(2, -(-260 // max(1, (S * NBOX * C * PS * PS * 4) // 1000000)))
-        gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+        self.with_roi = with_roi
+        self.map_b, self.out_b = S * C * sh.HF * sh.WF * 4, S * NB * C * PS * PS * 4
+        self.roi_alg_bytes = roi_alg_bytes(sh, S)
         self.nhwc = 1 if channels_last else 0          # same values; only the memory order of each map differs
-        self.maps = torch.randn((self.nmap, S, HF, WF, C) if channels_last else (self.nmap, S, C, HF, WF),
-                                device=dev, generator=gen)
-        self.outs = torch.empty((self.nout, S * NBOX, C, PS, PS), device=dev)
-        self.trk = alufe_b200.MultiStreamTracker(S, alufe_b200.SHIPPED_CONF, max_tracks=256, max_dets=NBOX, device=dev)
+        if with_roi:
+            # enough distinct maps / output buffers that nothing is served from the 126 MB L2
+            self.nmap = max(2, -(-160 // max(1, self.map_b // 1000000)))
+            self.nout = max(2, -(-260 // max(1, self.out_b // 1000000)))
+            gen = torch.Generator(device=dev).manual_seed(1234 + seed_base)
+            self.maps = torch.randn((self.nmap, S, sh.HF, sh.WF, C) if channels_last else (self.nmap, S, C, sh.HF, sh.WF),
+                                    device=dev, generator=gen)
+            self.outs = torch.empty((self.nout, S * NB, C, PS, PS), device=dev)
+        self.trk = alufe_b200.MultiStreamTracker(S, alufe_b200.SHIPPED_CONF, max_tracks=max_tracks or max(256, 2 * NB),
+                                                 max_dets=NB, device=dev)
         self.results = torch.zeros((n_frames, S, self.trk.stride), dtype=torch.int32, device=dev)
         # the association chain is short and latency-bound: it gets the high-priority stream so its CTAs are
         # scheduled ahead of the queued ROI Align tiles of the next frame
         self.sA, self.sB = torch.cuda.Stream(dev, priority=0), torch.cuda.Stream(dev, priority=-1)
         self.roi_done = [torch.cuda.Event() for _ in range(8)]
-
-        self.map_b, self.out_b = S * C * HF * WF * 4, S * NBOX * C * PS * PS * 4
-        self.roi_alg_bytes = S * NBOX * C * PS * PS * 4 + S * C * HF * WF * 4 + S * NBOX * 20
         self.ptr = {k: getattr(self, k).data_ptr() for k in
-                    ("maps", "outs", "d_rois", "d_ndet", "d_boxes", "d_confs", "d_embs", "d_frame", "results")}
+                    ("d_rois", "d_ndet", "d_boxes", "d_confs", "d_embs", "d_frame", "results")}
+        if with_roi:
+            self.ptr.update(maps=self.maps.data_ptr(), outs=self.outs.data_ptr())
 
     def roi(self, i):
-        P, S, p = ctypes.c_void_p, self.S, self.ptr
-        rc = self.lib.b200_roi_align_fwd_f32(P(p["maps"] + (i % self.nmap) * self.map_b), self.nhwc, S, C, HF, WF,
-                                             P(p["d_rois"] + i * S * NBOX * 20), S * NBOX, PS, PS, HF / float(H_IN), 2, 1,
+        P, S, p, sh = ctypes.c_void_p, self.S, self.ptr, self.sh
+        rc = self.lib.b200_roi_align_fwd_f32(P(p["maps"] + (i % self.nmap) * self.map_b), self.nhwc, S, C, sh.HF, sh.WF,
+                                             P(p["d_rois"] + (i % self.F) * S * sh.NBOX * 20), S * sh.NBOX, PS, PS,
+                                             sh.HF / float(sh.H_IN), 2, 1,
                                              P(p["outs"] + (i % self.nout) * self.out_b), P(self.sA.cuda_stream))
         if rc:
             self._lib.check(rc)
 
     def assoc(self, i):
-        P, S, p = ctypes.c_void_p, self.S, self.ptr
-        rc = self.lib.b200_tracker_step(self.trk._h, P(p["d_ndet"] + 4 * i * S), P(p["d_boxes"] + i * S * NBOX * 32),
-                                        P(p["d_confs"] + i * S * NBOX * 8), P(p["d_embs"] + i * S * NBOX * 512),
+        P, S, p, NB = ctypes.c_void_p, self.S, self.ptr, self.sh.NBOX
+        rc = self.lib.b200_tracker_step(self.trk._h, P(p["d_ndet"] + 4 * i * S), P(p["d_boxes"] + i * S * NB * 32),
+                                        P(p["d_confs"] + i * S * NB * 8), P(p["d_embs"] + i * S * NB * 512),
                                         P(p["d_frame"] + 4 * i * S), P(p["results"] + i * S * self.trk.stride * 4),
                                         P(self.sB.cuda_stream))
         if rc:
             self._lib.check(rc)
 
-    def step(self, i, probe=None):
-        if probe is not None:
-            # roofline probe: this ROI Align launch runs with no association kernel beside it, so the
-            # events bracket the kernel alone (the other steps overlap it with the previous frame)
-            self.sA.wait_stream(self.sB)
-            probe[0].record(self.sA)
-        self.roi(i)
-        if probe is not None:
-            probe[1].record(self.sA)
-        ev = self.roi_done[i % len(self.roi_done)]
-        ev.record(self.sA)
-        self.sB.wait_event(ev)
+    def step(self, i):
+        if self.with_roi:
+            self.roi(i)
+            ev = self.roi_done[i % len(self.roi_done)]
+            ev.record(self.sA)
+            self.sB.wait_event(ev)
         self.assoc(i)
 
-    def run(self, first, count, n_probe=0, after_step=None):
-        """Runs `count` steps starting at frame `first`; returns (elapsed ms on the device, probe times us)."""
+    def run(self, first, count, after_step=None, start_after=None):
+        """Runs `count` steps starting at frame `first`; returns (elapsed ms on the device, per-step ms).
+        Per-step times come from one event per step recorded on the association stream (recording an event does
+        not order the two streams, so the overlap of the pipeline is untouched)."""
         torch = self.torch
         main = torch.cuda.current_stream(self.dev)
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        probes = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_probe)]
-        every = max(1, count // max(1, n_probe))
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(count)]
+        if start_after is not None:
+            start_after()                     # e.g. a collective that lines the ranks up right before the first event
         ev0.record(main)
         self.sA.wait_event(ev0)
         self.sB.wait_event(ev0)
         for k in range(count):
-            q = k // every
-            self.step(first + k, probes[q] if (n_probe and k % every == 0 and q < n_probe) else None)
+            self.step(first + k)
+            marks[k].record(self.sB)
             if after_step is not None:
                 after_step(first + k)
         main.wait_stream(self.sA)
         main.wait_stream(self.sB)
-        ev1.record(main)
+        return ev0, ev1, marks
+
+    def finish(self, ev0, ev1, marks):
+        torch = self.torch
+        ev1.record(torch.cuda.current_stream(self.dev))
         torch.cuda.synchronize(self.dev)
-        return ev0.elapsed_time(ev1), [a.elapsed_time(b) * 1e3 for a, b in probes]
+        ends = [ev0.elapsed_time(m) for m in marks]
+        return ev0.elapsed_time(ev1), [b - a for a, b in zip([0.0] + ends[:-1], ends)]
+
+    def timed(self, first, count, **kw):
+        return self.finish(*self.run(first, count, **kw))
+
+    def probe_roi(self, n, first=0):
+        """n ROI Align launches alone on their stream (nothing else on the GPU), CUDA events around each: the
+        roofline measurement.  Map sets and output buffers keep rotating, so nothing is served from L2."""
+        torch = self.torch
+        torch.cuda.synchronize(self.dev)
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+        for k, (a, b) in enumerate(evs):
+            a.record(self.sA)
+            self.roi(first + k)
+            b.record(self.sA)
+        torch.cuda.synchronize(self.dev)
+        return [a.elapsed_time(b) * 1e3 for a, b in evs]
+
+
+def dist_summary(ms):
+    a = np.asarray(ms, dtype=np.float64)
+    return {"min": float(a.min()), "median": float(np.median(a)), "max": float(a.max()), "n": int(a.size)}
+
+
+def oracle_check(dev, frames=40):
+    """A fresh 2-stream device-side run (b200_tracker_step with device-resident inputs, the call the timed region
+    makes) against the oracle tracker, every result row of every frame."""
+    import torch
+    from oracle import tracker_ref
+    sh = WORKLOADS["c2"]
+    g = StreamGroup(sh, 2, frames, 777, dev, with_roi=False)
+    g.timed(0, frames)
+    res = g.results.cpu().numpy()
+    bad = 0
+    for s in range(2):
+        ref = tracker_ref.TrackerRef(tracker_ref.SHIPPED_CONF)
+        objs = make_frames(sh, 1000 * 777 + s, frames)[0]
+        for f, obj in enumerate(objs):
+            want = ref.update(obj)
+            got = g.trk.decode(res[f, s])
+            if not (got[0] == want[0] and got[1] == want[1] and got[2] == want[2] and int(res[f, s, 5]) == 0):
+                bad += 1
+    del g
+    torch.cuda.empty_cache()
+    return {"frames_checked": 2 * frames, "mismatching_frames": bad}
 
 
 def main():
@@ -323,26 +384,26 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=40)
-    ap.add_argument("--streams", type=int, default=64, help="config-2 streams per GPU stepped together")
+    ap.add_argument("--streams", type=int, default=64, help="streams per GPU stepped together")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="c2",
+    ap.add_argument("--workload", choices=["c2", "c5"], default="c2",
                     help="per-stream frame shape: c2 (BASELINE configs[1], the headline) or c5 (configs[4])")
-    ap.add_argument("--gather-every", type=int, default=8,
+    ap.add_argument("--gather-every", type=int, default=16,
                     help="N > 1: all-gather the result tables every this many frames")
-    ap.add_argument("--no-extra", action="store_true", help="skip the single-stream side measurement")
+    ap.add_argument("--no-extra", action="store_true", help="skip the side measurements (other BASELINE configs)")
     args = ap.parse_args()
-    select_workload(args.workload)
     quiet_stdout()
     if args.impl == "reference":
         return run_reference(args)
     if args.warmup < 3:
         args.warmup = 3
+    sh = WORKLOADS[args.workload]
 
     import torch
     import torch.distributed as dist
     import alufe_b200
-    from alufe_b200 import _lib, synth
+    from alufe_b200 import _lib, dist as bdist
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -363,46 +424,56 @@ def main():
         pass
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        bdist.init_process_group_small_footprint(dev)
     lib = _lib.lib()
     K, W, S = args.steps, args.warmup, args.streams
     peak, peak_src = measured_peaks()
+    NB = sh.NBOX
 
-    # ---- stream group of S config-2 streams on this GPU --------------------------------------------
+    # ---- stream group of S streams on this GPU --------------------------------------------------------
     # The workload is defined with full history banks (hist_max = 30) and steady-state Kalman dtypes, which
     # takes 35 frames.  If the caller asks for fewer warm-up steps, the difference is run as untimed set-up
     # before the W warm-up steps, so the timed K steps always see the same workload.
-    pre = max(0, 35 - W)
-    grp = StreamGroup(S, pre + W + K, rank, dev)
-    # The only inter-GPU traffic: the per-stream result tables, all-gathered for the consumer of tracking.py:329.
-    # They are gathered GATHER_EVERY frames at a time ("optionally gather every K frames"):
-    # a NCCL kernel per step holds SM slots while it waits for the slowest rank, which cost 17 % at 8 GPUs.
-    GATHER_EVERY = max(1, args.gather_every)
+    pre = max(0, SETUP_FRAMES - W)
     n_total = pre + W + K
-    gathered = (torch.zeros((2, world, GATHER_EVERY, S, grp.trk.stride), dtype=torch.int32, device=dev)
-                if world > 1 else None)
-    pending = []
 
-    def gather_after(i):
+    def make_gather(grp, n_streams_global, frames_total, boundaries):
+        """The only inter-GPU traffic: the per-stream result tables, all-gathered for the consumer of tracking.py:329,
+        GATHER_EVERY frames per collective ("optionally gather every K frames") through the
+        product's ResultGatherer: one-CTA NCCL kernels on a side stream that waits for an event on the association
+        stream, so neither pipeline stream ever waits for another rank."""
         if world == 1:
-            return
-        full = (i + 1) % GATHER_EVERY == 0
-        if not (full or i == n_total - 1 or i == pre + W - 1):     # also flush at the end of each run() call
-            return
-        i0 = (i // GATHER_EVERY) * GATHER_EVERY
-        n = i + 1 - i0
-        torch.cuda.current_stream(dev).wait_stream(grp.sB)         # NCCL orders after the current stream
-        dst = gathered[(i // GATHER_EVERY) % 2][:, :n] if n == GATHER_EVERY else \
-            torch.empty((world, n, S, grp.trk.stride), dtype=torch.int32, device=dev)
-        pending.append(dist.all_gather_into_tensor(dst.reshape(-1) if n == GATHER_EVERY else dst.view(-1),
-                                                   grp.results[i0:i0 + n].reshape(-1), async_op=True))
-        if len(pending) > 1:
-            pending.pop(0).wait()
+            return None, lambda: None
+        G = max(1, args.gather_every)
+        gat = bdist.ResultGatherer(n_streams_global, grp.trk.stride, dev)
+        pending = []
 
-    grp.run(0, pre + W, after_step=gather_after)
-    for h in pending:
-        h.wait()
-    pending.clear()
+        def after_step(i):
+            full = (i + 1) % G == 0
+            if not (full or i == frames_total - 1 or (i + 1) in boundaries):   # also flush at the end of each run() call
+                return
+            i0 = (i // G) * G
+            ev = torch.cuda.Event()
+            ev.record(grp.sB)
+            pending.append(gat.gather_frames(grp.results[i0:i + 1], async_op=True, after=ev))
+            while len(pending) > 2:
+                gat.wait(pending.pop(0))
+
+        def flush():
+            while pending:
+                gat.wait(pending.pop(0))
+            torch.cuda.current_stream(dev).wait_stream(gat.stream)
+        return after_step, flush
+
+    def lineup():
+        """All ranks' first timing event lands right behind the same collective (start skew of microseconds)."""
+        if world > 1:
+            dist.all_reduce(torch.zeros(1, device=dev))
+
+    grp = StreamGroup(sh, S, n_total, rank, dev)
+    after_step, flush = make_gather(grp, world * S, n_total, {pre + W})
+    grp.timed(0, pre + W, after_step=after_step)
+    flush()
 
     sampler = ClockSampler(local)
     if world > 1:
@@ -411,10 +482,9 @@ def main():
     launches0 = lib.b200_launch_count()
     sampler.sample()
     sampler.start()
-    elapsed_ms, roi_us = grp.run(pre + W, K, n_probe=min(K, 16), after_step=gather_after)
-    for h in pending:
-        h.wait()
-    torch.cuda.synchronize()
+    ev = grp.run(pre + W, K, after_step=after_step, start_after=lineup)
+    flush()                                    # the last gather completes inside the timed region
+    elapsed_ms, step_ms = grp.finish(*ev)
     sampler.sample()
     sampler.stop_flag = True
     launches = lib.b200_launch_count() - launches0
@@ -424,20 +494,61 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     elapsed_ms = float(t.item())
-    roi_us_avg = float(np.mean(roi_us))
     last = grp.results[pre + W + K - 1].cpu().numpy()
     assert (last[:, 5] == 0).all() and (last[:, 0] > 0).all(), "device path produced no matches"
 
+    # ---- roofline probe: ROI Align launches alone, after the timed region ---------------------------------
+    roi_us = grp.probe_roi(16, first=pre + W)
+    roi_us_avg = float(np.mean(roi_us))
+    if world > 1:                              # every rank probes at the same time (what an N-GPU job looks like)
+        tp = torch.tensor([roi_us_avg], dtype=torch.float64, device=dev)
+        dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+        roi_us_max_ranks = float(tp.item())
+    else:
+        roi_us_max_ranks = roi_us_avg
+
+    extra = {}
+    # ---- BASELINE configs[4] as written: 64 c5 streams in total, 64 / N per GPU (strong scaling) ---------
+    if not args.no_extra and 64 % world == 0:
+        try:
+            sh5, S5, K5 = WORKLOADS["c5"], 64 // world, min(max(K, 20), 60)
+            n5 = SETUP_FRAMES + 5 + K5
+            del grp.maps, grp.outs
+            torch.cuda.empty_cache()
+            g5 = StreamGroup(sh5, S5, n5, 300 + rank, dev)
+            a5, f5 = make_gather(g5, 64, n5, {SETUP_FRAMES + 5})
+            g5.timed(0, SETUP_FRAMES + 5, after_step=a5)
+            f5()
+            if world > 1:
+                dist.barrier()
+            ev5 = g5.run(SETUP_FRAMES + 5, K5, after_step=a5, start_after=lineup)
+            f5()
+            ms5, step5 = g5.finish(*ev5)
+            t5 = torch.tensor([ms5], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t5, op=dist.ReduceOp.MAX)
+            ms5 = float(t5.item())
+            roi5 = g5.probe_roi(8, first=SETUP_FRAMES + 5)
+            extra["c5_strong"] = {"value": 64 * K5 / (ms5 * 1e-3), "unit": "frames/s", "scaling": "strong",
+                                  "streams_total": 64, "streams_per_gpu": S5, "steps": K5, "ms_per_step": ms5 / K5,
+                                  "step_ms": dist_summary(step5), "roi_us_per_launch": float(np.mean(roi5)),
+                                  "roi_frac_of_peak": g5.roi_alg_bytes / float(np.mean(roi5)) / 1e3 / peak,
+                                  "workload": "64 streams in total, each " + sh5.desc}
+            del g5
+            torch.cuda.empty_cache()
+        except Exception as exc:                                    # noqa: BLE001
+            extra["c5_strong_error"] = repr(exc)
+
     # ---- end to end through the public API with host (pinned) buffers --------------------------------
-    ms2 = alufe_b200.MultiStreamTracker(S, alufe_b200.SHIPPED_CONF, max_tracks=256, max_dets=NBOX, device=dev)
+    ms2 = alufe_b200.MultiStreamTracker(S, alufe_b200.SHIPPED_CONF, max_tracks=max(256, 2 * NB), max_dets=NB, device=dev)
     NPIN = 2
-    pin_maps = torch.randn((NPIN, S, C, HF, WF), generator=torch.Generator().manual_seed(99 + rank)).pin_memory()
+    pin_maps = torch.randn((NPIN, S, C, sh.HF, sh.WF), generator=torch.Generator().manual_seed(99 + rank)).pin_memory()
     pin_rois = torch.from_numpy(grp.rois).pin_memory()
-    feat_dev = [torch.empty((S, C, HF, WF), device=dev) for _ in range(2)]     # double-buffered upload target
-    rois_dev = [torch.empty((S * NBOX, 5), device=dev) for _ in range(2)]
-    n_det = np.full(S, NBOX, np.int32)
+    feat_dev = [torch.empty((S, C, sh.HF, sh.WF), device=dev) for _ in range(2)]     # double-buffered upload target
+    rois_dev = [torch.empty((S * NB, 5), device=dev) for _ in range(2)]
+    n_det = np.full(S, NB, np.int32)
     n_e2e = min(K, 60)
-    scale = HF / float(H_IN)
+    scale = sh.HF / float(sh.H_IN)
     copy_stream = torch.cuda.Stream(dev)
     uploaded = [torch.cuda.Event() for _ in range(2)]
     consumed = [torch.cuda.Event() for _ in range(2)]
@@ -452,7 +563,7 @@ def main():
 
     def e2e_step(i):
         """One frame of every stream through the public API.  The upload of frame i+1 is queued on a copy stream
-        before the (synchronising) tracker call of frame i, as a caller feeding frames from the host would do."""
+        before the tracker call of frame i, as a caller feeding frames from the host would do."""
         b = i & 1
         main = torch.cuda.current_stream(dev)
         main.wait_event(uploaded[b])
@@ -479,87 +590,163 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t.item())
-    h2d = grp.map_b + S * NBOX * 20 + S * (8 + NBOX * (32 + 8 + 512))
+    h2d = grp.map_b + S * NB * 20 + S * (8 + NB * (32 + 8 + 512))
     d2h = S * grp.trk.stride * 4
-    extra = {}
     # ---- the same public-API loop with the maps already on the device (how the reference's CUDA deployment calls
     # roi_align: the detector's map never leaves the GPU, only boxes / confidences / embeddings come from the host) ----
-    if rank == 0 and not args.no_extra and K - n_e2e > 0:          # needs frames beyond those of the e2e leg
+    if rank == 0 and not args.no_extra:
         try:
             def api_step(i):
-                rois_dev[i & 1].copy_(pin_rois[i % len(pin_rois)], non_blocking=True)
+                j = pre + W + (i % K)              # frames of the timed region again (the state has moved on; same shapes)
+                rois_dev[i & 1].copy_(pin_rois[j % len(pin_rois)], non_blocking=True)
                 patches = alufe_b200.roi_align(feat_dev[i & 1], rois_dev[i & 1], (PS, PS), scale, 2, True)
-                return patches, ms2.step(n_det, grp.boxes[i], grp.confs[i], grp.embs[i], np.full(S, i, np.int32))
+                return patches, ms2.step(n_det, grp.boxes[j], grp.confs[j], grp.embs[j], np.full(S, n_total + i, np.int32))
+            for k in range(3):
+                api_step(k)
             torch.cuda.synchronize()
-            n_api = min(60, K - n_e2e)                 # the frames after those of the e2e leg
+            n_api = 40
             t0 = time.perf_counter()
             for k in range(n_api):
-                _, res = api_step(pre + W + n_e2e + k)
+                _, res = api_step(3 + k)
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
-            assert (res[:, 0] > 0).all()
             extra["api_device_maps"] = {"value": S * n_api / dt, "unit": "frames/s", "ms_per_step": 1e3 * dt / n_api,
-                                        "h2d_bytes_per_step": S * NBOX * 20 + S * (8 + NBOX * (32 + 8 + 512)),
+                                        "h2d_bytes_per_step": S * NB * 20 + S * (8 + NB * (32 + 8 + 512)),
                                         "note": "alufe_b200.roi_align + MultiStreamTracker.step with host boxes / "
                                                 "confidences / embeddings and device-resident maps"}
         except Exception as exc:                                    # noqa: BLE001
             extra["api_device_maps_error"] = repr(exc)
-    del pin_maps, feat_dev
+    del pin_maps, feat_dev, ms2
+    torch.cuda.empty_cache()
+
+    def side(name, fn):
+        if rank == 0 and world == 1 and not args.no_extra:
+            try:
+                extra[name] = fn()
+            except Exception as exc:                                # noqa: BLE001
+                extra[name + "_error"] = repr(exc)
+            torch.cuda.empty_cache()
 
     # ---- single-stream latency mode (one frame in flight; the shape the reference runs) --------------
-    if rank == 0 and not args.no_extra:
-        try:
-            K1 = 400
-            g1 = StreamGroup(1, pre + W + K1, 7000 + rank, dev)
-            g1.run(0, pre + W)
-            ms1, roi1 = g1.run(pre + W, K1, n_probe=32)
-            extra["single_stream"] = {"value": K1 / (ms1 * 1e-3), "unit": "frames/s", "ms_per_frame": ms1 / K1,
-                                      "roi_us_per_launch": float(np.mean(roi1)),
-                                      "roi_frac_of_peak": g1.roi_alg_bytes / float(np.mean(roi1)) / 1e3 / peak}
-            del g1
-        except Exception as exc:                                    # noqa: BLE001
-            extra["single_stream_error"] = repr(exc)
+    def single(shape):
+        def fn():
+            K1 = 300
+            g1 = StreamGroup(shape, 1, SETUP_FRAMES + 5 + K1, 7000, dev)
+            g1.timed(0, SETUP_FRAMES + 5)
+            ms1, step1 = g1.timed(SETUP_FRAMES + 5, K1)
+            roi1 = g1.probe_roi(32)
+            return {"value": K1 / (ms1 * 1e-3), "unit": "frames/s", "ms_per_frame": ms1 / K1, "step_ms": dist_summary(step1),
+                    "roi_us_per_launch": float(np.mean(roi1)), "workload": "one stream, " + shape.desc,
+                    "roi_frac_of_peak": g1.roi_alg_bytes / float(np.mean(roi1)) / 1e3 / peak}
+        return fn
+    side("single_stream", single(sh))
+    side("c1", single(WORKLOADS["c1"]))
 
     # ---- the same stream group fed channels-last maps (what a channels_last detector would hand over) ----
-    if rank == 0 and world == 1 and not args.no_extra:
-        try:
-            del grp.maps, grp.outs
-            torch.cuda.empty_cache()
-            Kc = min(K, 100)
-            gc = StreamGroup(S, pre + W + Kc, 9000 + rank, dev, channels_last=True)
-            gc.run(0, pre + W)
-            msc, roic = gc.run(pre + W, Kc, n_probe=min(Kc, 16))
-            extra["channels_last_maps"] = {"value": S * Kc / (msc * 1e-3), "unit": "frames/s", "ms_per_step": msc / Kc,
-                                           "roi_us_per_launch": float(np.mean(roic)),
-                                           "roi_frac_of_peak": gc.roi_alg_bytes / float(np.mean(roic)) / 1e3 / peak,
-                                           "kernel": "roi_prep_kernel + roi_align_pipe_kernel<10,10,NHWC>"}
-            del gc
-        except Exception as exc:                                    # noqa: BLE001
-            extra["channels_last_error"] = repr(exc)
+    def channels_last():
+        Kc = min(K, 100)
+        gc = StreamGroup(sh, S, SETUP_FRAMES + 5 + Kc, 9000, dev, channels_last=True)
+        gc.timed(0, SETUP_FRAMES + 5)
+        msc, stepc = gc.timed(SETUP_FRAMES + 5, Kc)
+        roic = gc.probe_roi(16)
+        return {"value": S * Kc / (msc * 1e-3), "unit": "frames/s", "ms_per_step": msc / Kc, "step_ms": dist_summary(stepc),
+                "roi_us_per_launch": float(np.mean(roic)),
+                "roi_frac_of_peak": gc.roi_alg_bytes / float(np.mean(roic)) / 1e3 / peak,
+                "kernel": "roi_prep_kernel + roi_align_pipe_kernel<10,10,NHWC>"}
+    side("channels_last_maps", channels_last)
+
+    # ---- BASELINE configs[2]: training-style batched extraction, 256 maps x 16 boxes -> [4096,512,10,10] ----
+    def c3_roi():
+        Bm, per = 256, 16
+        from alufe_b200 import synth
+        rng = np.random.default_rng(0)
+        boxes = np.concatenate([synth.random_boxes(rng, per, 1280, 1280) for _ in range(Bm)])
+        rois = np.concatenate([np.repeat(np.arange(Bm), per)[:, None].astype(np.float64), boxes], 1).astype(np.float32)
+        r = torch.from_numpy(rois).to(dev)
+        feat = torch.randn((Bm, C, 40, 40), device=dev)
+        out = None
+        evs = []
+        for k in range(13):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            out = alufe_b200.roi_align(feat, r, (PS, PS), 40 / 1280.0, 2, True)
+            b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        us = float(np.median([a.elapsed_time(b) for a, b in evs[3:]])) * 1e3
+        alg = Bm * per * C * PS * PS * 4 + Bm * C * 40 * 40 * 4 + Bm * per * 20
+        touched = None
+        tp = os.path.join(ROOT, "profiles", "roi_traffic.json")
+        if os.path.exists(tp):
+            touched = json.load(open(tp)).get("dram_bytes_per_launch_c3")
+        d = {"us_per_launch": us, "rois": Bm * per, "out_shape": list(out.shape), "alg_bytes": alg,
+             "frac_of_peak_algorithmic": alg / us / 1e3 / peak,
+             "note": "inputs (839 MB of maps) and output (839 MB) are each larger than L2; the algorithmic figure counts "
+                     "every map byte once although only the sectors under the boxes are read"}
+        if touched:
+            d["dram_bytes_measured"] = touched
+            d["frac_of_peak_dram_traffic"] = touched / us / 1e3 / peak
+        return d
+    side("c3_roi", c3_roi)
+
+    # ---- BASELINE configs[3]: dense crowd, 512 detections x ~512 tracks, association only ---------------
+    def c4_assoc():
+        sh4 = Shape("c4", 40, 40, 1280, 1280, 512, "c4: 512 detections vs ~512 tracks, cost + gate + Kalman + assignment")
+        K4 = 30
+        g4 = StreamGroup(sh4, 1, SETUP_FRAMES + K4, 4000, dev, with_roi=False, max_tracks=1088)
+        g4.timed(0, SETUP_FRAMES)
+        ms4, step4 = g4.timed(SETUP_FRAMES, K4)
+        last4 = g4.results[SETUP_FRAMES + K4 - 1].cpu().numpy()
+        d = {"ms_per_frame": ms4 / K4, "step_ms": dist_summary(step4), "matches_last_frame": int(last4[0, 0]),
+             "live_tracks": int(last4[0, 3]), "workload": sh4.desc}
+        # the dense bank contraction of north_star kernel 2 as an operator: 512 tracks x 30 rows x 128 against 512 detections
+        from alufe_b200 import cost as cost_ops
+        bank = torch.nn.functional.normalize(torch.randn((512, 30, 128), device=dev), dim=2)
+        lens = torch.full((512,), 30, dtype=torch.int32, device=dev)
+        det = torch.nn.functional.normalize(torch.randn((512, 128), device=dev), dim=1)
+        evs = []
+        for k in range(13):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            cost_ops.app_cost_topk(bank, lens, det, topk=5)
+            b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        us = float(np.median([a.elapsed_time(b) for a, b in evs[3:]])) * 1e3
+        d["dense_app_cost_us"] = us
+        d["dense_app_cost_tflops"] = 2.0 * 512 * 30 * 512 * 128 / us / 1e6
+        return d
+    side("c4_assoc", c4_assoc)
 
     # ---- CPU baseline on this box's host cores (rank 0, N == 1 only) ---------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         if affinity0 is not None:
             os.sched_setaffinity(0, affinity0)                       # the CPU baseline uses every host core
-        cpu = cpu_group_fps(warm=30, max_frames=60, budget_s=12.0)
+        cpu = cpu_group_fps(sh, warm=30, max_frames=60, budget_s=12.0)
+        try:
+            extra["oracle_check"] = oracle_check(dev)
+        except Exception as exc:                                    # noqa: BLE001
+            extra["oracle_check_error"] = repr(exc)
 
     if rank == 0:
         traffic = None
         tp = os.path.join(ROOT, "profiles", "roi_traffic.json")
-        if os.path.exists(tp):
+        if os.path.exists(tp) and args.workload == "c2":
             traffic = json.load(open(tp)).get("dram_bytes_per_launch_%d_streams" % S)
         frames = world * S * K
         line = {
             "metric": METRIC, "value": frames / (elapsed_ms * 1e-3), "unit": "frames/s", "n_gpus": world, "steps": K,
-            "warmup": W, "setup_steps": pre, "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "warmup": W, "setup_steps": pre, "ms_per_step": elapsed_ms / K, "step_ms": dist_summary(step_ms),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "%d independent streams per GPU, each " % S + WORKLOAD, "streams_per_gpu": S,
+            "config": {"workload": "%d independent streams per GPU, each " % S + sh.desc, "streams_per_gpu": S,
                        "frames_per_step": S, "roi_out": [PS, PS], "layout": "nchw",
                        "l2": "inputs larger than L2: each step reads %d maps (%.0f MB) and writes %.0f MB; %d map sets and %d "
                              "output buffers rotate" % (S, grp.map_b / 1e6, grp.out_b / 1e6, grp.nmap, grp.nout),
                        "pipeline": "ROI Align of frame t+1 (stream A) overlaps the association of frame t (stream B)",
-                       "gather": ("result tables of all ranks all-gathered with NCCL every %d frames" % GATHER_EVERY)
+                       "gather": ("result tables of all ranks all-gathered with NCCL (one-CTA kernels, side stream) every %d "
+                                  "frames; the last gather completes inside the timed region" % max(1, args.gather_every))
                        if world > 1 else "single GPU: none",
                        "state_dtype": "f64 Kalman/assignment duals, f32 ROI/cost"},
             "clocks": sampler.summary(),
@@ -567,13 +754,14 @@ def main():
                     "steps": n_e2e, "api": "alufe_b200.roi_align + MultiStreamTracker.step (pinned host buffers)",
                     "h2d_gbps": h2d * n_e2e / e2e_s / 1e9, "host_cpus_near_gpu": near_cpus},
             "gpu_launches": int(launches),
-            "roofline": {"kernel": "roi_prep_kernel + roi_align_multi_kernel<10,10,NCHW> (one ROI Align launch)", "bound": "hbm",
-                         "achieved": grp.roi_alg_bytes / roi_us_avg / 1e3, "peak": peak, "unit": "GB/s",
+            "roofline": {"kernel": "roi_prep_kernel + roi_align_tma_kernel<10,10,float> (one ROI Align launch, NCHW maps)",
+                         "bound": "hbm", "achieved": grp.roi_alg_bytes / roi_us_avg / 1e3, "peak": peak, "unit": "GB/s",
                          "frac": grp.roi_alg_bytes / roi_us_avg / 1e3 / peak, "traffic": traffic,
-                         "alg_bytes_per_launch": grp.roi_alg_bytes, "us_per_launch": roi_us_avg, "launches_timed": len(roi_us),
+                         "alg_bytes_per_launch": grp.roi_alg_bytes, "us_per_launch": roi_us_avg,
+                         "us_per_launch_slowest_rank": roi_us_max_ranks, "launches_timed": len(roi_us),
                          "peak_source": peak_src,
-                         "note": "the timed launches are %d of the K ROI Align launches of the timed region, bracketed by CUDA "
-                                 "events on their stream and run without a concurrent association kernel" % len(roi_us)},
+                         "note": "separate pass after the timed region: %d ROI Align launches on the same rotating buffers, "
+                                 "bracketed by CUDA events on their stream, nothing else running on the GPU" % len(roi_us)},
             "cpu_baseline": cpu,
             "extra": extra,
         }

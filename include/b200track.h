@@ -168,6 +168,32 @@ int  b200_tracker_step(b200_tracker* t, const int32_t* n_det, const double* boxe
 int  b200_tracker_step_host(b200_tracker* t, const int32_t* n_det_host, const double* boxes_host,
                             const double* confs_host, const float* embs_host,
                             const int32_t* frame_id_host, int32_t* result_host, void* stream);
+/* ---- Tracking's methods one by one (mainTracking.py:340-448) ------------------------------------------------
+ * The reference exposes the pieces of update() as methods a caller may drive itself; these entry points are
+ * those methods on one stream of a handle.  Host arrays in, synchronous (they synchronise `stream`); the fused
+ * b200_tracker_step does not go through them.
+ *   predict_all   (:340-345)  Kalman predict of every live track, last_bbox <- predicted box
+ *   mark_missed   (:347-355)  miss_count += 1 for the listed track ids (unknown ids are skipped)
+ *   purge_dead    (:357-360)  drops tracks with miss_count > max_age
+ *   create_tracks (:362-373)  births for det_ids (caller's order) whose confidence >= init_conf_min; boxes [n_det,4],
+ *                             confs [n_det], embs [n_det,128] are the frame's detections; returns the number created,
+ *                             B200_ECAPACITY if the handle is full
+ *   update_matched(:375-448)  per match (track id, detection index, cost = C_total[row, det]): Kalman update, last box /
+ *                             confidence / frame / cost, age, miss reset, then -- if confidence >= conf_update_min, cost <=
+ *                             cost_update_max and the posterior squared Mahalanobis distance <= maha_thr -- EMA embedding and
+ *                             history-bank push.  B200_EINVAL if a track id is not live (the reference: KeyError). */
+int  b200_tracker_predict_all(b200_tracker* t, int stream_idx, void* stream);
+int  b200_tracker_mark_missed(b200_tracker* t, int stream_idx, const int32_t* track_ids_host, int n, void* stream);
+int  b200_tracker_purge_dead(b200_tracker* t, int stream_idx, void* stream);
+int  b200_tracker_create_tracks(b200_tracker* t, int stream_idx, const int32_t* det_ids_host, int n_ids,
+                                const double* boxes_host, const double* confs_host, const float* embs_host,
+                                int n_det, int frame_id, void* stream);
+int  b200_tracker_update_matched(b200_tracker* t, int stream_idx, const int32_t* match_tid_host,
+                                 const int32_t* match_det_host, const float* match_cost_host, int n_matches,
+                                 const double* boxes_host, const double* confs_host, const float* embs_host,
+                                 int n_det, int frame_id, double ema_alpha, double conf_update_min,
+                                 double cost_update_max, double maha_thr, void* stream);
+
 /* Copies one stream's live tracks (ascending track id) to host arrays sized for max_tracks;
  * any pointer may be NULL.  bank is [n, hist_max, 128] oldest-first.  Returns n_live or <0. */
 int  b200_tracker_export(b200_tracker* t, int stream_idx, int32_t* ids, double* x, double* P,

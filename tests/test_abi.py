@@ -23,7 +23,7 @@ def test_library_builds_and_exports_header_symbols():
     _lib.build()
     h = ctypes.CDLL(_lib.LIB_PATH)
     names = _declared_symbols()
-    assert len(names) >= 22
+    assert len(names) >= 27
     for n in names:
         assert hasattr(h, n), "libb200track.so does not export %s" % n
     assert sorted(_lib.SIGNATURES) == names, "python bindings and header disagree"

@@ -237,6 +237,72 @@ def test_multistream_equals_independent_trackers():
             assert int(res[s, 3]) == len(singles[s].tracks) and int(res[s, 4]) == singles[s].next_id
 
 
+def test_tracker_methods_one_by_one_vs_oracle():
+    """predict_all / update_matched / mark_missed / create_new_tracks / purge_dead (mainTracking.py:340-448) driven by hand
+    in the order Tracking.update uses them, state compared with the oracle after EVERY call; costs and assignments come
+    from the oracle so that only the methods under test touch the device state."""
+    from oracle.lsap_ref import hungarian_assign
+    cfg = dict(SHIPPED_CONF, lost_reid_after=3, max_age=6, hist_max=5)
+    ref = tracker_ref.TrackerRef(cfg)
+    trk = Tracking(conf=cfg, max_tracks=12, max_dets=8)            # small on purpose: create_new_tracks has to grow it
+    scene = synth.Scene(21, 14, 640, 640, drop=0.25, churn=0.2, churn_every=4)
+
+    def same(what):
+        ids, st = _oracle_state(ref)
+        _compare_state(trk, ids, st, what)
+        assert trk.next_id == ref.next_id, what
+
+    for f in range(24):
+        obj = scene.step()
+        embs, boxes, confs = obj["embs"], obj["bboxes"], obj["confs"]
+        N = len(boxes)
+        ref.predict_all()
+        trk.predict_all()
+        same("predict_all %d" % f)
+        main = sorted(t for t, tr in ref.tracks.items() if tr.miss_count <= cfg["lost_reid_after"])
+        reid = sorted(t for t, tr in ref.tracks.items() if tr.miss_count > cfg["lost_reid_after"])
+        free = list(range(N))
+        if main and N:
+            C = np.array(ref.stage1_cost(main, embs, boxes, confs, obj["input_hw"])["C_total"], dtype=np.float32)
+            C = ref.gate(C, main, boxes, cfg["maha_thr"])
+            m1, ur, free = hungarian_assign(C, cost_max=cfg["cost_max"])
+            ref.absorb(m1, main, embs, boxes, confs, f, C, cost_update_max=cfg["cost_update_max"], maha_thr=cfg["maha_thr"])
+            trk.update_matched(m1, main, embs, boxes, confs, f, C, ema_alpha=cfg["ema_alpha"],
+                               conf_update_min=cfg["conf_update_min"], cost_update_max=cfg["cost_update_max"],
+                               maha_thr=cfg["maha_thr"])
+            same("update_matched %d" % f)
+            lost = [main[r] for r in ur]
+            ref.mark_missed(lost)
+            trk.mark_missed(lost + [10 ** 6])                      # an id that is not live is skipped (:350-351)
+            same("mark_missed %d" % f)
+        if reid and free:
+            e_u, b_u, c_u = [embs[j] for j in free], [boxes[j] for j in free], [confs[j] for j in free]
+            C2 = np.array(ref.app_cost(reid, e_u), dtype=np.float32)
+            m2, ur2, ud2 = hungarian_assign(C2, cost_max=cfg["reid_only_cost_max"])
+            ref.absorb(m2, reid, e_u, b_u, c_u, f, C2, cost_update_max=cfg["reid_only_cost_max"], maha_thr=1e18)
+            trk.update_matched(m2, reid, e_u, b_u, c_u, f, C2, ema_alpha=cfg["ema_alpha"],
+                               conf_update_min=cfg["conf_update_min"], cost_update_max=cfg["reid_only_cost_max"], maha_thr=1e18)
+            same("update_matched (reid) %d" % f)
+            ref.mark_missed([reid[r] for r in ur2])
+            trk.mark_missed([reid[r] for r in ur2])
+            free = [free[j] for j in ud2]
+        elif reid:
+            ref.mark_missed(reid)
+            trk.mark_missed(reid)
+        ref.spawn(free, embs, boxes, confs, f)
+        trk.create_new_tracks(free, embs, boxes, confs, f)
+        same("create_new_tracks %d" % f)
+        ref.purge_dead()
+        trk.purge_dead()
+        same("purge_dead %d" % f)
+    assert ref.next_id > 20 and trk._ms.max_tracks > 12
+    with pytest.raises(KeyError):
+        trk.update_matched([(0, 0)], [10 ** 6], [obj["embs"][0]], [obj["bboxes"][0]], [0.9], 99, np.zeros((1, 1), np.float32))
+    # the hand-driven tracker and a fused update() agree on the next frame
+    obj = scene.step()
+    assert trk.update(obj) == tuple(ref.update(obj))
+
+
 def test_step_device_vs_oracle():
     """MultiStreamTracker.step_device / b200_tracker_step with DEVICE-resident inputs (the path bench.py times):
     every result row of every frame and the exported state against one oracle tracker per stream, 36 frames with

@@ -13,19 +13,19 @@ torch.cuda.set_device(0)
 lib = ctypes.CDLL(_lib.LIB_PATH)
 names = ["roi", "begin", "cost1", "assign1", "cost2", "assign2", "update"]
 for mode in ("serial", "overlap"):
-    g = bench.StreamGroup(S, W + 12, 0, dev)
+    g = bench.StreamGroup(bench.WORKLOADS["c2"], S, W + 12, 0, dev)
     if mode == "serial":
         g.sB = g.sA
-    g.run(0, W)
+    g.timed(0, W)
     print("==", mode)
     b1, b2 = (ctypes.c_ulonglong * 128)(), (ctypes.c_ulonglong * 128)()
     lib.b200_debug_spans_roi(None, 1)
     lib.b200_debug_spans_trk(None, 1)
     first = W + (8 - W % 8) % 8          # frame index that is a multiple of 8
-    g.run(W, first - W) if first > W else None
+    g.timed(W, first - W) if first > W else None
     lib.b200_debug_spans_roi(None, 1)
     lib.b200_debug_spans_trk(None, 1)
-    g.run(first, 6)                      # six consecutive steady-state steps, one span slot each
+    g.timed(first, 6)                      # six consecutive steady-state steps, one span slot each
     lib.b200_debug_spans_roi(b1, 0)
     lib.b200_debug_spans_trk(b2, 0)
     roi = np.array(b1[:16], dtype=np.float64).reshape(8, 2)
