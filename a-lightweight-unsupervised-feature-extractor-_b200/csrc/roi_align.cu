@@ -802,28 +802,36 @@ roi_align_pipe_kernel(const T* __restrict__ feat, int B, int C, int H, int W, co
 // ---- TMA-staged pipelined kernel: large launches on NCHW maps --------------------------------------------
 // The plane-strided footprint of an NCHW map (FY rows x FX floats in each of 32 channel planes) is exactly a
 // box of a 4-D tensor (W, H, C, B): one cp.async.bulk.tensor (SASS UTMALDG) moves it with no LSU wavefronts and
-// no per-element address arithmetic, which were the two costs of the LDGSTS staging above.  The box is
-// {16 bytes, kTmaRows rows, 32 channels, 1 map} and lands in shared memory as V[channel][row][x], x fastest; with
-// an ODD row count the per-channel stride (kTmaRows * 16 B) is an odd multiple of 16 bytes, so the 128-bit read
-// of one footprint row by the 8 lanes of a quarter-warp (lane = channel) touches 8 different bank groups:
-// conflict-free, and one LDS.128 per row instead of FX 32-bit ones.  The contraction therefore runs row-outer:
-//   tx[pw] = sum_x Wx[x][pw] * V[r][x];   acc[ph][pw] += Wy[r][ph] * tx[pw]
-// (same FFMA count as the column-outer form of separable_accumulate).  A box can only start on a 16-byte boundary of a
-// map row (measured: an inner coordinate that is not a multiple of 16 bytes raises "illegal instruction",
-// tools/tma_probe.cu), so roi_prep_kernel widens the footprint to the left to a multiple of four cells and
-// records which columns really carry weight (RoiPrep::xmask); the others are skipped, not multiplied by zero.
-// Footprints wider than 16 bytes take a second box to the right, taller than kTmaRows a second box below (up to
-// the 8 x 8 cells of the staged path); coordinates beyond the map are zero-filled by the TMA unit.  The ROI's ready-made weight tables
-// arrive on the same mbarrier with one cp.async.bulk.  A warp walks `tiles_per_warp` tiles and keeps the
-// footprint of the NEXT tile in flight while it accumulates the current one (two table slots; the V region is
-// shared by the two tiles in flight, growing from both ends, and a tile that does not fit beside its
-// predecessor is simply requested after it has been consumed), stages its [32][PH*PW] result in a separate
-// output tile and hands that to the TMA engine as one bulk store whose completion is awaited only when the next
-// result is ready.  Tiles the prep kernel did not stage go through process_tile() with the output tile as
-// scratch.
-constexpr int kTmaRows = 5;
-constexpr int kTmaBoxBytes = 16 * kTmaRows * 32;          // one box: 16 B x kTmaRows rows x 32 channels
-constexpr int kTmaVBytes = 4 * kTmaBoxBytes;              // one 2 x 2-box tile, or two smaller tiles in flight
+// no per-element address arithmetic, which were the two costs of the LDGSTS staging above.  What the hardware
+// dictates (tools/tma_probe.cu, profiles/r02_roi_ncu_summary.md):
+//   * a box can only start on a 16-byte boundary of a map row (an inner coordinate that is not a multiple of
+//     16 bytes raises "illegal instruction"), so roi_prep_kernel widens the footprint to the left to a multiple
+//     of four cells and records which columns really carry weight (RoiPrep::xmask); the others are skipped,
+//     not multiplied by zero;
+//   * the TMA unit works row by row and a warp's next instruction waits until the unit has accepted the box, so
+//     the number of box rows, not bytes, is the cost: boxes are 32 bytes wide (eight cells: every widened
+//     footprint of the staged path fits one box) and come in three heights, 1 / 3 / 5 rows (three tensor maps),
+//     the smallest that covers the footprint; taller footprints (6-8 rows) take a second box below.
+// A box lands in shared memory as V[channel][row][8 cells]; with an ODD row count the 128-bit reads of one half
+// row by the 8 lanes of a quarter-warp (lane = channel, stride rows * 32 B) fall on four bank groups: two
+// wavefronts per read, of which there are only two per footprint row.  Coordinates beyond the map are zero-filled
+// by the TMA unit.  The contraction keeps the rows of four columns in registers and runs column-outer
+// (tma_accumulate).  The ROI's ready-made weight tables arrive on the same mbarrier with one cp.async.bulk.  A
+// warp walks `tiles_per_warp` tiles and keeps the footprint of the NEXT tile in flight while it accumulates the
+// current one (two table slots; the V region is shared by the two tiles in flight, growing from both ends, and a
+// tile that does not fit beside its predecessor is simply requested after it has been consumed), stages its
+// [32][PH*PW] result in a separate output tile and hands that to the TMA engine as one bulk store whose
+// completion is awaited only when the next result is ready.  Tiles the prep kernel did not stage go through
+// process_tile() with the output tile as scratch.
+constexpr int kTmaRows = 5;                                // rows of the tallest box
+constexpr int kTmaCols = 8;                                // cells per box row (32 bytes)
+constexpr int kTmaRowBytes = kTmaCols * 4 * 32;            // one box row of all 32 channels in shared memory
+constexpr int kTmaVRows = 10;                              // V region in box rows: two tiles of <= 5 rows in flight
+constexpr int kTmaVBytes = kTmaVRows * kTmaRowBytes;
+struct TmaMaps {                                           // the same map with boxes of 1, 3 and 5 rows
+    CUtensorMap m[3];
+};
+__device__ __forceinline__ int tma_box_rows(int rows) { return rows <= 1 ? 1 : rows <= 3 ? 3 : 5; }
 #ifndef B200_ROI_TMA_WARPS
 #define B200_ROI_TMA_WARPS 2
 #endif
@@ -873,13 +881,12 @@ __device__ __forceinline__ void bulk_load(unsigned dst, const void* src, unsigne
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
-// Boxes of a staged tile (0 for a ROI that samples nothing) and the bytes they occupy in the V region.
-template <typename T>
-__device__ __forceinline__ int tma_tile_boxes(const int4 h0, const int4 h1) {
-    constexpr int BX = 16 / (int)sizeof(T);
+// Box rows a staged tile occupies in the V region (0 for a ROI that samples nothing): one box of 1 / 3 / 5 rows, plus a
+// second one for footprints of 6-8 rows.
+__device__ __forceinline__ int tma_tile_rows(const int4 h0, const int4 h1) {
     const int FY = h0.w, FX = h1.x;
     if (FY == 0 || FX == 0) return 0;
-    return (FY > kTmaRows ? 2 : 1) * (FX > BX ? 2 : 1);
+    return FY > kTmaRows ? kTmaRows + tma_box_rows(FY - kTmaRows) : tma_box_rows(FY);
 }
 
 __device__ __forceinline__ bool elect_one() {
@@ -894,41 +901,37 @@ __device__ __forceinline__ int bcast0(int v) { return __shfl_sync(0xffffffffu, v
 // go to the TMA instructions through uniform registers directly (with per-lane values ptxas wraps every UTMALDG /
 // UBLKCP in an ELECT / R2UR.BROADCAST loop, which showed up as 11 % of all stall samples).
 template <int PH, int PW, typename T>
-__device__ __forceinline__ void tma_issue(const CUtensorMap* tm, const int4 h0, const int4 h1, unsigned k, int c0,
+__device__ __forceinline__ void tma_issue(const TmaMaps* tm, const int4 h0, const int4 h1, unsigned k, int c0,
                                           const float* __restrict__ prep_tabs, unsigned sv, unsigned stab, unsigned bar) {
     using S = TmaSmem<PH, PW>;
-    constexpr int BX = 16 / (int)sizeof(T);
     const int b = bcast0(h0.x), ymin = bcast0(h0.y), xmin = bcast0(h0.z), FY = bcast0(h0.w), FX = bcast0(h1.x);
     const unsigned ku = (unsigned)bcast0((int)k);
     const int cu = bcast0(c0);
     const unsigned svu = (unsigned)bcast0((int)sv), stabu = (unsigned)bcast0((int)stab), baru = (unsigned)bcast0((int)bar);
-    const int nrb = FY > kTmaRows ? 2 : 1;
-    const int nb = (FY == 0 || FX == 0) ? 0 : nrb * (FX > BX ? 2 : 1);
+    const bool any = FY != 0 && FX != 0;
+    const int r0 = FY > kTmaRows ? kTmaRows : tma_box_rows(FY);                 // rows of the first box
+    const int r1 = FY > kTmaRows ? tma_box_rows(FY - kTmaRows) : 0;            // rows of the box below it
     if (elect_one()) {
 #ifdef B200_ROI_TMA_NOLOAD                       // timing experiment only (results are wrong): no footprint traffic
         mbar_expect_tx(baru, (unsigned)S::kTabBytes);
         bulk_load(stabu, prep_tabs + (size_t)ku * S::L::kTabFloats, S::kTabBytes, baru);
         if (false) {
 #else
-        mbar_expect_tx(baru, (unsigned)(S::kTabBytes + nb * kTmaBoxBytes));
+        mbar_expect_tx(baru, (unsigned)(S::kTabBytes + (any ? (r0 + r1) * kTmaRowBytes : 0)));
         bulk_load(stabu, prep_tabs + (size_t)ku * S::L::kTabFloats, S::kTabBytes, baru);
-        if (nb) {
+        if (any) {
 #endif
-            tma_box_4d(svu, tm, xmin, ymin, cu, b, baru);
-            if (nrb == 2) tma_box_4d(svu + kTmaBoxBytes, tm, xmin, ymin + kTmaRows, cu, b, baru);
-            if (FX > BX) {
-                tma_box_4d(svu + nrb * kTmaBoxBytes, tm, xmin + BX, ymin, cu, b, baru);
-                if (nrb == 2) tma_box_4d(svu + 3 * kTmaBoxBytes, tm, xmin + BX, ymin + kTmaRows, cu, b, baru);
-            }
+            tma_box_4d(svu, &tm->m[r0 >> 1], xmin, ymin, cu, b, baru);
+            if (r1) tma_box_4d(svu + kTmaRows * kTmaRowBytes, &tm->m[r1 >> 1], xmin, ymin + kTmaRows, cu, b, baru);
         }
     }
     __syncwarp();
 }
 
-// Separable contraction over V[channel][row][x] as the TMA boxes lay it out (see above).  Per box (kTmaRows rows x four
-// columns of this lane's channel) the rows are read once as 128-bit values into registers (rows beyond the footprint
-// as zeros, never as map data); then, column-outer like separable_accumulate: for every column that carries weight
-// (one uniform test per column and box, not per row), ty[ph] = sum_r Wy[r][ph] * V[r][x] and
+// Separable contraction over V[channel][row][8 cells] as the TMA boxes lay it out (see above).  Per box and half row
+// (four columns of this lane's channel) the rows are read once as 128-bit values into registers (rows beyond the
+// footprint as zeros, never as map data); then, column-outer like separable_accumulate: for every column that
+// carries weight (one uniform test per column and box, not per row), ty[ph] = sum_r Wy[r][ph] * V[r][x] and
 // acc[ph][pw] += Wx[x][pw] * ty[ph].
 template <int PH, int PW, typename T>
 __device__ __forceinline__ void tma_accumulate(float (&acc)[PH][PW], const unsigned char* sV, const float* sWy,
@@ -936,19 +939,19 @@ __device__ __forceinline__ void tma_accumulate(float (&acc)[PH][PW], const unsig
     static_assert(sizeof(T) == 4, "float32 maps only");
     constexpr int PHP = (PH + 3) & ~3, PWP = (PW + 3) & ~3;
     const int nrb = FY > kTmaRows ? 2 : 1, ncb = FX > 4 ? 2 : 1;
-    const unsigned char* mine = sV + lane * (kTmaRows * 16);
-    for (int cb = 0; cb < ncb; ++cb) {
-        for (int rb = 0; rb < nrb; ++rb) {
-            const unsigned char* box = mine + (cb * nrb + rb) * kTmaBoxBytes;
-            const int rows = FY - rb * kTmaRows;                      // rows of the footprint in this box (may exceed kTmaRows)
+    for (int rb = 0; rb < nrb; ++rb) {
+        const int rows = FY - rb * kTmaRows;                          // footprint rows from this box's first row on
+        const int brow = rb ? tma_box_rows(rows) : (nrb == 2 ? kTmaRows : tma_box_rows(rows));   // rows of the box itself
+        const unsigned char* mine = sV + rb * (kTmaRows * kTmaRowBytes) + lane * (brow * 32);
+        const float* wy0 = sWy + rb * kTmaRows * PHP;
+        for (int cb = 0; cb < ncb; ++cb) {
             float v[kTmaRows][4];
 #pragma unroll
             for (int i = 0; i < kTmaRows; ++i) {
                 float4 q = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                if (i < rows) q = *reinterpret_cast<const float4*>(box + i * 16);
+                if (i < rows) q = *reinterpret_cast<const float4*>(mine + i * 32 + cb * 16);
                 v[i][0] = q.x; v[i][1] = q.y; v[i][2] = q.z; v[i][3] = q.w;
             }
-            const float* wy0 = sWy + rb * kTmaRows * PHP;
             const int bits = (xmask >> (4 * cb)) & 15;
 #pragma unroll
             for (int xi = 0; xi < 4; ++xi) {
@@ -990,7 +993,7 @@ __device__ __forceinline__ void tma_accumulate(float (&acc)[PH][PW], const unsig
 
 template <int PH, int PW, typename T, bool OCL>
 __global__ void __maxnreg__(B200_ROI_TMA_REGS)
-roi_align_tma_kernel(const __grid_constant__ CUtensorMap tmap, const T* __restrict__ feat, int B, int C, int H, int W,
+roi_align_tma_kernel(const __grid_constant__ TmaMaps tmap, const T* __restrict__ feat, int B, int C, int H, int W,
                      const float* __restrict__ rois, long long K, float scale, int sr, int aligned, T* __restrict__ out,
                      int ctiles, const RoiPrep* __restrict__ prep, const float* __restrict__ prep_tabs, int group_warps,
                      int tiles_per_warp) {
@@ -1035,20 +1038,20 @@ roi_align_tma_kernel(const __grid_constant__ CUtensorMap tmap, const T* __restri
     bool pending = false;              // the bulk store of the previous result may still be reading sOut
     bool cur_issued = false;
     // V offset of a tile with `nb` boxes in slot p: slot 0 grows up from the start, slot 1 down from the end
-    auto v_off = [&](int p, int nb) { return p ? (unsigned)(kTmaVBytes - nb * kTmaBoxBytes) : 0u; };
+    auto v_off = [&](int p, int nr) { return p ? (unsigned)(kTmaVBytes - nr * kTmaRowBytes) : 0u; };
     if (a1.y) {
-        tma_issue<PH, PW, T>(&tmap, a0, a1, ka, ca, prep_tabs, sbase + v_off(0, tma_tile_boxes<T>(a0, a1)),
+        tma_issue<PH, PW, T>(&tmap, a0, a1, ka, ca, prep_tabs, sbase + v_off(0, tma_tile_rows(a0, a1)),
                              sbase + S::kOffTab, sbar);
         cur_issued = true;
     }
     for (;;) {
         const bool have_next = tn < total;
         const int cn = min(32, C - ca);
-        const int nba = a1.y ? tma_tile_boxes<T>(a0, a1) : 0;
-        const int nbn = (have_next && n1.y) ? tma_tile_boxes<T>(n0, n1) : 0;
+        const int nba = a1.y ? tma_tile_rows(a0, a1) : 0;                      // box rows of the current / next tile
+        const int nbn = (have_next && n1.y) ? tma_tile_rows(n0, n1) : 0;
         // the next tile's footprint is requested now if it fits beside the current one, else once that is consumed
         bool next_issued = false;
-        if (have_next && n1.y && (nba + nbn) * kTmaBoxBytes <= kTmaVBytes) {
+        if (have_next && n1.y && nba + nbn <= kTmaVRows) {
             tma_issue<PH, PW, T>(&tmap, n0, n1, kn, cnx, prep_tabs, sbase + v_off(par ^ 1, nbn),
                                  sbase + S::kOffTab + (par ^ 1) * S::kTabBytes, sbar + 8 * (par ^ 1));
             next_issued = true;
@@ -1083,7 +1086,7 @@ roi_align_tma_kernel(const __grid_constant__ CUtensorMap tmap, const T* __restri
             if (nba) tma_accumulate<PH, PW, T>(acc, base + v_off(par, nba), sWy, sWy + kFootCap * PHP, FY, FX, a1.z, lane);
             load_after_next();
             __syncwarp();              // V and the tables of this slot are dead
-            if (have_next && n1.y && !next_issued && nbn * kTmaBoxBytes <= kTmaVBytes) {
+            if (have_next && n1.y && !next_issued && nbn <= kTmaVRows) {
                 tma_issue<PH, PW, T>(&tmap, n0, n1, kn, cnx, prep_tabs, sbase + v_off(par ^ 1, nbn),
                                      sbase + S::kOffTab + (par ^ 1) * S::kTabBytes, sbar + 8 * (par ^ 1));
                 next_issued = true;
@@ -1146,7 +1149,7 @@ roi_align_tma_kernel(const __grid_constant__ CUtensorMap tmap, const T* __restri
                                                             lane, a0, a1, &pending);
             load_after_next();
             __syncwarp();
-            if (have_next && n1.y && !next_issued && nbn * kTmaBoxBytes <= kTmaVBytes) {
+            if (have_next && n1.y && !next_issued && nbn <= kTmaVRows) {
                 tma_issue<PH, PW, T>(&tmap, n0, n1, kn, cnx, prep_tabs, sbase + v_off(par ^ 1, nbn),
                                      sbase + S::kOffTab + (par ^ 1) * S::kTabBytes, sbar + 8 * (par ^ 1));
                 next_issued = true;
@@ -1297,15 +1300,17 @@ int launch_tma(const T* feat, int B, int C, int H, int W, const float* rois, lon
     if (reinterpret_cast<uintptr_t>(tabs) & 15) return 1;
     EncodeTiledFn encode = encode_tiled_fn();
     if (!encode) return 1;
-    CUtensorMap tmap;
+    TmaMaps tmap;
     const cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)C, (cuuint64_t)B};
     const cuuint64_t strides[3] = {(cuuint64_t)W * kEs, (cuuint64_t)H * W * kEs, (cuuint64_t)C * H * W * kEs};
-    const cuuint32_t box[4] = {(cuuint32_t)(16 / kEs), (cuuint32_t)kTmaRows, 32u, 1u};
     const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
-    const CUresult r = encode(&tmap, kEs == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4,
-                              const_cast<T*>(feat), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return 1;
+    for (int i = 0; i < 3; ++i) {                // boxes of 1, 3 and 5 rows
+        const cuuint32_t box[4] = {(cuuint32_t)kTmaCols, (cuuint32_t)(2 * i + 1), 32u, 1u};
+        const CUresult r = encode(&tmap.m[i], kEs == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4,
+                                  const_cast<T*>(feat), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return 1;
+    }
     static int cache[kMaxDevices];               // per instantiation and device
     auto kern = roi_align_tma_kernel<PH, PW, T, OCL>;
     int resident = 0;
