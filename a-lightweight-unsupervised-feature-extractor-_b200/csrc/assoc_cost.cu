@@ -1,7 +1,11 @@
 // Cost operators of the C ABI: build_C_app_topk and bbox/conf/total cost.  Math in assoc_cost.cuh.
+#include <stdlib.h>
+
 #include "assoc_cost.cuh"
 
 namespace b200 {
+int app_cost_tc(const float* bank, const int32_t* bank_len, const float* fallback, const float* det, int M, int N, int T,
+                int topk, int use_topk_mean, float* C_app, int ldc, cudaStream_t st);      // app_cost_tc.cu
 namespace {
 
 __global__ void __launch_bounds__(cost::kThreads)
@@ -57,11 +61,20 @@ extern "C" int b200_app_cost_topk_f32(const float* bank, const int32_t* bank_len
     B200_REQUIRE(bank && bank_len && det && C_app, "app_cost: null pointer");
     B200_REQUIRE(ldc >= N, "app_cost: ldc < N");
     B200_REQUIRE(M <= 65535, "app_cost: M too large");
-    static bool configured = false;
-    if (!configured) {
+    // large launches are a real GEMM: bf16x3-split tensor-core kernel (app_cost_tc.cu); B200TRACK_NO_TC=1 keeps the
+    // float32 FFMA kernel (used by the tests to compare the two)
+    static const bool no_tc = getenv("B200TRACK_NO_TC") != nullptr;
+    if (!no_tc) {
+        const int rc = app_cost_tc(bank, bank_len, fallback, det, M, N, T, topk, use_topk_mean, C_app, ldc, as_stream(stream));
+        if (rc != 1) return rc;
+    }
+    static bool configured[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+    if (!configured[dev]) {
         B200_CUDA(cudaFuncSetAttribute(app_cost_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)cost::smem_bytes(cost::kMaxBank)));
-        configured = true;
+        configured[dev] = true;
     }
     dim3 grid((N + cost::kTileN - 1) / cost::kTileN, M);
     app_cost_kernel<<<grid, cost::kThreads, cost::smem_bytes(T), as_stream(stream)>>>(

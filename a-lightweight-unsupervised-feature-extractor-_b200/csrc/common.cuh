@@ -14,6 +14,7 @@ extern thread_local char g_err[512];
 extern std::atomic<int64_t> g_launches;
 
 int fail(int code, const char* fmt, ...);
+int scratch_pool(cudaMemPool_t* out);       // private per-device pool for stream-ordered scratch (api.cu)
 
 inline int check_launch(const char* what) {
     g_launches.fetch_add(1, std::memory_order_relaxed);

@@ -36,7 +36,6 @@
 #include <cuda_fp16.h>
 
 #include "common.cuh"
-#include <mutex>
 #include <type_traits>
 
 namespace b200 {
@@ -1233,34 +1232,6 @@ int resident_warps_of(Kern kern, int (&cache)[kMaxDevices], int warps_per_cta, i
     return B200_OK;
 }
 
-// Stream-ordered scratch (per-ROI records and weight tables of the two-kernel path) comes from a PRIVATE pool per
-// device that keeps freed blocks cached; the application's default pool and its release threshold are not touched.
-struct ScratchPool {
-    std::mutex mu;
-    cudaMemPool_t pool = nullptr;
-};
-ScratchPool g_scratch[kMaxDevices];
-
-int scratch_pool(cudaMemPool_t* out) {
-    const int dev = device_ordinal();
-    ScratchPool& sp = g_scratch[dev];
-    std::lock_guard<std::mutex> lock(sp.mu);
-    if (!sp.pool) {
-        cudaMemPoolProps props = {};
-        props.allocType = cudaMemAllocationTypePinned;
-        props.handleTypes = cudaMemHandleTypeNone;
-        props.location.type = cudaMemLocationTypeDevice;
-        props.location.id = dev;
-        cudaMemPool_t pool = nullptr;
-        B200_CUDA(cudaMemPoolCreate(&pool, &props));
-        unsigned long long keep = ~0ull;
-        B200_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-        sp.pool = pool;
-    }
-    *out = sp.pool;
-    return B200_OK;
-}
-
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda).
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -1316,12 +1287,18 @@ int launch_tma(const T* feat, int B, int C, int H, int W, const float* rois, lon
     int resident = 0;
     const int rc = resident_warps_of(kern, cache, kTmaWarps, S::kBytesPerCta, &resident);
     if (rc) return rc;
-    const long long window = (long long)resident * B200_ROI_TMA_TILES;
+    // Tiles per warp: 16 amortise a warp's start-up (mbarrier init, first un-overlapped load) best, but a warp that walks
+    // 16 tiles lives ~60 us; a launch of only a few waves (8 streams of BASELINE config 5: 16 384 tiles) would then hold
+    // every SM slot from start to end and the association kernels of the other stream could not start beside it.  Keep
+    // at least four waves of warps, and never fewer than 2 tiles per warp.
+    long long tpw = tiles / ((long long)resident * 4);
+    tpw = tpw < 2 ? 2 : tpw > B200_ROI_TMA_TILES ? B200_ROI_TMA_TILES : tpw;
+    const long long window = (long long)resident * tpw;
     const long long groups = (tiles + window - 1) / window;
     const long long last = tiles - (groups - 1) * window;
     const long long warps = (groups - 1) * resident + (last < resident ? last : resident);
     kern<<<(unsigned)((warps + kTmaWarps - 1) / kTmaWarps), kTmaWarps * 32, S::kBytesPerCta, st>>>(
-        tmap, feat, B, C, H, W, rois, K, scale, sr, aligned, out, ctiles, prep, tabs, resident, B200_ROI_TMA_TILES);
+        tmap, feat, B, C, H, W, rois, K, scale, sr, aligned, out, ctiles, prep, tabs, resident, (int)tpw);
     return check_launch("roi_align_tma_kernel");
 }
 
