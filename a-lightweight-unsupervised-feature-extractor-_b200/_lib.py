@@ -62,6 +62,8 @@ SIGNATURES = {
     "b200_tracker_live_counts": (_I, [_P, _P, _P, _P]),
     "b200_tracker_step": (_I, [_P, _P, _P, _P, _P, _P, _P, _P]),
     "b200_tracker_step_host": (_I, [_P, _P, _P, _P, _P, _P, _P, _P]),
+    "b200_tracker_step_host_async": (_I, [_P, _P, _P, _P, _P, _P, ctypes.POINTER(ctypes.c_int64), _P]),
+    "b200_tracker_step_result": (_I, [_P, ctypes.c_int64, _P]),
     "b200_tracker_predict_all": (_I, [_P, _I, _P]),
     "b200_tracker_mark_missed": (_I, [_P, _I, _P, _I, _P]),
     "b200_tracker_purge_dead": (_I, [_P, _I, _P]),

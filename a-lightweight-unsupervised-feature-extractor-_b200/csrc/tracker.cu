@@ -348,7 +348,10 @@ struct RowMin {
 //   flight), a shuffle reduction gives <bank_t, det>, lane t keeps the similarity of row t, then k rounds
 //   of warp-max give the top-k mean.  No shared memory and few registers, so every row of a 64-stream
 //   group is resident at once and the kernel can share SMs with ROI Align.
-constexpr int kCost1Warps = 4;
+#ifndef B200_COST1_WARPS
+#define B200_COST1_WARPS 4
+#endif
+constexpr int kCost1Warps = B200_COST1_WARPS;
 
 __device__ __forceinline__ unsigned fkey(float f) {                 // order-preserving float -> uint
     const unsigned b = __float_as_uint(f);
@@ -1002,11 +1005,16 @@ using namespace b200;
 struct b200_tracker {
     trk::Dev d;
     void* arena = nullptr;          // one device allocation holding state + scratch + inputs + result
-    void* pinned = nullptr;         // host staging for step_host (inputs then result)
-    size_t in_bytes = 0, res_bytes = 0;
+    static constexpr int kRing = 4;  // host staging slots: step_host_async may run this many steps ahead of their results
+    void* pinned = nullptr;         // host staging: kRing x (inputs then result)
+    size_t in_bytes = 0, res_bytes = 0, slot_bytes = 0;
+    cudaEvent_t done[kRing] = {};   // result of the step staged in slot i is on the host
+    long long ticket_of[kRing] = {-1, -1, -1, -1};
+    long long next_ticket = 0;
     int* in_ndet = nullptr; int* in_frame = nullptr; double* in_boxes = nullptr; double* in_confs = nullptr;
     float* in_embs = nullptr; int* dev_result = nullptr;
-    int ctl_threads = 256;              // CTA width of the per-stream control kernels (begin / assign)
+    int ctl_threads = 256;              // CTA width of the per-stream control kernels (assign)
+    int begin_threads = 256;            // CTA width of begin_kernel
     int cost_grid = 0, cost1_grid = 0, upd_grid = 0;   // persistent CTAs of the cost kernels (resident CTAs per SM x SMs)
     size_t assign_smem = 0;
     int smem_matrix_floats = 0;
@@ -1094,7 +1102,9 @@ extern "C" int b200_tracker_create(b200_tracker** out, int n_streams, int max_tr
     t->dev_result = reinterpret_cast<int*>(base + o_result);
     t->in_bytes = in_end - o_in;
     t->res_bytes = S * (size_t)d.res_stride * sizeof(int);
-    e = cudaMallocHost(&t->pinned, t->in_bytes + t->res_bytes + 256);
+    t->slot_bytes = ((t->in_bytes + 255) & ~(size_t)255) + ((t->res_bytes + 255) & ~(size_t)255);
+    e = cudaMallocHost(&t->pinned, t->slot_bytes * b200_tracker::kRing);
+    for (int i = 0; e == cudaSuccess && i < b200_tracker::kRing; ++i) e = cudaEventCreateWithFlags(&t->done[i], cudaEventDisableTiming);
     if (e != cudaSuccess) {
         cudaFree(t->arena);
         delete t;
@@ -1156,6 +1166,8 @@ extern "C" int b200_tracker_create(b200_tracker** out, int n_streams, int max_tr
 
 extern "C" void b200_tracker_destroy(b200_tracker* t) {
     if (!t) return;
+    for (int i = 0; i < b200_tracker::kRing; ++i)
+        if (t->done[i]) cudaEventDestroy(t->done[i]);
     cudaFreeHost(t->pinned);
     cudaFree(t->arena);
     delete t;
@@ -1197,7 +1209,7 @@ extern "C" int b200_tracker_step(b200_tracker* t, const int32_t* n_det, const do
     d.n_det = n_det; d.boxes = boxes; d.confs = confs; d.embs = embs; d.frame_id = frame_id; d.result = result;
     const size_t csm = cost::smem_bytes(d.HIST);
     const int cost_grid = t->cost_grid;
-    trk::begin_kernel<<<dim3(d.S, 2), t->ctl_threads, 0, st>>>(d);
+    trk::begin_kernel<<<dim3(d.S, 2), t->begin_threads, 0, st>>>(d);
     int rc = check_launch("trk begin_kernel");
     if (rc) return rc;
     // With a handful of streams the step is a chain of short, latency-bound kernels: launch the dependent ones
@@ -1229,13 +1241,19 @@ extern "C" int b200_tracker_step(b200_tracker* t, const int32_t* n_det, const do
     return B200_OK;
 }
 
-extern "C" int b200_tracker_step_host(b200_tracker* t, const int32_t* n_det_host, const double* boxes_host,
-                                      const double* confs_host, const float* embs_host, const int32_t* frame_id_host,
-                                      int32_t* result_host, void* stream) {
-    B200_REQUIRE(t && n_det_host && frame_id_host && result_host, "tracker_step_host: null pointer");
+// Host-buffer step, asynchronous: stages the detections in the next slot of a pinned ring, queues H2D copy, the step and
+// the D2H copy of the result table on `stream`, records the slot's event and returns a ticket.  b200_tracker_step_result
+// waits for that event only.  Up to kRing steps may be in flight; taking a slot whose result was never collected first
+// waits for it (its result is then lost to the caller).
+extern "C" int b200_tracker_step_host_async(b200_tracker* t, const int32_t* n_det_host, const double* boxes_host,
+                                            const double* confs_host, const float* embs_host,
+                                            const int32_t* frame_id_host, int64_t* ticket, void* stream) {
+    B200_REQUIRE(t && n_det_host && frame_id_host && ticket, "tracker_step_host_async: null pointer");
     cudaStream_t st = as_stream(stream);
     const trk::Dev& d = t->d;
-    char* pin = static_cast<char*>(t->pinned);
+    const int slot = (int)(t->next_ticket % b200_tracker::kRing);
+    if (t->ticket_of[slot] >= 0) B200_CUDA(cudaEventSynchronize(t->done[slot]));      // the DMA that last used this slot
+    char* pin = static_cast<char*>(t->pinned) + (size_t)slot * t->slot_bytes;
     char* dev_in = reinterpret_cast<char*>(t->in_ndet);
     auto host_of = [&](const void* dev_ptr) { return pin + (reinterpret_cast<const char*>(dev_ptr) - dev_in); };
     int* h_ndet = reinterpret_cast<int*>(host_of(t->in_ndet));
@@ -1243,13 +1261,23 @@ extern "C" int b200_tracker_step_host(b200_tracker* t, const int32_t* n_det_host
     double* h_boxes = reinterpret_cast<double*>(host_of(t->in_boxes));
     double* h_confs = reinterpret_cast<double*>(host_of(t->in_confs));
     float* h_embs = reinterpret_cast<float*>(host_of(t->in_embs));
+    bool dense = true;                               // every stream full: three large copies instead of 3 S small ones
     for (int s = 0; s < d.S; ++s) {
         const int n = n_det_host[s];
         B200_REQUIRE(n <= d.MD, "tracker_step_host: stream %d has %d detections, capacity %d", s, n, d.MD);
         h_ndet[s] = n;
         h_frame[s] = frame_id_host[s];
-        if (n > 0) {
-            B200_REQUIRE(boxes_host && confs_host && embs_host, "tracker_step_host: null detection arrays");
+        if (n != d.MD) dense = false;
+        if (n > 0) B200_REQUIRE(boxes_host && confs_host && embs_host, "tracker_step_host: null detection arrays");
+    }
+    if (dense) {
+        memcpy(h_boxes, boxes_host, sizeof(double) * 4 * (size_t)d.S * d.MD);
+        memcpy(h_confs, confs_host, sizeof(double) * (size_t)d.S * d.MD);
+        memcpy(h_embs, embs_host, sizeof(float) * 128 * (size_t)d.S * d.MD);
+    } else {
+        for (int s = 0; s < d.S; ++s) {
+            const int n = n_det_host[s];
+            if (n <= 0) continue;
             memcpy(h_boxes + (size_t)s * d.MD * 4, boxes_host + (size_t)s * d.MD * 4, sizeof(double) * 4 * n);
             memcpy(h_confs + (size_t)s * d.MD, confs_host + (size_t)s * d.MD, sizeof(double) * n);
             memcpy(h_embs + (size_t)s * d.MD * 128, embs_host + (size_t)s * d.MD * 128, sizeof(float) * 128 * n);
@@ -1260,9 +1288,32 @@ extern "C" int b200_tracker_step_host(b200_tracker* t, const int32_t* n_det_host
     if (rc) return rc;
     char* h_res = pin + ((t->in_bytes + 255) & ~(size_t)255);
     B200_CUDA(cudaMemcpyAsync(h_res, t->dev_result, t->res_bytes, cudaMemcpyDeviceToHost, st));
-    B200_CUDA(cudaStreamSynchronize(st));
-    memcpy(result_host, h_res, t->res_bytes);
+    B200_CUDA(cudaEventRecord(t->done[slot], st));
+    t->ticket_of[slot] = t->next_ticket;
+    *ticket = t->next_ticket++;
     return B200_OK;
+}
+
+extern "C" int b200_tracker_step_result(b200_tracker* t, int64_t ticket, int32_t* result_host) {
+    B200_REQUIRE(t && result_host, "tracker_step_result: null pointer");
+    const int slot = (int)(ticket % b200_tracker::kRing);
+    B200_REQUIRE(ticket >= 0 && t->ticket_of[slot] == ticket, "tracker_step_result: ticket %lld is not in flight (at most %d steps may be pending)",
+                 (long long)ticket, b200_tracker::kRing);
+    B200_CUDA(cudaEventSynchronize(t->done[slot]));
+    const char* pin = static_cast<const char*>(t->pinned) + (size_t)slot * t->slot_bytes;
+    memcpy(result_host, pin + ((t->in_bytes + 255) & ~(size_t)255), t->res_bytes);
+    t->ticket_of[slot] = -1;
+    return B200_OK;
+}
+
+extern "C" int b200_tracker_step_host(b200_tracker* t, const int32_t* n_det_host, const double* boxes_host,
+                                      const double* confs_host, const float* embs_host, const int32_t* frame_id_host,
+                                      int32_t* result_host, void* stream) {
+    B200_REQUIRE(result_host, "tracker_step_host: null pointer");
+    int64_t ticket = -1;
+    const int rc = b200_tracker_step_host_async(t, n_det_host, boxes_host, confs_host, embs_host, frame_id_host, &ticket, stream);
+    if (rc) return rc;
+    return b200_tracker_step_result(t, ticket, result_host);
 }
 
 // ---- step-by-step operations (host arrays in, synchronous) ----------------------------------------------------------

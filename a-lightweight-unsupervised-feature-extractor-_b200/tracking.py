@@ -76,9 +76,12 @@ class MultiStreamTracker:
         self._create(int(max_tracks), int(max_dets))
         self.n_live = np.zeros(self.S, dtype=np.int64)
         self._n_live_stale = False                 # set by step_device: the host copy of the live counts is out of date
+        self._pending = []                         # StepHandles of step_async calls whose result has not been collected
+        self._pending_births = np.zeros(self.S, dtype=np.int64)
 
     def n_live_now(self) -> np.ndarray:
         """Live tracks per stream as of the work queued so far (re-read from the device after device-side steps)."""
+        self.drain()
         if self._n_live_stale:
             n = np.zeros(self.S, np.int32)
             with torch.cuda.device(self.device):
@@ -99,6 +102,7 @@ class MultiStreamTracker:
 
     def grow(self, max_tracks: Optional[int] = None, max_dets: Optional[int] = None):
         """Migrates every stream's state into a handle with larger capacities (export -> create -> import)."""
+        self.drain()
         snaps = [self.export(s) for s in range(self.S)]
         old = self._h
         self._create(max(self.max_tracks, int(max_tracks or 0)), max(self.max_dets, int(max_dets or 0)))
@@ -143,39 +147,47 @@ class MultiStreamTracker:
         n_det [S], boxes [S,max_dets,4] float64 xyxy, confs [S,max_dets] float64, embs [S,max_dets,128] float32,
         frame_ids [S].  Returns the int32 result table [S, stride] (``decode`` turns a row into the reference's
         return value); raises ValueError where scipy would (NaN / infeasible cost matrix, hung.py:28)."""
+        return self.step_async(n_det, boxes, confs, embs, frame_ids).result()
+
+    def step_async(self, n_det, boxes, confs, embs, frame_ids) -> "StepHandle":
+        """``step`` without the wait: uploads the detections, queues the step and the download of the result table on the
+        current CUDA stream and returns at once; ``handle.result()`` blocks until THAT step is on the host and returns
+        (or raises) exactly what ``step`` would.  The reference's consumer is a queue (tracking.py:329): a caller can
+        queue frame t+1 before it looks at the result of frame t.  At most four steps may be pending; results must be
+        collected in order."""
         n_det = np.ascontiguousarray(n_det, dtype=np.int32).reshape(self.S)
         frame_ids = np.ascontiguousarray(frame_ids, dtype=np.int32).reshape(self.S)
         boxes = np.ascontiguousarray(boxes, dtype=np.float64).reshape(self.S, self.max_dets, 4)
         confs = np.ascontiguousarray(confs, dtype=np.float64).reshape(self.S, self.max_dets)
         embs = np.ascontiguousarray(embs, dtype=np.float32).reshape(self.S, self.max_dets, 128)
-        need = int((self.n_live_now() + np.maximum(n_det, 0)).max())
-        if need > self.max_tracks:                     # the reference is unbounded: migrate to a larger handle
+        # capacity: live tracks are only known up to the last collected result; every pending step may have added
+        # all of its detections
+        bound = self.n_live + self._pending_births + np.maximum(n_det, 0)
+        if int(bound.max()) > self.max_tracks and (self._pending or self._n_live_stale):
+            self.drain()
+            bound = self.n_live_now() + np.maximum(n_det, 0)
+        if int(bound.max()) > self.max_tracks:         # the reference is unbounded: migrate to a larger handle
             if not self.auto_grow:
                 raise _lib.B200Error("tracker capacity: live tracks + detections could exceed max_tracks=%d; "
                                      "construct the tracker with a larger max_tracks" % self.max_tracks)
-            self.grow(max_tracks=max(need, 2 * self.max_tracks))
+            self.grow(max_tracks=max(int(bound.max()), 2 * self.max_tracks))
+        if len(self._pending) >= 4:
+            raise _lib.B200Error("step_async: four steps are already pending; collect their results first")
         p = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+        ticket = ctypes.c_int64(-1)
         with torch.cuda.device(self.device):
-            rc = _lib.lib().b200_tracker_step_host(self._h, p(n_det), p(boxes), p(confs), p(embs), p(frame_ids),
-                                                   p(self._res), _lib.stream_ptr(self.device))
+            rc = _lib.lib().b200_tracker_step_host_async(self._h, p(n_det), p(boxes), p(confs), p(embs), p(frame_ids),
+                                                         ctypes.byref(ticket), _lib.stream_ptr(self.device))
         _lib.check(rc)
-        self.n_live[:] = self._res[:, R_NLIVE]
-        # A failing stream does not lose the others: the table (self.last_result) is complete before anything is raised,
-        # and the failing stream's state is what the reference leaves behind when scipy raises (predict only).
-        self.last_result = self._res
-        bad = np.nonzero(self._res[:, R_STATUS])[0]
-        if len(bad):
-            st = int(self._res[bad[0], R_STATUS])
-            if st == _lib.ENUMERIC:
-                raise ValueError("matrix contains invalid numeric entries (stream %d)" % bad[0])
-            if st == _lib.EINFEASIBLE:
-                raise ValueError("cost matrix is infeasible (stream %d)" % bad[0])
-            if st == _lib.ECAPACITY:
-                raise _lib.B200Error("tracker capacity exceeded on stream %d: births were dropped because live tracks + "
-                                     "detections exceeded max_tracks=%d (device-side steps do not grow the handle; "
-                                     "call grow() or construct with a larger max_tracks)" % (bad[0], self.max_tracks))
-            raise _lib.B200Error("tracker step failed on stream %d with status %d" % (bad[0], st))
-        return self._res
+        h = StepHandle(self, int(ticket.value), np.maximum(n_det, 0).astype(np.int64))
+        self._pending.append(h)
+        self._pending_births = self._pending_births + h._births
+        return h
+
+    def drain(self):
+        """Waits for every pending ``step_async`` (their results stay available on their handles)."""
+        for h in list(self._pending):
+            h._collect()
 
     # -- device-resident inputs, asynchronous on the current stream (no read-back) ------------------
     def step_device(self, n_det: torch.Tensor, boxes: torch.Tensor, confs: torch.Tensor, embs: torch.Tensor,
@@ -225,6 +237,63 @@ class MultiStreamTracker:
         out = {k: v[:n] for k, v in out.items()}
         out["next_id"] = int(nxt.value)
         return out
+
+
+class StepHandle:
+    """A queued ``MultiStreamTracker.step_async``; ``result()`` is what ``step`` would have returned."""
+
+    def __init__(self, ms: MultiStreamTracker, ticket: int, births: np.ndarray):
+        self._ms, self._ticket, self._births = ms, ticket, births
+        self._res, self._error = None, None
+
+    def _collect(self):
+        ms = self._ms
+        if self._res is not None or self._error is not None:
+            return
+        if not ms._pending or ms._pending[0] is not self:
+            for h in list(ms._pending):                # results come back in queue order
+                if h is self:
+                    break
+                h._collect()
+        res = np.zeros((ms.S, ms.stride), dtype=np.int32)
+        with torch.cuda.device(ms.device):
+            rc = _lib.lib().b200_tracker_step_result(ms._h, self._ticket, res.ctypes.data_as(ctypes.c_void_p))
+        ms._pending.remove(self)
+        ms._pending_births = ms._pending_births - self._births
+        try:
+            _lib.check(rc)
+        except Exception as exc:                       # noqa: BLE001
+            self._error = exc
+            return
+        self._res = res
+        ms._res = res
+        ms.n_live[:] = res[:, R_NLIVE]
+        # A failing stream does not lose the others: the table (ms.last_result) is complete before anything is raised,
+        # and the failing stream's state is what the reference leaves behind when scipy raises (predict only).
+        ms.last_result = res
+        bad = np.nonzero(res[:, R_STATUS])[0]
+        if len(bad):
+            st = int(res[bad[0], R_STATUS])
+            if st == _lib.ENUMERIC:
+                self._error = ValueError("matrix contains invalid numeric entries (stream %d)" % bad[0])
+            elif st == _lib.EINFEASIBLE:
+                self._error = ValueError("cost matrix is infeasible (stream %d)" % bad[0])
+            elif st == _lib.ECAPACITY:
+                self._error = _lib.B200Error(
+                    "tracker capacity exceeded on stream %d: births were dropped because live tracks + detections "
+                    "exceeded max_tracks=%d (device-side steps do not grow the handle; call grow() or construct with a "
+                    "larger max_tracks)" % (bad[0], ms.max_tracks))
+            else:
+                self._error = _lib.B200Error("tracker step failed on stream %d with status %d" % (bad[0], st))
+
+    def done(self) -> bool:
+        return self._res is not None or self._error is not None
+
+    def result(self) -> np.ndarray:
+        self._collect()
+        if self._error is not None:
+            raise self._error
+        return self._res
 
 
 class TrackView:
@@ -313,7 +382,8 @@ class Tracking:
             if not self._ms.auto_grow:
                 raise ValueError("%d detections exceed max_dets=%d" % (N, self._ms.max_dets))
             self._ms.grow(max_dets=max(N, 2 * self._ms.max_dets))
-            MD = self._ms.max_dets
+        MD = self._ms.max_dets
+        if self._boxes.shape[1] != MD:                 # the handle has grown (here or in one of the step-by-step methods)
             self._boxes, self._confs = np.zeros((1, MD, 4), np.float64), np.zeros((1, MD), np.float64)
             self._embs = np.zeros((1, MD, 128), np.float32)
         self._boxes[0, :N] = boxes

@@ -194,6 +194,14 @@ int  b200_tracker_update_matched(b200_tracker* t, int stream_idx, const int32_t*
                                  int n_det, int frame_id, double ema_alpha, double conf_update_min,
                                  double cost_update_max, double maha_thr, void* stream);
 
+/* The same step without the wait (the reference's consumer is a queue, tracking.py:329): stages the inputs in a
+ * pinned ring inside the handle, queues upload + step + download on `stream` and returns a ticket; at most four
+ * steps may be in flight.  b200_tracker_step_result blocks until THAT step's result table is on the host and copies
+ * it out.  b200_tracker_step_host is exactly step_host_async followed by step_result. */
+int  b200_tracker_step_host_async(b200_tracker* t, const int32_t* n_det_host, const double* boxes_host,
+                                  const double* confs_host, const float* embs_host,
+                                  const int32_t* frame_id_host, int64_t* ticket, void* stream);
+int  b200_tracker_step_result(b200_tracker* t, int64_t ticket, int32_t* result_host);
 /* Copies one stream's live tracks (ascending track id) to host arrays sized for max_tracks;
  * any pointer may be NULL.  bank is [n, hist_max, 128] oldest-first.  Returns n_live or <0. */
 int  b200_tracker_export(b200_tracker* t, int stream_idx, int32_t* ids, double* x, double* P,

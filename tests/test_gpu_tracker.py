@@ -368,6 +368,62 @@ def test_step_device_vs_oracle():
     assert ms.n_live_now().tolist() == [len(r.tracks) for r in refs]
 
 
+def test_step_async_matches_step_and_defers_errors():
+    """MultiStreamTracker.step_async: up to four steps queued ahead of their results; every result equals the oracle's,
+    results come back in order, a NaN frame raises at .result() of THAT step only and the stream carries on."""
+    cfg = dict(SHIPPED_CONF, lost_reid_after=5, max_age=15)
+    S, MD, F = 3, 32, 30
+    ms = MultiStreamTracker(S, cfg, max_tracks=96, max_dets=MD)
+    refs = [tracker_ref.TrackerRef(cfg) for _ in range(S)]
+    scenes = [synth.Scene(60 + s, 12 + 5 * s, 720, 1280, drop=0.15, churn=0.15, churn_every=6) for s in range(S)]
+    frames, want = [], []
+    for f in range(F):
+        n_det = np.zeros(S, np.int32)
+        boxes, confs, embs = np.zeros((S, MD, 4)), np.zeros((S, MD)), np.zeros((S, MD, 128), np.float32)
+        w = []
+        for s in range(S):
+            obj = scenes[s].step()
+            n = len(obj["bboxes"])
+            n_det[s] = n
+            boxes[s, :n], confs[s, :n], embs[s, :n] = obj["bboxes"], obj["confs"], np.stack(obj["embs"])
+            if f == 20 and s == 1:
+                embs[s, 0] = np.nan                       # scipy raises for this stream at this frame ...
+                obj = dict(obj, embs=[np.full(128, np.nan, np.float32)] + obj["embs"][1:])
+                with pytest.raises(ValueError):
+                    refs[s].update(obj)
+                w.append(None)
+            else:
+                w.append(refs[s].update(obj))
+        frames.append((n_det, boxes, confs, embs))
+        want.append(w)
+    handles = []
+    for f in range(F):
+        handles.append(ms.step_async(*frames[f], np.full(S, f)))
+        if len(handles) == 4:                             # the ring is full: collect the oldest
+            _check_async(ms, handles.pop(0), want[f - 3], f - 3)
+    with pytest.raises(_lib.B200Error):
+        pass_through = [ms.step_async(*frames[0], np.full(S, 99)) for _ in range(5)]  # noqa: F841  (a fifth pending step)
+    ms.drain()
+    base = F - len(handles)
+    for k, h in enumerate(handles):
+        _check_async(ms, h, want[base + k], base + k)
+
+
+def _check_async(ms, handle, want, f):
+    if any(w is None for w in want):
+        with pytest.raises(ValueError):
+            handle.result()
+        res = ms.last_result                              # ... and the other streams' rows are still there
+    else:
+        res = handle.result()
+    for s, w in enumerate(want):
+        if w is None:
+            assert int(res[s, 5]) != 0
+            continue
+        got = ms.decode(res[s])
+        assert got[0] == w[0] and got[1] == w[1] and got[2] == w[2], (f, s)
+
+
 @pytest.mark.parametrize("seed", range(10))
 def test_tracker_fuzz_vs_oracle(seed):
     """Randomised differential test: random hyper-parameters (including degenerate ones: one-row banks,

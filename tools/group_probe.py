@@ -12,7 +12,7 @@ W, K = 40, 100
 dev = torch.device("cuda", 0)
 torch.cuda.set_device(0)
 out = {}
-for mode in ("roi_only", "assoc_only", "serial", "overlap_prio"):
+for mode in os.environ.get("MODES", "roi_only,assoc_only,serial,overlap_prio").split(","):
     g = bench.StreamGroup(bench.WORKLOADS[WL], S, W + K, 0, dev, channels_last=CL)
     if mode == "serial":
         g.sB = g.sA
