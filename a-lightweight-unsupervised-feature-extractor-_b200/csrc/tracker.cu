@@ -162,14 +162,16 @@ __device__ inline void enqueue_cost_work(int2* work, int* counter, int s, int M,
 }
 
 // ---- detections: unit embeddings (:167-168), z (KalmanFilter.py:5-16), float32 boxes/confs (all threads of a CTA) ----
-__device__ inline void prep_detections(const Dev& d, int s, int n) {
+// part / nparts: the CTAs of one stream share the work (front_kernel); 0 / 1 = the whole stream.
+__device__ inline void prep_detections(const Dev& d, int s, int n, int part = 0, int nparts = 1) {
     const size_t db = (size_t)s * d.MD;
     const int tid = threadIdx.x;
-    for (int j = tid >> 5; j < n; j += blockDim.x >> 5) {
+    const int nw = blockDim.x >> 5, nt = blockDim.x;
+    for (int j = part * nw + (tid >> 5); j < n; j += nparts * nw) {
         const float4 v = reinterpret_cast<const float4*>(d.embs + (db + j) * cost::kD)[tid & 31];
         reinterpret_cast<float4*>(d.det_unit + (db + j) * cost::kD)[tid & 31] = cost::unit_row(v);
     }
-    for (int j = tid; j < n; j += blockDim.x) {
+    for (int j = part * nt + tid; j < n; j += nparts * nt) {
         double b[4];
         float z[4];
 #pragma unroll
@@ -265,48 +267,53 @@ __global__ void __launch_bounds__(kThreads) begin_kernel(Dev d) {
 // ------------------------------------------------------------------------------------------------
 // ReID-only stage (:552-558): rows_reid x leftover detections, appearance cost only, dense tiles (bank and
 // 64 detection rows staged in shared memory, see assoc_cost.cuh).  Persistent CTAs over queued work items.
+// One (long-lost row r, tile of 64 leftover detections starting at j0) item of stream s; every thread of a
+// cost::kThreads-wide CTA must call.  smem: cost::smem_bytes(HIST) bytes; s_idx: cost::kTileN ints of shared memory.
+__device__ inline void cost2_item(const Dev& d, int s, int r, int j0, float* smem, int* s_idx) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int N = d.cnt[s * kHdr + C_NU];
+    const size_t sb = (size_t)s * d.MT, db = (size_t)s * d.MD;
+    const size_t slot = sb + d.rows_reid[sb + r];
+    int T = d.bank_len[slot];
+    const float* rows = d.bank + slot * d.HIST * cost::kD;
+    if (T <= 0) { rows = d.ema + slot * cost::kD; T = 1; }        // :180-182 fallback to the EMA
+    if (tid < cost::kTileN) {                                      // leftover detections are gathered through ud1
+        const int j = j0 + tid;
+        s_idx[tid] = j < N ? d.ud1[db + j] : 0;
+    }
+    __syncthreads();
+    const int tc = cost::bank_cap(T);
+    float* sBank = smem;
+    float* sDet = sBank + tc * cost::kD;
+    float* sSim = sDet + cost::kTileN * cost::kDetStride;
+    for (int t = warp; t < tc; t += cost::kThreads / 32) {
+        float4 v = make_float4(0, 0, 0, 0);
+        if (t < T) v = cost::unit_row(reinterpret_cast<const float4*>(rows + (size_t)t * cost::kD)[lane]);
+        reinterpret_cast<float4*>(sBank + t * cost::kD)[lane] = v;
+    }
+    for (int j = warp; j < cost::kTileN; j += cost::kThreads / 32) {
+        float4 v = make_float4(0, 0, 0, 0);
+        if (j0 + j < N) v = reinterpret_cast<const float4*>(d.det_unit + (db + s_idx[j]) * cost::kD)[lane];
+        reinterpret_cast<float4*>(sDet + j * cost::kDetStride)[lane] = v;
+    }
+    __syncthreads();
+    const float c_app = cost::sims_and_topk(sBank, sDet, sSim, tc, T, d.topk, true);   // ends with a barrier
+    const int j = j0 + tid;
+    if (tid < cost::kTileN && j < N) {
+        d.C2[(sb + r) * d.MD + j] = c_app;
+        d.C2T[(db + j) * d.MT + r] = c_app;
+    }
+}
+
 __global__ void __launch_bounds__(cost::kThreads) cost2_kernel(Dev d) {
     Span span((d.frame_id[0] & 7) * 6 + 3);
     TRK_PDL_PROLOGUE();
     extern __shared__ __align__(16) float smem[];
     __shared__ int s_idx[cost::kTileN];
     const int total = d.wcount[1];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     for (int wi = blockIdx.x; wi < total; wi += gridDim.x) {        // uniform trip count per CTA
         const int2 item = d.work2[wi];
-        const int s = item.x, r = item.y >> 6, j0 = (item.y & 63) * cost::kTileN;
-        const int N = d.cnt[s * kHdr + C_NU];
-        const size_t sb = (size_t)s * d.MT, db = (size_t)s * d.MD;
-        const size_t slot = sb + d.rows_reid[sb + r];
-        int T = d.bank_len[slot];
-        const float* rows = d.bank + slot * d.HIST * cost::kD;
-        if (T <= 0) { rows = d.ema + slot * cost::kD; T = 1; }        // :180-182 fallback to the EMA
-        if (tid < cost::kTileN) {                                      // leftover detections are gathered through ud1
-            const int j = j0 + tid;
-            s_idx[tid] = j < N ? d.ud1[db + j] : 0;
-        }
-        __syncthreads();
-        const int tc = cost::bank_cap(T);
-        float* sBank = smem;
-        float* sDet = sBank + tc * cost::kD;
-        float* sSim = sDet + cost::kTileN * cost::kDetStride;
-        for (int t = warp; t < tc; t += cost::kThreads / 32) {
-            float4 v = make_float4(0, 0, 0, 0);
-            if (t < T) v = cost::unit_row(reinterpret_cast<const float4*>(rows + (size_t)t * cost::kD)[lane]);
-            reinterpret_cast<float4*>(sBank + t * cost::kD)[lane] = v;
-        }
-        for (int j = warp; j < cost::kTileN; j += cost::kThreads / 32) {
-            float4 v = make_float4(0, 0, 0, 0);
-            if (j0 + j < N) v = reinterpret_cast<const float4*>(d.det_unit + (db + s_idx[j]) * cost::kD)[lane];
-            reinterpret_cast<float4*>(sDet + j * cost::kDetStride)[lane] = v;
-        }
-        __syncthreads();
-        const float c_app = cost::sims_and_topk(sBank, sDet, sSim, tc, T, d.topk, true);   // ends with a barrier
-        const int j = j0 + tid;
-        if (tid < cost::kTileN && j < N) {
-            d.C2[(sb + r) * d.MD + j] = c_app;
-            d.C2T[(db + j) * d.MT + r] = c_app;
-        }
+        cost2_item(d, item.x, item.y >> 6, (item.y & 63) * cost::kTileN, smem, s_idx);
     }
 }
 
@@ -468,106 +475,136 @@ __device__ __forceinline__ void transpose_reduce32(float (&p)[32]) {
 // Stage-1 cost for hist_max <= 32 (the shipped 30): same algorithm as cost1_sparse_kernel, but the row's
 // whole bank is read once into registers (one global round trip, reused by every surviving detection) and
 // the 32 dot products of a detection are reduced together (transpose_reduce32).
+// One track row of the stage-1 cost (one warp): gate for every detection, contraction for the survivors, C / C^T / row
+// summary written.  FLY = false: the detection-side inputs (z, float32 boxes / confidences, unit embeddings) were
+// prepared by begin_kernel; FLY = true (front_kernel): they are derived here from the caller's arrays with the same
+// functions, value for value.
+template <bool FLY>
+__device__ __forceinline__ void cost1_row32(const Dev& d, int s, int r, size_t slot, int N, int lane) {
+    const float kNegInf = -__int_as_float(0x7f800000);
+    const size_t sb = (size_t)s * d.MT, db = (size_t)s * d.MD;
+    int T = d.bank_len[slot];
+    const float* rows = d.bank + slot * d.HIST * cost::kD;
+    if (T <= 0) { rows = d.ema + slot * cost::kD; T = 1; }        // :180-182 fallback to the EMA
+    const int kk = min(d.topk, T);
+    double SI[16], xs[4];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) SI[k] = d.gate_SI[slot * 16 + k];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) xs[k] = d.kf_x[slot * 8 + k];
+    const int stage = d.kf_stage[slot];
+    float pb[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) pb[k] = d.prev_boxf[slot * 4 + k];
+    const float pconf = d.prev_conff[slot];
+    float4 bv[32];
+    float inv = 0.0f;                          // 1 / (|bank_lane| + 1e-12), :188-189
+    bool have_bank = false;
+    RowMin rmin;
+    for (int j0 = 0; j0 < N; j0 += 32) {
+        const int j = j0 + lane;
+        bool alive = false;
+        float zl[4], bf[4];
+        float cf = 0.0f;
+        if (j < N) {
+            if (FLY) {
+                double b[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { b[k] = d.boxes[(db + j) * 4 + k]; bf[k] = (float)b[k]; }
+                kf::box_to_z(b, zl);
+                cf = (float)d.confs[db + j];
+                alive = !(kf::gate_d2(SI, xs, stage, zl) > d.maha_thr);                     // :335
+            } else {
+                alive = !(kf::gate_d2(SI, xs, stage, d.det_z + (db + j) * 4) > d.maha_thr);   // :335
+            }
+        }
+        unsigned todo = __ballot_sync(0xffffffffu, alive);
+        float c_app = 0.0f;
+        if (todo && !have_bank) {
+            float q[32];
+#pragma unroll
+            for (int t = 0; t < 32; ++t)
+                bv[t] = t < T ? reinterpret_cast<const float4*>(rows + (size_t)t * cost::kD)[lane] : make_float4(0, 0, 0, 0);
+#pragma unroll
+            for (int t = 0; t < 32; ++t) {
+                float a = bv[t].x * bv[t].x;
+                a = fmaf(bv[t].y, bv[t].y, a); a = fmaf(bv[t].z, bv[t].z, a); a = fmaf(bv[t].w, bv[t].w, a);
+                q[t] = a;
+            }
+            transpose_reduce32(q);
+            inv = __fdiv_rn(1.0f, __fadd_rn(sqrtf(q[0]), 1e-12f));
+            have_bank = true;
+        }
+        while (todo) {
+            const int jl = __ffs(todo) - 1;
+            todo &= todo - 1;
+            float4 dv;
+            if (FLY) dv = cost::unit_row(reinterpret_cast<const float4*>(d.embs + (db + j0 + jl) * cost::kD)[lane]);
+            else dv = reinterpret_cast<const float4*>(d.det_unit + (db + j0 + jl) * cost::kD)[lane];
+            float p[32];
+#pragma unroll
+            for (int t = 0; t < 32; ++t) {
+                float a = bv[t].x * dv.x;
+                a = fmaf(bv[t].y, dv.y, a); a = fmaf(bv[t].z, dv.z, a); a = fmaf(bv[t].w, dv.w, a);
+                p[t] = a;
+            }
+            transpose_reduce32(p);
+            float sim = lane < T ? p[0] * inv : kNegInf;        // <bank_lane, det> of unit vectors
+            float sum = 0.0f;                                   // top-k mean, largest first (:196-202)
+            for (int q = 0; q < kk; ++q) {
+                const unsigned m = __reduce_max_sync(0xffffffffu, fkey(sim));
+                const unsigned who = __ballot_sync(0xffffffffu, fkey(sim) == m);
+                if (lane == __ffs(who) - 1) sim = kNegInf;
+                const unsigned bits = m ^ ((m >> 31) ? 0x80000000u : 0xffffffffu);
+                sum = __fadd_rn(sum, __uint_as_float(bits));
+            }
+            const float ca = __fsub_rn(1.0f, __fdiv_rn(sum, (float)kk));
+            if (lane == jl) c_app = ca;
+        }
+        if (j < N) {
+            float total_c = 1e9f;
+            if (alive) {
+                if (FLY) total_c = cost::pair_cost(pb, bf, pconf, cf, d.pw, c_app).total;
+                else total_c = cost::pair_cost(pb, d.det_boxf + (db + j) * 4, pconf, d.det_conff[db + j], d.pw, c_app).total;
+            }
+            d.C1[(sb + r) * d.MD + j] = total_c;
+            d.C1T[(db + j) * d.MT + r] = total_c;
+            rmin.see(total_c, j);
+        }
+    }
+    rmin.finish(d.row_fc + sb + r, d.row_fv + sb + r, lane);
+}
+
 __global__ void __launch_bounds__(kCost1Warps * 32, 2) cost1_sparse32_kernel(Dev d) {
     Span span((d.frame_id[0] & 7) * 6 + 1);
     TRK_PDL_PROLOGUE();
     const int total = d.wcount[0];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const float kNegInf = -__int_as_float(0x7f800000);
     for (int wi = blockIdx.x * kCost1Warps + warp; wi < total; wi += gridDim.x * kCost1Warps) {
         const int2 item = d.work1[wi];
         const int s = item.x, r = item.y >> 6;
-        const int N = d.n_det[s];
-        const size_t sb = (size_t)s * d.MT, db = (size_t)s * d.MD;
-        const size_t slot = sb + d.rows_main[sb + r];
-        int T = d.bank_len[slot];
-        const float* rows = d.bank + slot * d.HIST * cost::kD;
-        if (T <= 0) { rows = d.ema + slot * cost::kD; T = 1; }        // :180-182 fallback to the EMA
-        const int kk = min(d.topk, T);
-        double SI[16], xs[4];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) SI[k] = d.gate_SI[slot * 16 + k];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) xs[k] = d.kf_x[slot * 8 + k];
-        const int stage = d.kf_stage[slot];
-        float pb[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) pb[k] = d.prev_boxf[slot * 4 + k];
-        const float pconf = d.prev_conff[slot];
-        float4 bv[32];
-        float inv = 0.0f;                          // 1 / (|bank_lane| + 1e-12), :188-189
-        bool have_bank = false;
-        RowMin rmin;
-        for (int j0 = 0; j0 < N; j0 += 32) {
-            const int j = j0 + lane;
-            bool alive = false;
-            if (j < N) alive = !(kf::gate_d2(SI, xs, stage, d.det_z + (db + j) * 4) > d.maha_thr);   // :335
-            unsigned todo = __ballot_sync(0xffffffffu, alive);
-            float c_app = 0.0f;
-            if (todo && !have_bank) {
-                float q[32];
-#pragma unroll
-                for (int t = 0; t < 32; ++t)
-                    bv[t] = t < T ? reinterpret_cast<const float4*>(rows + (size_t)t * cost::kD)[lane] : make_float4(0, 0, 0, 0);
-#pragma unroll
-                for (int t = 0; t < 32; ++t) {
-                    float a = bv[t].x * bv[t].x;
-                    a = fmaf(bv[t].y, bv[t].y, a); a = fmaf(bv[t].z, bv[t].z, a); a = fmaf(bv[t].w, bv[t].w, a);
-                    q[t] = a;
-                }
-                transpose_reduce32(q);
-                inv = __fdiv_rn(1.0f, __fadd_rn(sqrtf(q[0]), 1e-12f));
-                have_bank = true;
-            }
-            while (todo) {
-                const int jl = __ffs(todo) - 1;
-                todo &= todo - 1;
-                const float4 dv = reinterpret_cast<const float4*>(d.det_unit + (db + j0 + jl) * cost::kD)[lane];
-                float p[32];
-#pragma unroll
-                for (int t = 0; t < 32; ++t) {
-                    float a = bv[t].x * dv.x;
-                    a = fmaf(bv[t].y, dv.y, a); a = fmaf(bv[t].z, dv.z, a); a = fmaf(bv[t].w, dv.w, a);
-                    p[t] = a;
-                }
-                transpose_reduce32(p);
-                float sim = lane < T ? p[0] * inv : kNegInf;        // <bank_lane, det> of unit vectors
-                float sum = 0.0f;                                   // top-k mean, largest first (:196-202)
-                for (int q = 0; q < kk; ++q) {
-                    const unsigned m = __reduce_max_sync(0xffffffffu, fkey(sim));
-                    const unsigned who = __ballot_sync(0xffffffffu, fkey(sim) == m);
-                    if (lane == __ffs(who) - 1) sim = kNegInf;
-                    const unsigned bits = m ^ ((m >> 31) ? 0x80000000u : 0xffffffffu);
-                    sum = __fadd_rn(sum, __uint_as_float(bits));
-                }
-                const float ca = __fsub_rn(1.0f, __fdiv_rn(sum, (float)kk));
-                if (lane == jl) c_app = ca;
-            }
-            if (j < N) {
-                float total_c = 1e9f;
-                if (alive)
-                    total_c = cost::pair_cost(pb, d.det_boxf + (db + j) * 4, pconf, d.det_conff[db + j], d.pw, c_app).total;
-                d.C1[(sb + r) * d.MD + j] = total_c;
-                d.C1T[(db + j) * d.MT + r] = total_c;
-                rmin.see(total_c, j);
-            }
-        }
-        rmin.finish(d.row_fc + sb + r, d.row_fv + sb + r, lane);
+        const size_t sb = (size_t)s * d.MT;
+        cost1_row32<false>(d, s, r, sb + d.rows_main[sb + r], d.n_det[s], lane);
     }
 }
 
 // update_matched (:375-448), part 1, inside the assignment kernel: the bookkeeping that later steps of the same
 // frame depend on (:403-415: last box / conf / frame, age, miss reset, match cost), and one queue entry per
 // match for update_kernel, which does the arithmetic (Kalman update, posterior gate, EMA, bank push).
+// queue_base >= 0: the entries go to upd_*[queue_base ..] (the fused path keeps one queue per stream); < 0: they are
+// appended to the step's global queue (update_kernel).
 __device__ inline void note_matches(const Dev& d, int s, int nm, const int* rows, const float* C, int ldc,
-                                    const int* m_col, int reid_stage, int* scratch) {
+                                    const int* m_col, int reid_stage, int* scratch, int queue_base = -1) {
     if (nm <= 0) return;                                          // uniform across the CTA
     const size_t sb = (size_t)s * d.MT, db = (size_t)s * d.MD;
     const int frame = d.frame_id[s];
-    __syncthreads();
-    if (threadIdx.x == 0) scratch[0] = atomicAdd(d.wcount + 2, nm);
-    __syncthreads();
-    const int base = scratch[0];
+    int base = queue_base;
+    if (queue_base < 0) {
+        __syncthreads();
+        if (threadIdx.x == 0) scratch[0] = atomicAdd(d.wcount + 2, nm);
+        __syncthreads();
+        base = scratch[0];
+    }
     for (int qd = threadIdx.x; qd < nm; qd += blockDim.x) {
         const int r = d.m_row[sb + qd], j = d.m_det[sb + qd];
         const size_t slot = sb + rows[r];
@@ -591,18 +628,16 @@ __device__ inline void note_matches(const Dev& d, int s, int nm, const int* rows
 // gate (:424-426), then the warp applies the EMA and pushes the bank rows of those four matches (:429-448).
 constexpr int kUpdWarps = 4;
 
-__global__ void __launch_bounds__(kUpdWarps * 32) update_kernel(Dev d) {
-    Span span((d.frame_id[0] & 7) * 6 + 5);
-    TRK_PDL_PROLOGUE();
-    __shared__ double scratch[kUpdWarps * 4 * 96];
-    const int total = d.wcount[2];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, sub = lane & 7, grp = lane >> 3;
-    double* sP = scratch + (size_t)(warp * 4 + grp) * 96;
+// Queue entries first .. first + total - 1, four per warp and pass; `wq` = index of this warp among the `nwq` warps that
+// share the range; scratch: 4 x 96 doubles of shared memory private to the warp.
+__device__ __forceinline__ void update_entries(const Dev& d, int first, int total, int wq, int nwq, double* scratch) {
+    const int lane = threadIdx.x & 31, sub = lane & 7, grp = lane >> 3;
+    double* sP = scratch + (size_t)grp * 96;
     double* sK = sP + 64;
     const float rdiag[4] = {1.f, 1.f, 1.f, 1.f};                           // KalmanFilter.py:98-99
-    for (int w0 = (blockIdx.x * kUpdWarps + warp) * 4; w0 < total; w0 += gridDim.x * kUpdWarps * 4) {
-        const int idx = w0 + grp;
-        const bool on = idx < total;
+    for (int w0 = wq * 4; w0 < total; w0 += nwq * 4) {
+        const int idx = first + w0 + grp;
+        const bool on = w0 + grp < total;
         size_t slot = 0, det = 0;
         int st = -1, reid = 0;
         double c = 0.0, conf = 0.0;
@@ -672,6 +707,14 @@ __global__ void __launch_bounds__(kUpdWarps * 32) update_kernel(Dev d) {
     }
 }
 
+__global__ void __launch_bounds__(kUpdWarps * 32) update_kernel(Dev d) {
+    Span span((d.frame_id[0] & 7) * 6 + 5);
+    TRK_PDL_PROLOGUE();
+    __shared__ double scratch[kUpdWarps * 4 * 96];
+    const int warp = threadIdx.x >> 5;
+    update_entries(d, 0, d.wcount[2], blockIdx.x * kUpdWarps + warp, gridDim.x * kUpdWarps, scratch + (size_t)warp * 4 * 96);
+}
+
 // create_new_tracks (:362-373) for the detections listed in born[0..want) (already filtered by init_conf_min, in
 // order): free slots, Kalman initial state, creat_item (:98-139), ids next_id, next_id + 1, ...  All threads of the
 // CTA must call; returns the number of tracks created (fewer than `want` only when the handle is full, which is
@@ -726,17 +769,17 @@ __device__ inline int spawn_tracks(const Dev& d, int s, const int* born, int wan
 
 // hungarian_assign (hung.py:5-45) for this stream's matrix; fills m_row/m_det, marks misses.
 // Returns the number of matches; *n_unmatched_rows is the count appended to the unmatched list.
-template <int STAGE>
-__global__ void __launch_bounds__(kThreads) assign_kernel(Dev d, int smem_matrix_floats) {
-    Span span((d.frame_id[0] & 7) * 6 + (STAGE == 1 ? 2 : 4));
-    TRK_PDL_PROLOGUE();
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+// Returns true when stream s has nothing more to do in this step (idle / empty frame / the assignment failed / stage 2
+// done).  FUSED (back_kernel): both stages, the ReID cost and the updates of a stream run in ONE CTA, so nothing is queued
+// for other kernels and the matches go to the stream's own update queue.
+template <int STAGE, bool FUSED>
+__device__ inline bool assign_body(const Dev& d, int s, unsigned char* smem_raw, int smem_matrix_floats) {
     __shared__ int scratch[kThreads / 32];
     __shared__ int s_rc;
-    const int s = blockIdx.x, tid = threadIdx.x;
+    const int tid = threadIdx.x;
     int* cnt = d.cnt + s * kHdr;
     // both cost launches of this step are done: clear their queues for the next step
-    if (STAGE == 2 && s == 0 && tid == 0) { d.wcount[0] = 0; d.wcount[1] = 0; }
+    if (!FUSED && STAGE == 2 && s == 0 && tid == 0) { d.wcount[0] = 0; d.wcount[1] = 0; }
     int* hdr = d.hdr + s * kHdr;
     int* res = d.result + (size_t)s * d.res_stride;
     if (STAGE == 2 && cnt[C_MODE] == MODE_FAILED) {
@@ -747,9 +790,9 @@ __global__ void __launch_bounds__(kThreads) assign_kernel(Dev d, int smem_matrix
             res[R_NLIVE] = hdr[H_NLIVE]; res[R_NEXT] = hdr[H_NEXT]; res[R_STATUS] = cnt[C_STATUS];
             res[R_M1] = cnt[C_M1]; res[R_M2] = cnt[C_M2];
         }
-        return;
+        return true;
     }
-    if (cnt[C_MODE] != MODE_NORMAL) return;
+    if (cnt[C_MODE] != MODE_NORMAL) return true;
     const size_t sb = (size_t)s * d.MT, db = (size_t)s * d.MD;
     const int M = STAGE == 1 ? cnt[C_M1] : cnt[C_M2];
     const int N = STAGE == 1 ? d.n_det[s] : cnt[C_NU];
@@ -804,7 +847,7 @@ __global__ void __launch_bounds__(kThreads) assign_kernel(Dev d, int smem_matrix
                 out_ut[ut0 + pos] = d.tid[slot];
             }, scratch);
             __syncthreads();
-            note_matches(d, s, n_match, rows, C, d.MD, m_col, STAGE == 2, scratch);
+            note_matches(d, s, n_match, rows, C, d.MD, m_col, STAGE == 2, scratch, FUSED ? (int)sb + match0 : -1);
         }
     } else if (M > 0) {                             // no detections left for these rows: all missed
         for (int r = tid; r < M; r += blockDim.x) {
@@ -819,15 +862,16 @@ __global__ void __launch_bounds__(kThreads) assign_kernel(Dev d, int smem_matrix
     if (STAGE == 1) {
         if (failed) {                               // nothing else happens to this stream in this step
             if (tid == 0) { cnt[C_NU] = 0; cnt[C_NMATCH] = 0; cnt[C_NUT] = 0; }
-            return;
+            return true;
         }
         // leftover detections, ascending (hung.py:43)
         n_left = block_compact(N, [&](int j) { return d.det_used[db + j] == 0; },
                                [&](int pos, int j) { d.ud1[db + pos] = j; }, scratch);
         if (tid == 0) { cnt[C_NU] = n_left; cnt[C_NMATCH] = n_match; cnt[C_NUT] = n_ut; }
-        enqueue_cost_work(d.work2, d.wcount + 1, s, n_left > 0 ? cnt[C_M2] : 0, n_left, scratch);
+        if (!FUSED) enqueue_cost_work(d.work2, d.wcount + 1, s, n_left > 0 ? cnt[C_M2] : 0, n_left, scratch);
         TRK_STAMP(5);
-        return;
+        __syncthreads();
+        return false;
     }
 
     if (failed) {
@@ -837,7 +881,7 @@ __global__ void __launch_bounds__(kThreads) assign_kernel(Dev d, int smem_matrix
             res[R_NLIVE] = hdr[H_NLIVE]; res[R_NEXT] = hdr[H_NEXT]; res[R_STATUS] = cnt[C_STATUS];
             res[R_M1] = cnt[C_M1]; res[R_M2] = cnt[C_M2];
         }
-        return;
+        return true;
     }
     // ---- stage 2 tail: leftover dets, births (:362-373), purge (:357-360), result table ------------
     int* out_ud = res_ud(d, res);
@@ -859,7 +903,122 @@ __global__ void __launch_bounds__(kThreads) assign_kernel(Dev d, int smem_matrix
         res[R_M1] = cnt[C_M1];
         res[R_M2] = cnt[C_M2];
     }
+    return true;
 }
+
+template <int STAGE>
+__global__ void __launch_bounds__(kThreads) assign_kernel(Dev d, int smem_matrix_floats) {
+    Span span((d.frame_id[0] & 7) * 6 + (STAGE == 1 ? 2 : 4));
+    TRK_PDL_PROLOGUE();
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    assign_body<STAGE, false>(d, blockIdx.x, smem_raw, smem_matrix_floats);
+}
+
+// ---- fused step for tracking-sized streams (max_tracks <= 512, max_dets <= 256, hist_max <= 32): two launches ------
+// front_kernel (grid G x S, 128 threads): what begin_kernel and the stage-1 cost kernel do, without a kernel boundary
+// between them.  Every CTA of a stream derives the stream's row split itself (a block compaction over <= 512 miss
+// counters: cheaper than a dependent launch), predicts the tracks whose rows it owns (thread per track) and then runs
+// those rows' stage-1 cost, one warp per row, deriving the detection-side inputs (z, float32 box / confidence, unit
+// embedding of the few surviving detections) on the fly with the same functions begin_kernel uses.  The CTAs of a stream
+// share the detection prep the back kernel needs.
+// back_kernel (one CTA of 256 threads per stream): stage-1 assignment and bookkeeping, the ReID-only cost of the
+// stream's long-lost rows (usually none), stage-2 assignment, births, purge, result table, and finally the Kalman / EMA
+// / bank updates of the stream's own matches.  Streams are independent, so nothing inside waits for another CTA.
+constexpr int kFrontWarps = 4;
+
+__global__ void __launch_bounds__(kFrontWarps * 32, 2) front_kernel(Dev d) {
+    Span span((d.frame_id[0] & 7) * 6 + 0);
+    extern __shared__ __align__(16) int s_rows[];              // rows_main [MT] | rows_reid [MT]
+    __shared__ int scratch[kThreads / 32];
+    const int s = blockIdx.y, g = blockIdx.x, G = gridDim.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    int* hdr = d.hdr + s * kHdr;
+    int* cnt = d.cnt + s * kHdr;
+    int* res = d.result + (size_t)s * d.res_stride;
+    const size_t sb = (size_t)s * d.MT;
+    const int n = d.n_det[s], nl = hdr[H_NLIVE];
+    const int* order = d.order + sb;
+    if (n < 0) {                                   // stream idle this step
+        if (g == 0 && tid == 0) {
+            cnt[C_MODE] = MODE_SKIP;
+            res[R_NMATCH] = res[R_NUT] = res[R_NUD] = res[R_STATUS] = res[R_M1] = res[R_M2] = 0;
+            res[R_NLIVE] = nl;
+            res[R_NEXT] = hdr[H_NEXT];
+        }
+        return;
+    }
+    if (n == 0) {                                  // :467-471 -- every track missed, NO predict
+        if (g != 0) return;
+        int* ut = res_ut(d, res);
+        for (int p = tid; p < nl; p += blockDim.x) {
+            const size_t slot = sb + order[p];
+            d.miss[slot] += 1;
+            ut[p] = d.tid[slot];
+        }
+        __syncthreads();
+        purge(d, s, nl, scratch);
+        if (tid == 0) {
+            cnt[C_MODE] = MODE_EMPTY;
+            res[R_NMATCH] = 0; res[R_NUT] = nl; res[R_NUD] = 0; res[R_STATUS] = 0; res[R_M1] = res[R_M2] = 0;
+            res[R_NLIVE] = hdr[H_NLIVE];
+            res[R_NEXT] = hdr[H_NEXT];
+        }
+        return;
+    }
+    // ---- rows_main / rows_reid in ascending track-id order (:478-487), in every CTA of the stream ----
+    int* rm = s_rows;
+    int* rr = s_rows + d.MT;
+    const int M1 = block_compact(nl, [&](int i) { return d.miss[sb + order[i]] <= d.lost_reid_after; },
+                                 [&](int pos, int i) { rm[pos] = order[i]; }, scratch);
+    const int M2 = block_compact(nl, [&](int i) { return d.miss[sb + order[i]] > d.lost_reid_after; },
+                                 [&](int pos, int i) { rr[pos] = order[i]; }, scratch);
+    if (g == 0) {
+        for (int i = tid; i < M1; i += blockDim.x) d.rows_main[sb + i] = rm[i];
+        for (int i = tid; i < M2; i += blockDim.x) d.rows_reid[sb + i] = rr[i];
+        if (tid == 0) {
+            cnt[C_M1] = M1; cnt[C_M2] = M2; cnt[C_NU] = 0; cnt[C_MODE] = MODE_NORMAL;
+            cnt[C_NMATCH] = 0; cnt[C_NUT] = 0; cnt[C_STATUS] = 0;
+        }
+    }
+    prep_detections(d, s, n, g, G);
+    // ---- predict_all (:340-345): thread per track, the tracks of the rows this CTA owns (r = g, g + G, ...) ----
+    const int own1 = M1 > g ? (M1 - g + G - 1) / G : 0, own2 = M2 > g ? (M2 - g + G - 1) / G : 0;
+    for (int i = tid; i < own1 + own2; i += blockDim.x)
+        predict_slot(d, sb + (i < own1 ? rm[g + i * G] : rr[g + (i - own1) * G]));
+    __syncthreads();
+    // ---- stage-1 cost of the owned rows, one warp per row ----
+    for (int i = warp; i < own1; i += kFrontWarps) {
+        const int r = g + i * G;
+        cost1_row32<true>(d, s, r, sb + rm[r], n, lane);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) back_kernel(Dev d, int smem_matrix_floats) {
+    Span span((d.frame_id[0] & 7) * 6 + 2);
+    TRK_PDL_PROLOGUE();
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int s_idx[cost::kTileN];
+    const int s = blockIdx.x, tid = threadIdx.x;
+    const int* cnt = d.cnt + s * kHdr;
+    if (!assign_body<1, true>(d, s, smem_raw, smem_matrix_floats)) {
+        // ReID-only cost (:552-558) of this stream's long-lost rows against the leftover detections
+        const int M2 = cnt[C_M2], NU = cnt[C_NU];
+        if (M2 > 0 && NU > 0) {
+            const int tiles = (NU + cost::kTileN - 1) / cost::kTileN;
+            for (int it = 0; it < M2 * tiles; ++it)
+                cost2_item(d, s, it / tiles, (it % tiles) * cost::kTileN, reinterpret_cast<float*>(smem_raw), s_idx);
+        }
+        __syncthreads();
+    }
+    assign_body<2, true>(d, s, smem_raw, smem_matrix_floats);
+    __syncthreads();
+    if (cnt[C_MODE] != MODE_NORMAL) return;        // idle, empty or failed in stage 1: nothing was matched
+    // ---- update_matched, arithmetic half, for this stream's own queue (stage 1 then stage 2 entries) ----
+    const int total = d.result[(size_t)s * d.res_stride + R_NMATCH];
+    const int warp = tid >> 5;
+    update_entries(d, (int)((size_t)s * d.MT), total, warp, kThreads / 32,
+                   reinterpret_cast<double*>(smem_raw) + (size_t)warp * 4 * 96);
+}
+
 
 // ---- the pieces of Tracking.update as separate operations on one stream of a handle (mainTracking.py:340-448) ----
 // One CTA each; they exist so that a caller that drives the association step by step, like the reference's own
@@ -1018,6 +1177,9 @@ struct b200_tracker {
     int cost_grid = 0, cost1_grid = 0, upd_grid = 0;   // persistent CTAs of the cost kernels (resident CTAs per SM x SMs)
     size_t assign_smem = 0;
     int smem_matrix_floats = 0;
+    bool fused = false;                 // tracking-sized streams: front_kernel + back_kernel instead of the six-kernel chain
+    int front_resident = 0;             // CTAs of front_kernel the device holds at once
+    size_t front_smem = 0, back_smem = 0;
 };
 
 namespace {
@@ -1159,6 +1321,23 @@ extern "C" int b200_tracker_create(b200_tracker** out, int n_streams, int max_tr
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trk::cost1_sparse_kernel, trk::kCost1Warps * 32, 0);
         t->cost1_grid = sms * (per_sm > 0 ? per_sm : 1);
         t->upd_grid = sms * 2;
+        // Two-launch step for a handful of tracking-sized streams (latency mode).  Measured (profiles/r02_group_probe.txt):
+        // one stream 43.5 -> 40.8 us per frame; with 64 streams the chain alone is faster (68 -> 59 us) but its CTAs need
+        // a whole SM each and cannot start beside ROI Align of the next frame (overlapped step 232 -> 273 us), so stream
+        // groups keep the six-kernel chain.  B200TRACK_LEGACY_CHAIN=1 / B200TRACK_FUSED_CHAIN=1 force either path (tests).
+        t->fused = max_tracks <= 512 && max_dets <= 256 && d.HIST <= 32 && getenv("B200TRACK_LEGACY_CHAIN") == nullptr &&
+                   (n_streams <= 8 || getenv("B200TRACK_FUSED_CHAIN") != nullptr);
+        if (t->fused) {
+            t->front_smem = sizeof(int) * 2 * (size_t)max_tracks;
+            size_t bs = t->assign_smem;
+            if (cost::smem_bytes(d.HIST) > bs) bs = cost::smem_bytes(d.HIST);
+            if (sizeof(double) * (trk::kThreads / 32) * 4 * 96 > bs) bs = sizeof(double) * (trk::kThreads / 32) * 4 * 96;
+            t->back_smem = bs;
+            cudaFuncSetAttribute(trk::back_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
+            per_sm = 1;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trk::front_kernel, trk::kFrontWarps * 32, t->front_smem);
+            t->front_resident = sms * (per_sm > 0 ? per_sm : 1);
+        }
     }
     *out = t;
     return B200_OK;
@@ -1209,8 +1388,26 @@ extern "C" int b200_tracker_step(b200_tracker* t, const int32_t* n_det, const do
     d.n_det = n_det; d.boxes = boxes; d.confs = confs; d.embs = embs; d.frame_id = frame_id; d.result = result;
     const size_t csm = cost::smem_bytes(d.HIST);
     const int cost_grid = t->cost_grid;
+    int rc;
+    if (t->fused) {
+        // CTAs per stream of the front kernel: fill the device once, never more than one CTA per four rows
+        int G = t->front_resident / d.S;
+        const int gmax = (d.MT + 3) / 4;
+        G = G < 1 ? 1 : G > gmax ? gmax : G;
+        trk::front_kernel<<<dim3(G, d.S), trk::kFrontWarps * 32, t->front_smem, st>>>(d);
+        if ((rc = check_launch("trk front_kernel"))) return rc;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(d.S); cfg.blockDim = dim3(trk::kThreads); cfg.dynamicSmemBytes = t->back_smem; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = d.S <= 8 ? 1 : 0;           // few streams: have the back kernel resident when the front one ends
+        (void)cudaLaunchKernelEx(&cfg, trk::back_kernel, d, t->smem_matrix_floats);
+        return check_launch("trk back_kernel");
+    }
     trk::begin_kernel<<<dim3(d.S, 2), t->begin_threads, 0, st>>>(d);
-    int rc = check_launch("trk begin_kernel");
+    rc = check_launch("trk begin_kernel");
     if (rc) return rc;
     // With a handful of streams the step is a chain of short, latency-bound kernels: launch the dependent ones
     // with programmatic stream serialisation so that each is resident (and past its launch latency) by the

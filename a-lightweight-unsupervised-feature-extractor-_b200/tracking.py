@@ -245,6 +245,7 @@ class StepHandle:
     def __init__(self, ms: MultiStreamTracker, ticket: int, births: np.ndarray):
         self._ms, self._ticket, self._births = ms, ticket, births
         self._res, self._error = None, None
+        self.table = None                              # the step's result table once collected, also when result() raises
 
     def _collect(self):
         ms = self._ms
@@ -265,11 +266,12 @@ class StepHandle:
         except Exception as exc:                       # noqa: BLE001
             self._error = exc
             return
-        self._res = res
+        self._res = self.table = res
         ms._res = res
         ms.n_live[:] = res[:, R_NLIVE]
-        # A failing stream does not lose the others: the table (ms.last_result) is complete before anything is raised,
-        # and the failing stream's state is what the reference leaves behind when scipy raises (predict only).
+        # A failing stream does not lose the others: the table (handle.table; ms.last_result = the most recently collected
+        # one) is complete before anything is raised, and the failing stream's state is what the reference leaves behind
+        # when scipy raises (predict only).
         ms.last_result = res
         bad = np.nonzero(res[:, R_STATUS])[0]
         if len(bad):

@@ -85,10 +85,18 @@ def _oracle_state(ref):
     dict(n=512, H=1280, W=1280, frames=12, scene=dict(drop=0.1, churn=0.1, churn_every=4),
          conf=dict(lost_reid_after=3, max_age=8), every=3),
 ])
-def test_tracker_vs_oracle(case):
+@pytest.mark.parametrize("chain", ["fused", "six_kernels"])
+def test_tracker_vs_oracle(case, chain, monkeypatch):
+    """Both device paths of the step: the two-launch fused chain (handles of at most 512 tracks x 256 detections) and the
+    six-kernel chain that larger handles use (forced with B200TRACK_LEGACY_CHAIN for the small cases)."""
     cfg = dict(SHIPPED_CONF, **case["conf"])
+    if chain == "fused" and case["n"] > 128:
+        pytest.skip("crowds need more than 512 track slots: six-kernel chain only")
+    if chain == "six_kernels":
+        monkeypatch.setenv("B200TRACK_LEGACY_CHAIN", "1")
     ref = tracker_ref.TrackerRef(cfg)
-    trk = Tracking(conf=cfg, max_tracks=max(768, 3 * case["n"]), max_dets=max(192, case["n"]))
+    big = case["n"] > 128
+    trk = Tracking(conf=cfg, max_tracks=max(768, 3 * case["n"]) if big else 512, max_dets=max(192, case["n"]))
     scene = synth.Scene(7, case["n"], case["H"], case["W"], **case["scene"])
     saw_reid = 0
     for f in range(case["frames"]):
@@ -200,7 +208,10 @@ def test_tracker_grows_like_the_unbounded_reference():
     assert trk.next_id == ref.next_id
 
 
-def test_multistream_equals_independent_trackers():
+@pytest.mark.parametrize("chain", ["default", "fused", "six_kernels"])
+def test_multistream_equals_independent_trackers(chain, monkeypatch):
+    if chain != "default":
+        monkeypatch.setenv("B200TRACK_FUSED_CHAIN" if chain == "fused" else "B200TRACK_LEGACY_CHAIN", "1")
     cfg = dict(SHIPPED_CONF, lost_reid_after=5, max_age=15)
     S, MD = 5, 48
     ms = MultiStreamTracker(S, cfg, max_tracks=128, max_dets=MD)
@@ -413,7 +424,7 @@ def _check_async(ms, handle, want, f):
     if any(w is None for w in want):
         with pytest.raises(ValueError):
             handle.result()
-        res = ms.last_result                              # ... and the other streams' rows are still there
+        res = handle.table                                # ... and the other streams' rows are still there
     else:
         res = handle.result()
     for s, w in enumerate(want):
