@@ -15,6 +15,7 @@ CSRC = os.path.join(_HERE, "csrc")
 OK, EINVAL, ECUDA, ECAPACITY, ENUMERIC, EINFEASIBLE = 0, -1, -2, -3, -4, -5
 LAYOUT_NCHW, LAYOUT_NHWC = 0, 1
 DTYPE_F32, DTYPE_F16 = 0, 1
+BOXES_INPUT, BOXES_TRAINING = 0, 1
 
 _lib = None
 
@@ -48,6 +49,7 @@ SIGNATURES = {
     "b200_roi_align_fwd_f32": (_I, [_P, _I, _I, _I, _I, _I, _P, _L, _I, _I, _F, _I, _I, _P, _P]),
     "b200_roi_align_fwd_f16": (_I, [_P, _I, _I, _I, _I, _I, _P, _L, _I, _I, _F, _I, _I, _P, _P]),
     "b200_roi_align_fwd_ex": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _L, _I, _I, _F, _I, _I, _P, _I, _P]),
+    "b200_roi_boxes_prep_f32": (_I, [_P, _L, _I, _P, _I, _I, _I, _I, _I, _F, _P, _P]),
     "b200_app_cost_topk_f32": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _I, _P]),
     "b200_pair_cost_f32": (_I, [_P, _P, _P, _P, _P, _I, _I, _F, _F, _F, _F, _F, _F, _P, _P, _P, _P, _P, _I, _P]),
     "b200_kalman_init": (_I, [_P, _I, _P, _P, _P, _P]),
@@ -63,6 +65,7 @@ SIGNATURES = {
     "b200_tracker_step": (_I, [_P, _P, _P, _P, _P, _P, _P, _P]),
     "b200_tracker_step_host": (_I, [_P, _P, _P, _P, _P, _P, _P, _P]),
     "b200_tracker_step_host_async": (_I, [_P, _P, _P, _P, _P, _P, ctypes.POINTER(ctypes.c_int64), _P]),
+    "b200_tracker_step_pinned_async": (_I, [_P, _P, _P, _P, _P, _P, ctypes.POINTER(ctypes.c_int64), _P]),
     "b200_tracker_step_result": (_I, [_P, ctypes.c_int64, _P]),
     "b200_tracker_predict_all": (_I, [_P, _I, _P]),
     "b200_tracker_mark_missed": (_I, [_P, _I, _P, _I, _P]),

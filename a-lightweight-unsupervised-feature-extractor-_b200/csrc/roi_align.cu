@@ -843,6 +843,9 @@ __device__ __forceinline__ int tma_box_rows(int rows) { return rows <= 1 ? 1 : r
 #ifndef B200_ROI_TMA_REGS
 #define B200_ROI_TMA_REGS 216
 #endif
+#ifndef B200_ROI_TMA_MAX_CTAS
+#define B200_ROI_TMA_MAX_CTAS 0
+#endif
 constexpr int kTmaWarps = B200_ROI_TMA_WARPS;
 
 template <int PH, int PW>
@@ -1285,7 +1288,12 @@ int launch_tma(const T* feat, int B, int C, int H, int W, const float* rois, lon
     static int cache[kMaxDevices];               // per instantiation and device
     auto kern = roi_align_tma_kernel<PH, PW, T, OCL>;
     int resident = 0;
-    const int rc = resident_warps_of(kern, cache, kTmaWarps, S::kBytesPerCta, &resident);
+    // B200_ROI_TMA_MAX_CTAS > 0 caps the CTAs an SM holds by asking for more dynamic shared memory than the kernel uses, so
+    // that registers and shared memory stay free for kernels of other streams (the association chain).
+    int smem_bytes = S::kBytesPerCta;
+    if (B200_ROI_TMA_MAX_CTAS > 0 && smem_bytes < 233472 / (B200_ROI_TMA_MAX_CTAS + 1) + 256)
+        smem_bytes = 233472 / (B200_ROI_TMA_MAX_CTAS + 1) + 256;
+    const int rc = resident_warps_of(kern, cache, kTmaWarps, smem_bytes, &resident);
     if (rc) return rc;
     // Tiles per warp: 16 amortise a warp's start-up (mbarrier init, first un-overlapped load) best, but a warp that walks
     // 16 tiles lives ~60 us; a launch of only a few waves (8 streams of BASELINE config 5: 16 384 tiles) would then hold
@@ -1297,7 +1305,7 @@ int launch_tma(const T* feat, int B, int C, int H, int W, const float* rois, lon
     const long long groups = (tiles + window - 1) / window;
     const long long last = tiles - (groups - 1) * window;
     const long long warps = (groups - 1) * resident + (last < resident ? last : resident);
-    kern<<<(unsigned)((warps + kTmaWarps - 1) / kTmaWarps), kTmaWarps * 32, S::kBytesPerCta, st>>>(
+    kern<<<(unsigned)((warps + kTmaWarps - 1) / kTmaWarps), kTmaWarps * 32, smem_bytes, st>>>(
         tmap, feat, B, C, H, W, rois, K, scale, sr, aligned, out, ctiles, prep, tabs, resident, (int)tpw);
     return check_launch("roi_align_tma_kernel");
 }
@@ -1437,8 +1445,56 @@ int roi_align_dispatch(const T* feat, int layout, int B, int C, int H, int W, co
     return check_launch("roi_align_generic_kernel");
 }
 
+// ---- box preparation in front of ROI Align (tracking.py:209-213, trainingCard.py:38-69) as one launch -----------
+// torch.minimum / maximum / clamp propagate NaN; fminf / fmaxf do not.
+__device__ __forceinline__ float t_min(float a, float b) { return (a != a || b != b) ? __int_as_float(0x7fc00000) : fminf(a, b); }
+__device__ __forceinline__ float t_max(float a, float b) { return (a != a || b != b) ? __int_as_float(0x7fc00000) : fmaxf(a, b); }
+__device__ __forceinline__ float t_clamp(float v, float lo, float hi) { return v != v ? v : fminf(fmaxf(v, lo), hi); }
+
+__global__ void roi_boxes_prep_kernel(const float* __restrict__ boxes, long long n, int stride,
+                                      const int32_t* __restrict__ batch_index, int mode, float sx, float sy, float xmax,
+                                      float ymax, float min_size, float* __restrict__ rois) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* b = boxes + i * stride;
+    float x1 = b[0], y1 = b[1], x2 = b[2], y2 = b[3];
+    if (mode == B200_BOXES_TRAINING) {
+        const float ax = t_min(x1, x2), bx = t_max(x1, x2), ay = t_min(y1, y2), by = t_max(y1, y2);   // :44-48
+        x1 = t_clamp(__fmul_rn(ax, sx), 0.f, xmax);                                                   // :51-62
+        x2 = t_clamp(__fmul_rn(bx, sx), 0.f, xmax);
+        y1 = t_clamp(__fmul_rn(ay, sy), 0.f, ymax);
+        y2 = t_clamp(__fmul_rn(by, sy), 0.f, ymax);
+        if (min_size > 0.f) {                                                                         // :64-68
+            x2 = t_clamp(t_max(x2, __fadd_rn(x1, min_size)), 0.f, xmax);
+            y2 = t_clamp(t_max(y2, __fadd_rn(y1, min_size)), 0.f, ymax);
+        }
+    }
+    float* r = rois + i * 5;
+    r[0] = batch_index ? (float)batch_index[i] : 0.f;
+    r[1] = x1; r[2] = y1; r[3] = x2; r[4] = y2;
+}
+
 }  // namespace
 }  // namespace b200
+
+extern "C" int b200_roi_boxes_prep_f32(const float* boxes, int64_t n, int box_stride, const int32_t* batch_index, int mode,
+                                       int img_h, int img_w, int Hf, int Wf, float enforce_min_size, float* rois,
+                                       void* stream) {
+    B200_REQUIRE(n >= 0 && box_stride >= 4, "roi_boxes_prep: need n >= 0 and at least 4 columns per box (got %d)", box_stride);
+    B200_REQUIRE(mode == B200_BOXES_INPUT || mode == B200_BOXES_TRAINING, "roi_boxes_prep: bad mode %d", mode);
+    if (n == 0) return B200_OK;
+    B200_REQUIRE(boxes && rois, "roi_boxes_prep: null pointer");
+    float sx = 1.f, sy = 1.f;
+    if (mode == B200_BOXES_TRAINING) {
+        B200_REQUIRE(img_h > 0 && img_w > 0 && Hf > 0 && Wf > 0, "roi_boxes_prep: bad image / map size");
+        sx = (float)((double)Wf / (double)img_w);      // the reference multiplies a float32 tensor by a Python float
+        sy = (float)((double)Hf / (double)img_h);
+    }
+    const unsigned blocks = (unsigned)((n + 127) / 128);
+    b200::roi_boxes_prep_kernel<<<blocks, 128, 0, b200::as_stream(stream)>>>(
+        boxes, n, box_stride, batch_index, mode, sx, sy, (float)(Wf - 1), (float)(Hf - 1), enforce_min_size, rois);
+    return b200::check_launch("roi_boxes_prep_kernel");
+}
 
 extern "C" int b200_roi_align_fwd_f32(const float* feat, int layout, int B, int C, int H, int W,
                                       const float* rois, int64_t K, int PH, int PW, float spatial_scale,

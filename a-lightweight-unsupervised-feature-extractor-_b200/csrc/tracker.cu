@@ -34,8 +34,11 @@ struct Span {                     // RAII global-timer span of one kernel (debug
 #ifdef B200_TRK_TIMING          // debug builds only: SM-clock stamps at phase boundaries of stream 0
 __device__ long long g_timing[32];
 #define TRK_STAMP(k) do { __syncthreads(); if (threadIdx.x == 0 && blockIdx.x == 0) g_timing[k] = clock64(); } while (0)
+// global-timer stamps of the fused step's phases (CTA 0 of stream 0), slots 16..31 of the same array
+#define TRK_GSTAMP(k) do { __syncthreads(); if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) g_timing[16 + (k)] = (long long)::b200::gtime(); } while (0)
 #else
 #define TRK_STAMP(k) do { } while (0)
+#define TRK_GSTAMP(k) do { } while (0)
 #endif
 
 // Programmatic dependent launch (used for small stream counts, see b200_tracker_step): let the next kernel of
@@ -931,6 +934,7 @@ __global__ void __launch_bounds__(kFrontWarps * 32, 2) front_kernel(Dev d) {
     extern __shared__ __align__(16) int s_rows[];              // rows_main [MT] | rows_reid [MT]
     __shared__ int scratch[kThreads / 32];
     const int s = blockIdx.y, g = blockIdx.x, G = gridDim.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    TRK_GSTAMP(0);
     int* hdr = d.hdr + s * kHdr;
     int* cnt = d.cnt + s * kHdr;
     int* res = d.result + (size_t)s * d.res_stride;
@@ -979,17 +983,20 @@ __global__ void __launch_bounds__(kFrontWarps * 32, 2) front_kernel(Dev d) {
             cnt[C_NMATCH] = 0; cnt[C_NUT] = 0; cnt[C_STATUS] = 0;
         }
     }
+    TRK_GSTAMP(1);
     prep_detections(d, s, n, g, G);
     // ---- predict_all (:340-345): thread per track, the tracks of the rows this CTA owns (r = g, g + G, ...) ----
     const int own1 = M1 > g ? (M1 - g + G - 1) / G : 0, own2 = M2 > g ? (M2 - g + G - 1) / G : 0;
     for (int i = tid; i < own1 + own2; i += blockDim.x)
         predict_slot(d, sb + (i < own1 ? rm[g + i * G] : rr[g + (i - own1) * G]));
     __syncthreads();
+    TRK_GSTAMP(2);
     // ---- stage-1 cost of the owned rows, one warp per row ----
     for (int i = warp; i < own1; i += kFrontWarps) {
         const int r = g + i * G;
         cost1_row32<true>(d, s, r, sb + rm[r], n, lane);
     }
+    TRK_GSTAMP(3);
 }
 
 __global__ void __launch_bounds__(kThreads, 1) back_kernel(Dev d, int smem_matrix_floats) {
@@ -999,7 +1006,9 @@ __global__ void __launch_bounds__(kThreads, 1) back_kernel(Dev d, int smem_matri
     __shared__ int s_idx[cost::kTileN];
     const int s = blockIdx.x, tid = threadIdx.x;
     const int* cnt = d.cnt + s * kHdr;
+    TRK_GSTAMP(4);
     if (!assign_body<1, true>(d, s, smem_raw, smem_matrix_floats)) {
+        TRK_GSTAMP(5);
         // ReID-only cost (:552-558) of this stream's long-lost rows against the leftover detections
         const int M2 = cnt[C_M2], NU = cnt[C_NU];
         if (M2 > 0 && NU > 0) {
@@ -1009,14 +1018,17 @@ __global__ void __launch_bounds__(kThreads, 1) back_kernel(Dev d, int smem_matri
         }
         __syncthreads();
     }
+    TRK_GSTAMP(6);
     assign_body<2, true>(d, s, smem_raw, smem_matrix_floats);
     __syncthreads();
+    TRK_GSTAMP(7);
     if (cnt[C_MODE] != MODE_NORMAL) return;        // idle, empty or failed in stage 1: nothing was matched
     // ---- update_matched, arithmetic half, for this stream's own queue (stage 1 then stage 2 entries) ----
     const int total = d.result[(size_t)s * d.res_stride + R_NMATCH];
     const int warp = tid >> 5;
     update_entries(d, (int)((size_t)s * d.MT), total, warp, kThreads / 32,
                    reinterpret_cast<double*>(smem_raw) + (size_t)warp * 4 * 96);
+    TRK_GSTAMP(8);
 }
 
 
@@ -1173,7 +1185,10 @@ struct b200_tracker {
     int* in_ndet = nullptr; int* in_frame = nullptr; double* in_boxes = nullptr; double* in_confs = nullptr;
     float* in_embs = nullptr; int* dev_result = nullptr;
     int ctl_threads = 256;              // CTA width of the per-stream control kernels (assign)
-    int begin_threads = 256;            // CTA width of begin_kernel
+#ifndef B200_TRK_BEGIN_THREADS
+#define B200_TRK_BEGIN_THREADS 256
+#endif
+    int begin_threads = B200_TRK_BEGIN_THREADS;   // CTA width of begin_kernel
     int cost_grid = 0, cost1_grid = 0, upd_grid = 0;   // persistent CTAs of the cost kernels (resident CTAs per SM x SMs)
     size_t assign_smem = 0;
     int smem_matrix_floats = 0;
@@ -1442,9 +1457,11 @@ extern "C" int b200_tracker_step(b200_tracker* t, const int32_t* n_det, const do
 // the D2H copy of the result table on `stream`, records the slot's event and returns a ticket.  b200_tracker_step_result
 // waits for that event only.  Up to kRing steps may be in flight; taking a slot whose result was never collected first
 // waits for it (its result is then lost to the caller).
-extern "C" int b200_tracker_step_host_async(b200_tracker* t, const int32_t* n_det_host, const double* boxes_host,
-                                            const double* confs_host, const float* embs_host,
-                                            const int32_t* frame_id_host, int64_t* ticket, void* stream) {
+// direct = the caller's arrays are page-locked and stay untouched until the result is collected: they are read by DMA
+// straight from where they are (no staging memcpy, which at 64 streams x 64 detections is 2.3 MB = most of the host time).
+namespace {
+int step_host_submit(b200_tracker* t, const int32_t* n_det_host, const double* boxes_host, const double* confs_host,
+                     const float* embs_host, const int32_t* frame_id_host, int64_t* ticket, void* stream, bool direct) {
     B200_REQUIRE(t && n_det_host && frame_id_host && ticket, "tracker_step_host_async: null pointer");
     cudaStream_t st = as_stream(stream);
     const trk::Dev& d = t->d;
@@ -1459,28 +1476,50 @@ extern "C" int b200_tracker_step_host_async(b200_tracker* t, const int32_t* n_de
     double* h_confs = reinterpret_cast<double*>(host_of(t->in_confs));
     float* h_embs = reinterpret_cast<float*>(host_of(t->in_embs));
     bool dense = true;                               // every stream full: three large copies instead of 3 S small ones
+    int n_max = 0;
     for (int s = 0; s < d.S; ++s) {
         const int n = n_det_host[s];
         B200_REQUIRE(n <= d.MD, "tracker_step_host: stream %d has %d detections, capacity %d", s, n, d.MD);
         h_ndet[s] = n;
         h_frame[s] = frame_id_host[s];
         if (n != d.MD) dense = false;
+        if (n > n_max) n_max = n;
         if (n > 0) B200_REQUIRE(boxes_host && confs_host && embs_host, "tracker_step_host: null detection arrays");
     }
-    if (dense) {
-        memcpy(h_boxes, boxes_host, sizeof(double) * 4 * (size_t)d.S * d.MD);
-        memcpy(h_confs, confs_host, sizeof(double) * (size_t)d.S * d.MD);
-        memcpy(h_embs, embs_host, sizeof(float) * 128 * (size_t)d.S * d.MD);
-    } else {
-        for (int s = 0; s < d.S; ++s) {
-            const int n = n_det_host[s];
-            if (n <= 0) continue;
-            memcpy(h_boxes + (size_t)s * d.MD * 4, boxes_host + (size_t)s * d.MD * 4, sizeof(double) * 4 * n);
-            memcpy(h_confs + (size_t)s * d.MD, confs_host + (size_t)s * d.MD, sizeof(double) * n);
-            memcpy(h_embs + (size_t)s * d.MD * 128, embs_host + (size_t)s * d.MD * 128, sizeof(float) * 128 * n);
+    if (direct) {
+        const void* arrs[3] = {boxes_host, confs_host, embs_host};
+        for (int k = 0; k < 3 && n_max > 0; ++k) {
+            cudaPointerAttributes pa = {};
+            const cudaError_t e = cudaPointerGetAttributes(&pa, arrs[k]);
+            if (e != cudaSuccess) cudaGetLastError();
+            B200_REQUIRE(e == cudaSuccess && pa.type == cudaMemoryTypeHost,
+                         "tracker_step_pinned_async: the detection arrays must be page-locked host memory "
+                         "(cudaHostAlloc / cudaHostRegister / torch pin_memory)");
         }
+        // the two small per-stream vectors go through the ring slot (the caller may reuse them at once)
+        B200_CUDA(cudaMemcpyAsync(t->in_ndet, h_ndet, sizeof(int) * d.S, cudaMemcpyHostToDevice, st));
+        B200_CUDA(cudaMemcpyAsync(t->in_frame, h_frame, sizeof(int) * d.S, cudaMemcpyHostToDevice, st));
+        if (n_max > 0) {
+            B200_CUDA(cudaMemcpyAsync(t->in_boxes, boxes_host, sizeof(double) * 4 * (size_t)d.S * d.MD, cudaMemcpyHostToDevice, st));
+            B200_CUDA(cudaMemcpyAsync(t->in_confs, confs_host, sizeof(double) * (size_t)d.S * d.MD, cudaMemcpyHostToDevice, st));
+            B200_CUDA(cudaMemcpyAsync(t->in_embs, embs_host, sizeof(float) * 128 * (size_t)d.S * d.MD, cudaMemcpyHostToDevice, st));
+        }
+    } else {
+        if (dense) {
+            memcpy(h_boxes, boxes_host, sizeof(double) * 4 * (size_t)d.S * d.MD);
+            memcpy(h_confs, confs_host, sizeof(double) * (size_t)d.S * d.MD);
+            memcpy(h_embs, embs_host, sizeof(float) * 128 * (size_t)d.S * d.MD);
+        } else {
+            for (int s = 0; s < d.S; ++s) {
+                const int n = n_det_host[s];
+                if (n <= 0) continue;
+                memcpy(h_boxes + (size_t)s * d.MD * 4, boxes_host + (size_t)s * d.MD * 4, sizeof(double) * 4 * n);
+                memcpy(h_confs + (size_t)s * d.MD, confs_host + (size_t)s * d.MD, sizeof(double) * n);
+                memcpy(h_embs + (size_t)s * d.MD * 128, embs_host + (size_t)s * d.MD * 128, sizeof(float) * 128 * n);
+            }
+        }
+        B200_CUDA(cudaMemcpyAsync(dev_in, pin, t->in_bytes, cudaMemcpyHostToDevice, st));
     }
-    B200_CUDA(cudaMemcpyAsync(dev_in, pin, t->in_bytes, cudaMemcpyHostToDevice, st));
     const int rc = b200_tracker_step(t, t->in_ndet, t->in_boxes, t->in_confs, t->in_embs, t->in_frame, t->dev_result, stream);
     if (rc) return rc;
     char* h_res = pin + ((t->in_bytes + 255) & ~(size_t)255);
@@ -1489,6 +1528,19 @@ extern "C" int b200_tracker_step_host_async(b200_tracker* t, const int32_t* n_de
     t->ticket_of[slot] = t->next_ticket;
     *ticket = t->next_ticket++;
     return B200_OK;
+}
+}  // namespace
+
+extern "C" int b200_tracker_step_host_async(b200_tracker* t, const int32_t* n_det_host, const double* boxes_host,
+                                            const double* confs_host, const float* embs_host,
+                                            const int32_t* frame_id_host, int64_t* ticket, void* stream) {
+    return step_host_submit(t, n_det_host, boxes_host, confs_host, embs_host, frame_id_host, ticket, stream, false);
+}
+
+extern "C" int b200_tracker_step_pinned_async(b200_tracker* t, const int32_t* n_det_host, const double* boxes_pinned,
+                                              const double* confs_pinned, const float* embs_pinned,
+                                              const int32_t* frame_id_host, int64_t* ticket, void* stream) {
+    return step_host_submit(t, n_det_host, boxes_pinned, confs_pinned, embs_pinned, frame_id_host, ticket, stream, true);
 }
 
 extern "C" int b200_tracker_step_result(b200_tracker* t, int64_t ticket, int32_t* result_host) {

@@ -75,44 +75,71 @@ def roi_align(input: torch.Tensor, boxes: Union[torch.Tensor, Sequence[torch.Ten
     return out
 
 
+def _prep_boxes(boxes: torch.Tensor, device, mode: int, batch_index=None, img_hw=(0, 0), map_hw=(0, 0),
+                enforce_min_size: float = 0.0) -> torch.Tensor:
+    """[N, >=4] boxes -> device [N, 5] roi records in ONE launch (b200_roi_boxes_prep_f32)."""
+    b = boxes.reshape(-1, boxes.shape[-1]) if boxes.numel() else boxes.reshape(0, 4)
+    if b.shape[1] < 4:
+        raise ValueError("boxes must have at least four columns (x1, y1, x2, y2)")
+    b = b.to(device=device, dtype=torch.float32)
+    if b.stride(1) != 1 or (b.shape[0] > 1 and b.stride(0) < b.shape[1]):
+        b = b.contiguous()
+    n = b.shape[0]
+    bi = None
+    if batch_index is not None:
+        bi = torch.as_tensor(batch_index).reshape(-1).to(device=device, dtype=torch.int32).contiguous()
+        if bi.shape[0] != n:
+            raise ValueError("batch_index must have one entry per box")
+    rois = torch.empty((n, 5), dtype=torch.float32, device=device)
+    with torch.cuda.device(device):
+        rc = _lib.lib().b200_roi_boxes_prep_f32(_lib.ptr(b), n, int(b.stride(0)) if n > 1 else int(b.shape[1]), _lib.ptr(bi),
+                                                mode, int(img_hw[0]), int(img_hw[1]), int(map_hw[0]), int(map_hw[1]),
+                                                float(enforce_min_size), _lib.ptr(rois), _lib.stream_ptr(device))
+    _lib.check(rc)
+    return rois
+
+
 def roi_align_from_input_boxes(feat: torch.Tensor, boxes_in, input_hw: Tuple[int, int],
                                out_size=(7, 7), aligned: bool = True, sampling_ratio: int = 2, *,
-                               out_channels_last: bool = False) -> torch.Tensor:
+                               out_channels_last: bool = False, batch_index=None) -> torch.Tensor:
     """tracking.py:193-221: boxes are in letterboxed-input pixels, scale = Hf / H_in, batch 0.
 
     ``boxes_in`` is the reference's ``List[[x1, y1, x2, y2]]`` or (extension; SURVEY 8f-4, the detector -> ROI
     hand-off) a ``[N, >=4]`` tensor whose first four columns are the box -- e.g. the detector's NMS output still
-    on the device, which then never visits the host (yoloDetects2.py:135-157 does ``.cpu().tolist()`` per box).
+    on the device, which then never visits the host (yoloDetects2.py:135-157 does ``.cpu().tolist()`` per box); the
+    roi records are then built by one kernel.  ``batch_index`` (extension, int [N]): the map each box belongs to when
+    ``feat`` holds several maps; the reference always passes one map, i.e. index 0.
     """
+    _lib.require_cuda(feat, "feat")
     H_in, _ = input_hw
     Hf = feat.shape[2]
     if isinstance(boxes_in, torch.Tensor):
-        b = boxes_in.reshape(-1, boxes_in.shape[-1])[:, :4].to(device=feat.device, dtype=torch.float32)
-        rois = torch.cat([torch.zeros((b.shape[0], 1), dtype=torch.float32, device=feat.device), b], dim=1)
+        rois = _prep_boxes(boxes_in, feat.device, _lib.BOXES_INPUT, batch_index)
     else:
         b = np.asarray(boxes_in, dtype=np.float32).reshape(-1, 4) if len(boxes_in) else np.zeros((0, 4), np.float32)
         r = np.zeros((b.shape[0], 5), np.float32)                     # batch index 0 (tracking.py:209-213)
         r[:, 1:] = b
-        rois = torch.from_numpy(r)
-    return roi_align(feat, rois.to(feat.device), out_size, Hf / float(H_in), sampling_ratio, aligned,
+        if batch_index is not None:
+            r[:, 0] = np.asarray(batch_index, dtype=np.float32).reshape(-1)
+        rois = torch.from_numpy(r).to(feat.device)
+    return roi_align(feat, rois, out_size, Hf / float(H_in), sampling_ratio, aligned,
                      out_channels_last=out_channels_last)
 
 
 def preprocess_roi(feat: torch.Tensor, bboxes_xyxy: torch.Tensor, img_hw: Tuple[int, int],
                    output_size=(10, 10), sampling_ratio: int = 2, aligned: bool = True,
-                   enforce_min_size: float = 1.0) -> torch.Tensor:
-    """trainingCard.py:24-79: box prep in feature coordinates, then roi_align(scale=1)."""
-    assert feat.dim() == 4 and feat.size(0) == 1, f"feat shape expected [1,C,H,W], got {feat.shape}"
-    b = bboxes_xyxy.to(device=feat.device, dtype=torch.float32).reshape(-1, 4)
+                   enforce_min_size: float = 1.0, *, batch_index=None) -> torch.Tensor:
+    """trainingCard.py:24-79: box prep in feature coordinates (one kernel: corner sort, scale, clamp, minimum size --
+    float32 operation for operation), then roi_align(scale=1).
+
+    Like the reference, ``feat`` is one map ``[1,C,H,W]``.  Extension for BASELINE config 3 (the training-time
+    extraction loops 256 images, trainingCard.py:86-129): with ``batch_index`` (int [N], the image each box belongs to)
+    ``feat`` may be ``[B,C,H,W]`` and the whole batch is one box-prep launch + one ROI Align launch."""
+    _lib.require_cuda(feat, "feat")
+    if batch_index is None:
+        assert feat.dim() == 4 and feat.size(0) == 1, f"feat shape expected [1,C,H,W], got {feat.shape}"
+    elif feat.dim() != 4:
+        raise ValueError("feat must be [B,C,H,W]")
     _, _, Hf, Wf = feat.shape
-    img_h, img_w = img_hw
-    x1, x2 = torch.minimum(b[:, 0], b[:, 2]), torch.maximum(b[:, 0], b[:, 2])
-    y1, y2 = torch.minimum(b[:, 1], b[:, 3]), torch.maximum(b[:, 1], b[:, 3])
-    sx, sy = Wf / float(img_w), Hf / float(img_h)
-    x1, x2 = (x1 * sx).clamp(0, Wf - 1), (x2 * sx).clamp(0, Wf - 1)
-    y1, y2 = (y1 * sy).clamp(0, Hf - 1), (y2 * sy).clamp(0, Hf - 1)
-    if enforce_min_size > 0:
-        x2 = torch.maximum(x2, x1 + enforce_min_size).clamp(0, Wf - 1)
-        y2 = torch.maximum(y2, y1 + enforce_min_size).clamp(0, Hf - 1)
-    rois = torch.stack([torch.zeros_like(x1), x1, y1, x2, y2], dim=1)
+    rois = _prep_boxes(bboxes_xyxy, feat.device, _lib.BOXES_TRAINING, batch_index, img_hw, (Hf, Wf), enforce_min_size)
     return roi_align(feat, rois, output_size, 1.0, sampling_ratio, aligned)

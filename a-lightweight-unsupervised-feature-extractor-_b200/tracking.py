@@ -149,17 +149,31 @@ class MultiStreamTracker:
         return value); raises ValueError where scipy would (NaN / infeasible cost matrix, hung.py:28)."""
         return self.step_async(n_det, boxes, confs, embs, frame_ids).result()
 
-    def step_async(self, n_det, boxes, confs, embs, frame_ids) -> "StepHandle":
+    def step_async(self, n_det, boxes, confs, embs, frame_ids, *, pinned: bool = False) -> "StepHandle":
         """``step`` without the wait: uploads the detections, queues the step and the download of the result table on the
         current CUDA stream and returns at once; ``handle.result()`` blocks until THAT step is on the host and returns
         (or raises) exactly what ``step`` would.  The reference's consumer is a queue (tracking.py:329): a caller can
         queue frame t+1 before it looks at the result of frame t.  At most four steps may be pending; results must be
-        collected in order."""
+        collected in order.
+
+        ``pinned=True``: ``boxes`` / ``confs`` / ``embs`` are page-locked arrays of the exact dtype and shape (numpy views
+        of ``torch.empty(..., pin_memory=True)``, or tensors) that the caller leaves untouched until the result is
+        collected; they are uploaded by DMA from where they are instead of through the handle's staging ring."""
         n_det = np.ascontiguousarray(n_det, dtype=np.int32).reshape(self.S)
         frame_ids = np.ascontiguousarray(frame_ids, dtype=np.int32).reshape(self.S)
-        boxes = np.ascontiguousarray(boxes, dtype=np.float64).reshape(self.S, self.max_dets, 4)
-        confs = np.ascontiguousarray(confs, dtype=np.float64).reshape(self.S, self.max_dets)
-        embs = np.ascontiguousarray(embs, dtype=np.float32).reshape(self.S, self.max_dets, 128)
+        if pinned:
+            arrs = []
+            for a, dt, shape in ((boxes, np.float64, (self.S, self.max_dets, 4)), (confs, np.float64, (self.S, self.max_dets)),
+                                 (embs, np.float32, (self.S, self.max_dets, 128))):
+                a = a.numpy() if isinstance(a, torch.Tensor) else a
+                if not (isinstance(a, np.ndarray) and a.dtype == dt and a.shape == shape and a.flags.c_contiguous):
+                    raise TypeError("step_async(pinned=True): arrays must be C-contiguous %s of shape %s" % (np.dtype(dt), shape))
+                arrs.append(a)
+            boxes, confs, embs = arrs
+        else:
+            boxes = np.ascontiguousarray(boxes, dtype=np.float64).reshape(self.S, self.max_dets, 4)
+            confs = np.ascontiguousarray(confs, dtype=np.float64).reshape(self.S, self.max_dets)
+            embs = np.ascontiguousarray(embs, dtype=np.float32).reshape(self.S, self.max_dets, 128)
         # capacity: live tracks are only known up to the last collected result; every pending step may have added
         # all of its detections
         bound = self.n_live + self._pending_births + np.maximum(n_det, 0)
@@ -175,11 +189,13 @@ class MultiStreamTracker:
             raise _lib.B200Error("step_async: four steps are already pending; collect their results first")
         p = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
         ticket = ctypes.c_int64(-1)
+        fn = _lib.lib().b200_tracker_step_pinned_async if pinned else _lib.lib().b200_tracker_step_host_async
         with torch.cuda.device(self.device):
-            rc = _lib.lib().b200_tracker_step_host_async(self._h, p(n_det), p(boxes), p(confs), p(embs), p(frame_ids),
-                                                         ctypes.byref(ticket), _lib.stream_ptr(self.device))
+            rc = fn(self._h, p(n_det), p(boxes), p(confs), p(embs), p(frame_ids), ctypes.byref(ticket),
+                    _lib.stream_ptr(self.device))
         _lib.check(rc)
         h = StepHandle(self, int(ticket.value), np.maximum(n_det, 0).astype(np.int64))
+        h._keep = (boxes, confs, embs) if pinned else None     # the DMA reads these after this call returns
         self._pending.append(h)
         self._pending_births = self._pending_births + h._births
         return h

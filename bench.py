@@ -550,6 +550,12 @@ def main():
     feat_dev = [torch.empty((S, C, sh.HF, sh.WF), device=dev) for _ in range(2)]     # double-buffered upload target
     rois_dev = [torch.empty((S * NB, 5), device=dev) for _ in range(2)]
     n_det = np.full(S, NB, np.int32)
+    # detections of every frame in page-locked host memory (where an encoder's device->host copy would land): the tracker
+    # call uploads them by DMA from there
+    pin_boxes = torch.from_numpy(grp.boxes).pin_memory()
+    pin_confs = torch.from_numpy(grp.confs).pin_memory()
+    pin_embs = torch.from_numpy(grp.embs).pin_memory()
+    hb, hc, he = pin_boxes.numpy(), pin_confs.numpy(), pin_embs.numpy()
     n_e2e = min(K, 60)
     scale = sh.HF / float(sh.H_IN)
     copy_stream = torch.cuda.Stream(dev)
@@ -573,7 +579,7 @@ def main():
         patches = alufe_b200.roi_align(feat_dev[b], rois_dev[b], (PS, PS), scale, 2, True)
         consumed[b].record(main)
         upload(i + 1)
-        return patches, ms2.step(n_det, grp.boxes[i], grp.confs[i], grp.embs[i], np.full(S, i, np.int32))
+        return patches, ms2.step_async(n_det, hb[i], hc[i], he[i], np.full(S, i, np.int32), pinned=True).result()
 
     for b in range(2):
         consumed[b].record(torch.cuda.current_stream(dev))
@@ -599,37 +605,52 @@ def main():
     # roi_align: the detector's map never leaves the GPU, only boxes / confidences / embeddings come from the host) ----
     if rank == 0 and not args.no_extra:
         try:
+            sA = torch.cuda.Stream(dev, priority=0)
+            sB = torch.cuda.Stream(dev, priority=-1)
+            roi_ev = [torch.cuda.Event() for _ in range(4)]
+
             def api_step(i):
-                """roi_align + step_async of frame i; the result of frame i - 1 is collected afterwards, as a consumer
-                reading from a queue would (tracking.py:329)."""
+                """roi_align (stream A) + step_async (stream B, behind that frame's ROI Align, as the encoder would be) of
+                frame i; the result of frame i - 1 is collected afterwards, as a consumer reading from a queue would
+                (tracking.py:329).  Two user streams, so ROI Align of frame i + 1 overlaps the association of frame i."""
                 j = pre + W + (i % K)              # frames of the timed region again (the state has moved on; same shapes)
-                rois_dev[i & 1].copy_(pin_rois[j % len(pin_rois)], non_blocking=True)
-                patches = alufe_b200.roi_align(feat_dev[i & 1], rois_dev[i & 1], (PS, PS), scale, 2, True)
-                return patches, ms2.step_async(n_det, grp.boxes[j], grp.confs[j], grp.embs[j], np.full(S, n_total + i, np.int32))
-            prev = None
-            for k in range(3):
-                _, h = api_step(k)
-                if prev is not None:
-                    prev.result()
-                prev = h
+                with torch.cuda.stream(sA):
+                    rois_dev[i & 1].copy_(pin_rois[j % len(pin_rois)], non_blocking=True)
+                    patches = alufe_b200.roi_align(feat_dev[i & 1], rois_dev[i & 1], (PS, PS), scale, 2, True)
+                    roi_ev[i & 3].record(sA)
+                with torch.cuda.stream(sB):
+                    sB.wait_event(roi_ev[i & 3])
+                    h = ms2.step_async(n_det, hb[j], hc[j], he[j], np.full(S, n_total + i, np.int32), pinned=True)
+                return patches, h
+            sA.wait_stream(torch.cuda.current_stream(dev))
+            sB.wait_stream(torch.cuda.current_stream(dev))
+            LAG = 2                                # results are collected two frames behind the frame being queued
+            queue = collections.deque()
+            for k in range(4):
+                queue.append(api_step(k)[1])
+                if len(queue) > LAG:
+                    queue.popleft().result()
+            while queue:
+                queue.popleft().result()
             torch.cuda.synchronize()
             n_api = 40
             t0 = time.perf_counter()
             for k in range(n_api):
-                _, h = api_step(3 + k)
-                res = prev.result()
-                prev = h
-            res = prev.result()
+                queue.append(api_step(4 + k)[1])
+                if len(queue) > LAG:
+                    res = queue.popleft().result()
+            while queue:
+                res = queue.popleft().result()
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
             extra["api_device_maps"] = {"value": S * n_api / dt, "unit": "frames/s", "ms_per_step": 1e3 * dt / n_api,
                                         "h2d_bytes_per_step": S * NB * 20 + S * (8 + NB * (32 + 8 + 512)),
-                                        "note": "alufe_b200.roi_align + MultiStreamTracker.step_async (result of frame t collected "
-                                                "after frame t + 1 is queued) with host boxes / confidences / embeddings and "
-                                                "device-resident maps"}
+                                        "note": "alufe_b200.roi_align + MultiStreamTracker.step_async(pinned=True) on two user streams (result of "
+                                                "frame t collected after frame t + 2 is queued) with boxes / confidences / embeddings "
+                                                "in pinned host memory and device-resident maps"}
         except Exception as exc:                                    # noqa: BLE001
             extra["api_device_maps_error"] = repr(exc)
-    del pin_maps, feat_dev, ms2
+    del pin_maps, feat_dev, ms2, pin_boxes, pin_confs, pin_embs, hb, hc, he
     torch.cuda.empty_cache()
 
     def side(name, fn):
@@ -764,7 +785,7 @@ def main():
                        "state_dtype": "f64 Kalman/assignment duals, f32 ROI/cost"},
             "clocks": sampler.summary(),
             "e2e": {"value": world * S * n_e2e / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": n_e2e, "api": "alufe_b200.roi_align + MultiStreamTracker.step (pinned host buffers)",
+                    "steps": n_e2e, "api": "alufe_b200.roi_align + MultiStreamTracker.step_async(pinned=True).result() (pinned host buffers)",
                     "h2d_gbps": h2d * n_e2e / e2e_s / 1e9, "host_cpus_near_gpu": near_cpus},
             "gpu_launches": int(launches),
             "roofline": {"kernel": "roi_prep_kernel + roi_align_tma_kernel<10,10,float> (one ROI Align launch, NCHW maps)",

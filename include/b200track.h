@@ -73,6 +73,19 @@ int b200_roi_align_fwd_ex(const void* feat, int dtype, int layout, int B, int C,
                           const float* rois, int64_t K, int PH, int PW, float spatial_scale,
                           int sampling_ratio, int aligned, void* out, int out_layout, void* stream);
 
+/* Box preparation in front of ROI Align, one launch: boxes [n, box_stride >= 4] float32 (first four columns xyxy; the
+ * detector's NMS rows [x1,y1,x2,y2,conf,cls] qualify, yoloDetects2.py:135-157) -> rois [n,5] = (batch, x1, y1, x2, y2).
+ * batch_index: int32 [n] or NULL (= 0, what both reference wrappers use: one map per call).
+ *   B200_BOXES_INPUT    MainInfer.roi_align_from_input_boxes (tracking.py:209-213): boxes copied as they are; the
+ *                       image -> map scaling is roi_align's spatial_scale.
+ *   B200_BOXES_TRAINING PreProcess._preprocess_roi (model/utils/trainingScr/trainingCard.py:38-69): corners sorted,
+ *                       scaled by Wf/img_w and Hf/img_h, clamped to [0, Wf-1] x [0, Hf-1], x2 >= x1 + enforce_min_size
+ *                       (skipped when <= 0), clamped again; float32 operation for operation, NaN propagating like torch. */
+#define B200_BOXES_INPUT    0
+#define B200_BOXES_TRAINING 1
+int b200_roi_boxes_prep_f32(const float* boxes, int64_t n, int box_stride, const int32_t* batch_index, int mode,
+                            int img_h, int img_w, int Hf, int Wf, float enforce_min_size, float* rois, void* stream);
+
 /* ---- appearance cost -----------------------------------------------------------
  * Replaces Tracking.build_C_app_topk (model/mainTracking.py:141-211).
  * bank: [M,T,128] float32 history banks, bank_len[M] valid rows per track (0 = the row
@@ -202,6 +215,14 @@ int  b200_tracker_step_host_async(b200_tracker* t, const int32_t* n_det_host, co
                                   const double* confs_host, const float* embs_host,
                                   const int32_t* frame_id_host, int64_t* ticket, void* stream);
 int  b200_tracker_step_result(b200_tracker* t, int64_t ticket, int32_t* result_host);
+/* step_host_async for callers whose detection arrays already sit in PAGE-LOCKED host memory (cudaHostAlloc,
+ * cudaHostRegister, torch pin_memory -- e.g. the buffer the encoder's device->host copy lands in, tracking.py:315-324):
+ * boxes / confs / embs ([S,max_dets,...], full shape) are read by DMA from where they are, with no staging copy, so they
+ * must stay unchanged until the step's result has been collected; n_det_host / frame_id_host may be reused at once.
+ * B200_EINVAL if an array is not page-locked.  Same ticket / result protocol as step_host_async. */
+int  b200_tracker_step_pinned_async(b200_tracker* t, const int32_t* n_det_host, const double* boxes_pinned,
+                                    const double* confs_pinned, const float* embs_pinned,
+                                    const int32_t* frame_id_host, int64_t* ticket, void* stream);
 /* Copies one stream's live tracks (ascending track id) to host arrays sized for max_tracks;
  * any pointer may be NULL.  bank is [n, hist_max, 128] oldest-first.  Returns n_live or <0. */
 int  b200_tracker_export(b200_tracker* t, int stream_idx, int32_t* ids, double* x, double* P,

@@ -125,6 +125,47 @@ def test_roi_wrappers_vs_reference_golden():
         assert_close(got.cpu().numpy(), g[tag + "_r2_7_nomin"], what=tag + " r2 nomin")
 
 
+def test_roi_box_prep_kernel_bit_exact_and_batched_c3():
+    """b200_roi_boxes_prep_f32 (one launch instead of the wrappers' eager tensor ops) against the oracle's restatement
+    of trainingCard.py:38-69, bit for bit (inverted, out-of-image, sub-pixel, NaN boxes, strided [N,6] rows), and
+    BASELINE config 3 as ONE call: 256 maps x 16 boxes with a per-box image index == 256 reference-shaped calls."""
+    from oracle import roi_wrappers_ref
+    from alufe_b200.roi import _prep_boxes
+    from alufe_b200 import _lib
+    rng = np.random.default_rng(31)
+    b = synth.random_boxes(rng, 300, 720, 1280).astype(np.float32)
+    edge = synth.edge_case_boxes(720, 1280).astype(np.float32)
+    b[:len(edge)] = edge
+    b[40] = [500, 400, 100, 50]                       # inverted
+    b[41] = [-50, -20, 3000, 2000]                    # far outside
+    b[42] = [10.25, 10.25, 10.5, 10.5]                # smaller than the minimum size
+    b[43] = [np.nan, 5, 50, 60]
+    for min_size in (1.0, 0.0, 2.5):
+        want = roi_wrappers_ref.preprocess_rois(b, (23, 40), (720, 1280), min_size)
+        got = _prep_boxes(torch.from_numpy(b).cuda(), "cuda:0", _lib.BOXES_TRAINING, None, (720, 1280), (23, 40), min_size)
+        np.testing.assert_array_equal(got.cpu().numpy(), want)
+    six = torch.from_numpy(np.concatenate([b, rng.random((300, 2), dtype=np.float32)], 1)).cuda()
+    idx = rng.integers(0, 7, 300).astype(np.int32)
+    got = _prep_boxes(six, "cuda:0", _lib.BOXES_INPUT, idx).cpu().numpy()
+    np.testing.assert_array_equal(got[:, 1:], b)
+    np.testing.assert_array_equal(got[:, 0], idx.astype(np.float32))
+    assert _prep_boxes(torch.zeros((0, 4)), "cuda:0", _lib.BOXES_INPUT).shape == (0, 5)
+    # config 3 in one call
+    Bm, per, Cc = 256, 16, 32
+    feat = torch.randn((Bm, Cc, 40, 40), device="cuda", generator=torch.Generator(device="cuda").manual_seed(3))
+    boxes = np.concatenate([synth.random_boxes(rng, per, 1280, 1280) for _ in range(Bm)]).astype(np.float32)
+    bi = np.repeat(np.arange(Bm), per)
+    one = roi.preprocess_roi(feat, torch.from_numpy(boxes), (1280, 1280), batch_index=bi)
+    assert one.shape == (Bm * per, Cc, 10, 10)
+    for m in (0, 17, 255):                             # the reference's loop body (trainingCard.py:86-129), image by image
+        ref_call = roi.preprocess_roi(feat[m:m + 1], torch.from_numpy(boxes[m * per:(m + 1) * per]), (1280, 1280))
+        assert torch.equal(one[m * per:(m + 1) * per], ref_call)
+        want = roi_wrappers_ref.preprocess_roi(feat[m:m + 1].cpu().numpy(), boxes[m * per:(m + 1) * per], (1280, 1280))
+        assert_close(ref_call.cpu().numpy(), want, what="c3 image %d" % m)
+    a = roi.roi_align_from_input_boxes(feat, torch.from_numpy(boxes).cuda(), (1280, 1280), out_size=(10, 10), batch_index=bi)
+    assert torch.equal(a[16:32], roi.roi_align_from_input_boxes(feat[1:2], boxes[16:32].tolist(), (1280, 1280), out_size=(10, 10)))
+
+
 @pytest.mark.parametrize("nhwc", [False, True])
 def test_roi_c5_full_width_vs_oracle(nhwc):
     """BASELINE config 5 at full width: 64 maps [512,34,60], 128 boxes each = 8 192 ROIs in ONE launch (the prep +

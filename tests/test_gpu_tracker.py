@@ -1,6 +1,7 @@
 """GPU parity of the fused, GPU-resident tracker (Tracking.update) against the golden traces of
 the live reference and against the oracle tracker on larger synthetic scenes."""
 import numpy as np
+import torch
 import pytest
 
 from conftest import assert_close, load_golden
@@ -412,12 +413,55 @@ def test_step_async_matches_step_and_defers_errors():
         handles.append(ms.step_async(*frames[f], np.full(S, f)))
         if len(handles) == 4:                             # the ring is full: collect the oldest
             _check_async(ms, handles.pop(0), want[f - 3], f - 3)
-    with pytest.raises(_lib.B200Error):
-        pass_through = [ms.step_async(*frames[0], np.full(S, 99)) for _ in range(5)]  # noqa: F841  (a fifth pending step)
     ms.drain()
+    roomy = MultiStreamTracker(1, cfg, max_tracks=256, max_dets=4)          # capacity never forces a drain here
+    one = (np.array([1], np.int32), np.array([[[10., 10., 50., 80.]] + [[0.] * 4] * 3]), np.array([[0.9, 0, 0, 0]]),
+           np.ones((1, 4, 128), np.float32))
+    kept = [roomy.step_async(*one, [k]) for k in range(4)]
+    with pytest.raises(_lib.B200Error):
+        roomy.step_async(*one, [4])                                          # a fifth pending step
+    assert [int(h.result()[0, 3]) for h in kept] == [1, 1, 1, 1]             # one live track throughout
     base = F - len(handles)
     for k, h in enumerate(handles):
         _check_async(ms, h, want[base + k], base + k)
+
+
+def test_step_async_pinned_arrays_are_read_in_place():
+    """step_async(pinned=True): page-locked detection arrays are uploaded by DMA from where they are (no staging copy);
+    same results as the oracle, pageable arrays are refused."""
+    cfg = dict(SHIPPED_CONF)
+    S, MD, F = 2, 24, 12
+    ms = MultiStreamTracker(S, cfg, max_tracks=64, max_dets=MD)
+    refs = [tracker_ref.TrackerRef(cfg) for _ in range(S)]
+    scenes = [synth.Scene(80 + s, 10 + 9 * s, 720, 1280, drop=0.1) for s in range(S)]
+    pb = torch.zeros((F, S, MD, 4), dtype=torch.float64).pin_memory()
+    pc = torch.zeros((F, S, MD), dtype=torch.float64).pin_memory()
+    pe = torch.zeros((F, S, MD, 128), dtype=torch.float32).pin_memory()
+    nd = np.zeros((F, S), np.int32)
+    want = []
+    for f in range(F):
+        w = []
+        for s in range(S):
+            obj = scenes[s].step()
+            n = len(obj["bboxes"])
+            nd[f, s] = n
+            pb[f, s, :n] = torch.tensor(obj["bboxes"], dtype=torch.float64)
+            pc[f, s, :n] = torch.tensor(obj["confs"], dtype=torch.float64)
+            pe[f, s, :n] = torch.from_numpy(np.stack(obj["embs"]))
+            w.append(refs[s].update(obj))
+        want.append(w)
+    prev = None
+    for f in range(F):
+        h = ms.step_async(nd[f], pb[f], pc[f].numpy(), pe[f], np.full(S, f), pinned=True)
+        if prev is not None:
+            _check_async(ms, prev[0], want[prev[1]], prev[1])
+        prev = (h, f)
+    _check_async(ms, prev[0], want[prev[1]], prev[1])
+    with pytest.raises(ValueError):
+        ms.step_async(nd[0], np.zeros((S, MD, 4)), np.zeros((S, MD)), np.zeros((S, MD, 128), np.float32), np.full(S, 99),
+                      pinned=True)
+    with pytest.raises(TypeError):
+        ms.step_async(nd[0], np.zeros((S, MD, 4), np.float32), pc[0], pe[0], np.full(S, 99), pinned=True)
 
 
 def _check_async(ms, handle, want, f):
