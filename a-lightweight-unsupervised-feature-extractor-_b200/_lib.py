@@ -72,6 +72,12 @@ SIGNATURES = {
     "b200_tracker_purge_dead": (_I, [_P, _I, _P]),
     "b200_tracker_create_tracks": (_I, [_P, _I, _P, _I, _P, _P, _P, _I, _I, _P]),
     "b200_tracker_update_matched": (_I, [_P, _I, _P, _P, _P, _I, _P, _P, _P, _I, _I, _D, _D, _D, _D, _P]),
+    "b200_peer_gather_create": (_I, [ctypes.POINTER(_P), _I, _I, _L, _I]),
+    "b200_peer_gather_handle": (_I, [_P, _P]),
+    "b200_peer_gather_connect": (_I, [_P, _P]),
+    "b200_peer_gather_push": (_I, [_P, _P, _L, _L, _P]),
+    "b200_peer_gather_collect": (_I, [_P, _P, _L, _L, _P]),
+    "b200_peer_gather_destroy": (None, [_P]),
     "b200_tracker_export": (_I, [_P, _I] + [_P] * 14),
     "b200_tracker_import": (_I, [_P, _I, _I] + [_P] * 12 + [_I, _P]),
 }

@@ -999,34 +999,58 @@ __global__ void __launch_bounds__(kFrontWarps * 32, 2) front_kernel(Dev d) {
     TRK_GSTAMP(3);
 }
 
+// Launched as thread-block clusters of kBackCluster CTAs per stream when the handle has few streams (latency mode): CTA 0
+// of the cluster runs the serial part (assignments, births, purge, result table) while the others wait at the cluster
+// barrier, then all CTAs of the cluster share the stream's Kalman / EMA / bank updates -- 12.5 -> 6 us for 64 matches,
+// 23 -> 6 us for 128 (profiles/r02_fused_timeline.txt).  Without the cluster attribute the cluster is the CTA itself.
+constexpr int kBackCluster = 4;
+
+__device__ __forceinline__ unsigned cluster_ctarank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ unsigned cluster_nctarank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {       // release / acquire at cluster scope: CTA 0's global writes are visible
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 __global__ void __launch_bounds__(kThreads, 1) back_kernel(Dev d, int smem_matrix_floats) {
     Span span((d.frame_id[0] & 7) * 6 + 2);
     TRK_PDL_PROLOGUE();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int s_idx[cost::kTileN];
-    const int s = blockIdx.x, tid = threadIdx.x;
+    const unsigned rank = cluster_ctarank(), nrank = cluster_nctarank();
+    const int s = blockIdx.x / nrank, tid = threadIdx.x;
     const int* cnt = d.cnt + s * kHdr;
     TRK_GSTAMP(4);
-    if (!assign_body<1, true>(d, s, smem_raw, smem_matrix_floats)) {
-        TRK_GSTAMP(5);
-        // ReID-only cost (:552-558) of this stream's long-lost rows against the leftover detections
-        const int M2 = cnt[C_M2], NU = cnt[C_NU];
-        if (M2 > 0 && NU > 0) {
-            const int tiles = (NU + cost::kTileN - 1) / cost::kTileN;
-            for (int it = 0; it < M2 * tiles; ++it)
-                cost2_item(d, s, it / tiles, (it % tiles) * cost::kTileN, reinterpret_cast<float*>(smem_raw), s_idx);
+    if (rank == 0) {
+        if (!assign_body<1, true>(d, s, smem_raw, smem_matrix_floats)) {
+            TRK_GSTAMP(5);
+            // ReID-only cost (:552-558) of this stream's long-lost rows against the leftover detections
+            const int M2 = cnt[C_M2], NU = cnt[C_NU];
+            if (M2 > 0 && NU > 0) {
+                const int tiles = (NU + cost::kTileN - 1) / cost::kTileN;
+                for (int it = 0; it < M2 * tiles; ++it)
+                    cost2_item(d, s, it / tiles, (it % tiles) * cost::kTileN, reinterpret_cast<float*>(smem_raw), s_idx);
+            }
+            __syncthreads();
         }
+        TRK_GSTAMP(6);
+        assign_body<2, true>(d, s, smem_raw, smem_matrix_floats);
         __syncthreads();
+        TRK_GSTAMP(7);
     }
-    TRK_GSTAMP(6);
-    assign_body<2, true>(d, s, smem_raw, smem_matrix_floats);
-    __syncthreads();
-    TRK_GSTAMP(7);
+    if (nrank > 1) cluster_sync_all();
     if (cnt[C_MODE] != MODE_NORMAL) return;        // idle, empty or failed in stage 1: nothing was matched
     // ---- update_matched, arithmetic half, for this stream's own queue (stage 1 then stage 2 entries) ----
     const int total = d.result[(size_t)s * d.res_stride + R_NMATCH];
     const int warp = tid >> 5;
-    update_entries(d, (int)((size_t)s * d.MT), total, warp, kThreads / 32,
+    update_entries(d, (int)((size_t)s * d.MT), total, (int)rank * (kThreads / 32) + warp, (int)nrank * (kThreads / 32),
                    reinterpret_cast<double*>(smem_raw) + (size_t)warp * 4 * 96);
     TRK_GSTAMP(8);
 }
@@ -1180,6 +1204,12 @@ struct b200_tracker {
     void* pinned = nullptr;         // host staging: kRing x (inputs then result)
     size_t in_bytes = 0, res_bytes = 0, slot_bytes = 0;
     cudaEvent_t done[kRing] = {};   // result of the step staged in slot i is on the host
+    // Device side of the ring (inputs then result per slot, same layout as a pinned slot) and two private streams: the
+    // upload of step k+1 and the download of step k's result run beside the kernels of step k instead of in line with
+    // them (a DMA queued between kernels costs ~20 us of engine hand-over each: 292 -> 120 us per pipelined 64-stream step).
+    void* ring_dev = nullptr;
+    cudaStream_t up_stream = nullptr, down_stream = nullptr;
+    cudaEvent_t up[kRing] = {}, ran[kRing] = {};
     long long ticket_of[kRing] = {-1, -1, -1, -1};
     long long next_ticket = 0;
     int* in_ndet = nullptr; int* in_frame = nullptr; double* in_boxes = nullptr; double* in_confs = nullptr;
@@ -1281,11 +1311,17 @@ extern "C" int b200_tracker_create(b200_tracker** out, int n_streams, int max_tr
     t->res_bytes = S * (size_t)d.res_stride * sizeof(int);
     t->slot_bytes = ((t->in_bytes + 255) & ~(size_t)255) + ((t->res_bytes + 255) & ~(size_t)255);
     e = cudaMallocHost(&t->pinned, t->slot_bytes * b200_tracker::kRing);
-    for (int i = 0; e == cudaSuccess && i < b200_tracker::kRing; ++i) e = cudaEventCreateWithFlags(&t->done[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaMalloc(&t->ring_dev, t->slot_bytes * b200_tracker::kRing);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&t->up_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&t->down_stream, cudaStreamNonBlocking);
+    for (int i = 0; e == cudaSuccess && i < b200_tracker::kRing; ++i) {
+        e = cudaEventCreateWithFlags(&t->done[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&t->up[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&t->ran[i], cudaEventDisableTiming);
+    }
     if (e != cudaSuccess) {
-        cudaFree(t->arena);
-        delete t;
-        return fail(B200_ECUDA, "tracker_create: cudaMallocHost: %s", cudaGetErrorString(e));
+        b200_tracker_destroy(t);
+        return fail(B200_ECUDA, "tracker_create: host ring / streams: %s", cudaGetErrorString(e));
     }
     // host offsets inside the pinned block mirror the device input block
     d.pw = cost::PairWeights{(float)conf->w_app, (float)conf->w_bbox, (float)conf->w_conf, (float)conf->alpha,
@@ -1300,14 +1336,15 @@ extern "C" int b200_tracker_create(b200_tracker** out, int n_streams, int max_tr
     const int Rm = max_tracks < max_dets ? max_tracks : max_dets, Cm = max_tracks < max_dets ? max_dets : max_tracks;
     const size_t wb = lsap::work_bytes(Rm, Cm), budget = 200 * 1024;
     if (wb > budget) {
-        cudaFreeHost(t->pinned); cudaFree(t->arena); delete t;
+        b200_tracker_destroy(t);
         return fail(B200_EINVAL, "tracker_create: %d x %d exceeds the assignment kernel's shared memory", max_tracks, max_dets);
     }
     size_t mat = (size_t)Rm * Cm * sizeof(float);
     if (wb + mat > budget) mat = budget - wb;
     // Small problems (the tracking shapes) keep the shared-memory footprint of the assignment kernels modest
     // so that they can share an SM with resident ROI Align CTAs.
-    if (max_tracks <= 256 && max_dets <= 256 && mat > 32 * 1024) mat = 32 * 1024;
+    // (A frame's actual matrix is live tracks x detections, not the capacities; one that does not fit is read from global.)
+    if (max_tracks <= 1024 && max_dets <= 256 && mat > 32 * 1024) mat = 32 * 1024;
     t->smem_matrix_floats = (int)(mat / sizeof(float));
     t->assign_smem = wb + mat;
     // The opt-in belongs to the kernel function (per device), not to this handle: always the full budget, so
@@ -1318,7 +1355,7 @@ extern "C" int b200_tracker_create(b200_tracker** out, int n_streams, int max_tr
     trk::reset_kernel<<<n_streams, 128>>>(d);
     e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
-        cudaFreeHost(t->pinned); cudaFree(t->arena); delete t;
+        b200_tracker_destroy(t);
         return fail(B200_ECUDA, "tracker_create: %s", cudaGetErrorString(e));
     }
     g_launches.fetch_add(1);
@@ -1360,9 +1397,15 @@ extern "C" int b200_tracker_create(b200_tracker** out, int n_streams, int max_tr
 
 extern "C" void b200_tracker_destroy(b200_tracker* t) {
     if (!t) return;
-    for (int i = 0; i < b200_tracker::kRing; ++i)
+    if (t->up_stream) { cudaStreamSynchronize(t->up_stream); cudaStreamDestroy(t->up_stream); }
+    if (t->down_stream) { cudaStreamSynchronize(t->down_stream); cudaStreamDestroy(t->down_stream); }
+    for (int i = 0; i < b200_tracker::kRing; ++i) {
         if (t->done[i]) cudaEventDestroy(t->done[i]);
+        if (t->up[i]) cudaEventDestroy(t->up[i]);
+        if (t->ran[i]) cudaEventDestroy(t->ran[i]);
+    }
     cudaFreeHost(t->pinned);
+    cudaFree(t->ring_dev);
     cudaFree(t->arena);
     delete t;
 }
@@ -1411,13 +1454,18 @@ extern "C" int b200_tracker_step(b200_tracker* t, const int32_t* n_det, const do
         G = G < 1 ? 1 : G > gmax ? gmax : G;
         trk::front_kernel<<<dim3(G, d.S), trk::kFrontWarps * 32, t->front_smem, st>>>(d);
         if ((rc = check_launch("trk front_kernel"))) return rc;
+        // few streams: a cluster of CTAs per stream shares the updates, and the kernel is resident when the front one ends
+        const bool few = d.S <= 8;
+        const int cl = few ? trk::kBackCluster : 1;
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(d.S); cfg.blockDim = dim3(trk::kThreads); cfg.dynamicSmemBytes = t->back_smem; cfg.stream = st;
-        cudaLaunchAttribute attr[1];
+        cfg.gridDim = dim3(d.S * cl); cfg.blockDim = dim3(trk::kThreads); cfg.dynamicSmemBytes = t->back_smem; cfg.stream = st;
+        cudaLaunchAttribute attr[2];
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[0].val.programmaticStreamSerializationAllowed = 1;
+        attr[1].id = cudaLaunchAttributeClusterDimension;
+        attr[1].val.clusterDim.x = cl; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
         cfg.attrs = attr;
-        cfg.numAttrs = d.S <= 8 ? 1 : 0;           // few streams: have the back kernel resident when the front one ends
+        cfg.numAttrs = few ? 2 : 0;
         (void)cudaLaunchKernelEx(&cfg, trk::back_kernel, d, t->smem_matrix_floats);
         return check_launch("trk back_kernel");
     }
@@ -1453,10 +1501,11 @@ extern "C" int b200_tracker_step(b200_tracker* t, const int32_t* n_det, const do
     return B200_OK;
 }
 
-// Host-buffer step, asynchronous: stages the detections in the next slot of a pinned ring, queues H2D copy, the step and
-// the D2H copy of the result table on `stream`, records the slot's event and returns a ticket.  b200_tracker_step_result
-// waits for that event only.  Up to kRing steps may be in flight; taking a slot whose result was never collected first
-// waits for it (its result is then lost to the caller).
+// Host-buffer step, asynchronous: stages the detections in the next slot of a pinned ring, uploads them into the slot's
+// device block on the handle's upload stream, runs the step's kernels on `stream` (which waits for that upload), downloads
+// the result table on the handle's download stream, records the slot's event and returns a ticket.
+// b200_tracker_step_result waits for that event only.  Up to kRing steps may be in flight; taking a slot whose result was
+// never collected first waits for it (its result is then lost to the caller).
 // direct = the caller's arrays are page-locked and stay untouched until the result is collected: they are read by DMA
 // straight from where they are (no staging memcpy, which at 64 streams x 64 detections is 2.3 MB = most of the host time).
 namespace {
@@ -1486,6 +1535,16 @@ int step_host_submit(b200_tracker* t, const int32_t* n_det_host, const double* b
         if (n > n_max) n_max = n;
         if (n > 0) B200_REQUIRE(boxes_host && confs_host && embs_host, "tracker_step_host: null detection arrays");
     }
+    // device side of the slot: same layout as the pinned slot (inputs, then the result table)
+    char* dslot = static_cast<char*>(t->ring_dev) + (size_t)slot * t->slot_bytes;
+    auto dev_of = [&](const void* base_ptr) { return dslot + (reinterpret_cast<const char*>(base_ptr) - dev_in); };
+    int* d_ndet = reinterpret_cast<int*>(dev_of(t->in_ndet));
+    int* d_frame = reinterpret_cast<int*>(dev_of(t->in_frame));
+    double* d_boxes = reinterpret_cast<double*>(dev_of(t->in_boxes));
+    double* d_confs = reinterpret_cast<double*>(dev_of(t->in_confs));
+    float* d_embs = reinterpret_cast<float*>(dev_of(t->in_embs));
+    int* d_res = reinterpret_cast<int*>(dslot + ((t->in_bytes + 255) & ~(size_t)255));
+    cudaStream_t up = t->up_stream, down = t->down_stream;
     if (direct) {
         const void* arrs[3] = {boxes_host, confs_host, embs_host};
         for (int k = 0; k < 3 && n_max > 0; ++k) {
@@ -1497,12 +1556,12 @@ int step_host_submit(b200_tracker* t, const int32_t* n_det_host, const double* b
                          "(cudaHostAlloc / cudaHostRegister / torch pin_memory)");
         }
         // the two small per-stream vectors go through the ring slot (the caller may reuse them at once)
-        B200_CUDA(cudaMemcpyAsync(t->in_ndet, h_ndet, sizeof(int) * d.S, cudaMemcpyHostToDevice, st));
-        B200_CUDA(cudaMemcpyAsync(t->in_frame, h_frame, sizeof(int) * d.S, cudaMemcpyHostToDevice, st));
+        B200_CUDA(cudaMemcpyAsync(d_ndet, h_ndet, sizeof(int) * d.S, cudaMemcpyHostToDevice, up));
+        B200_CUDA(cudaMemcpyAsync(d_frame, h_frame, sizeof(int) * d.S, cudaMemcpyHostToDevice, up));
         if (n_max > 0) {
-            B200_CUDA(cudaMemcpyAsync(t->in_boxes, boxes_host, sizeof(double) * 4 * (size_t)d.S * d.MD, cudaMemcpyHostToDevice, st));
-            B200_CUDA(cudaMemcpyAsync(t->in_confs, confs_host, sizeof(double) * (size_t)d.S * d.MD, cudaMemcpyHostToDevice, st));
-            B200_CUDA(cudaMemcpyAsync(t->in_embs, embs_host, sizeof(float) * 128 * (size_t)d.S * d.MD, cudaMemcpyHostToDevice, st));
+            B200_CUDA(cudaMemcpyAsync(d_boxes, boxes_host, sizeof(double) * 4 * (size_t)d.S * d.MD, cudaMemcpyHostToDevice, up));
+            B200_CUDA(cudaMemcpyAsync(d_confs, confs_host, sizeof(double) * (size_t)d.S * d.MD, cudaMemcpyHostToDevice, up));
+            B200_CUDA(cudaMemcpyAsync(d_embs, embs_host, sizeof(float) * 128 * (size_t)d.S * d.MD, cudaMemcpyHostToDevice, up));
         }
     } else {
         if (dense) {
@@ -1518,13 +1577,17 @@ int step_host_submit(b200_tracker* t, const int32_t* n_det_host, const double* b
                 memcpy(h_embs + (size_t)s * d.MD * 128, embs_host + (size_t)s * d.MD * 128, sizeof(float) * 128 * n);
             }
         }
-        B200_CUDA(cudaMemcpyAsync(dev_in, pin, t->in_bytes, cudaMemcpyHostToDevice, st));
+        B200_CUDA(cudaMemcpyAsync(dslot, pin, t->in_bytes, cudaMemcpyHostToDevice, up));
     }
-    const int rc = b200_tracker_step(t, t->in_ndet, t->in_boxes, t->in_confs, t->in_embs, t->in_frame, t->dev_result, stream);
+    B200_CUDA(cudaEventRecord(t->up[slot], up));
+    B200_CUDA(cudaStreamWaitEvent(st, t->up[slot], 0));            // the caller's stream runs the kernels
+    const int rc = b200_tracker_step(t, d_ndet, d_boxes, d_confs, d_embs, d_frame, d_res, stream);
     if (rc) return rc;
+    B200_CUDA(cudaEventRecord(t->ran[slot], st));
+    B200_CUDA(cudaStreamWaitEvent(down, t->ran[slot], 0));
     char* h_res = pin + ((t->in_bytes + 255) & ~(size_t)255);
-    B200_CUDA(cudaMemcpyAsync(h_res, t->dev_result, t->res_bytes, cudaMemcpyDeviceToHost, st));
-    B200_CUDA(cudaEventRecord(t->done[slot], st));
+    B200_CUDA(cudaMemcpyAsync(h_res, d_res, t->res_bytes, cudaMemcpyDeviceToHost, down));
+    B200_CUDA(cudaEventRecord(t->done[slot], down));
     t->ticket_of[slot] = t->next_ticket;
     *ticket = t->next_ticket++;
     return B200_OK;

@@ -5,10 +5,13 @@ The association step itself never crosses GPUs -- a stream's state lives on exac
 so there is no data-path collective; ``ResultGatherer`` exists because a consumer (the display /
 sink process of tracking.py:329) wants every stream's matches in one place.
 """
+import ctypes
 from typing import List, Optional
 
 import torch
 import torch.distributed as dist
+
+from . import _lib
 
 
 def init_process_group_small_footprint(device, **kw):
@@ -127,3 +130,99 @@ class ResultGatherer:
         if async_op:
             return work, finish
         return finish()
+
+
+class PeerResultGatherer:
+    """``ResultGatherer.gather_frames`` without a collective: every rank pushes its tables straight into every peer's
+    receive ring over NVLink peer memory (``b200_peer_gather_*``: CUDA IPC mappings, 16-byte stores, a flag per cell) and
+    collects a sequence number only when it wants to look at it.  No kernel of the producing side ever waits for another
+    rank, so nothing sits on SMs while ranks drift, and the transfer runs at link speed (a one-CTA NCCL all-gather moved
+    the same 15 MB in ~0.6 ms at 8 GPUs).  One process per GPU on one node; ``torch.distributed`` is used once, to
+    exchange the IPC handles.
+
+    ``push_frames(tables, after=event)`` -> sequence number; ``collect(seq)`` -> Tensor[F, n_streams, stride] in global
+    stream order (stream s lives on rank s mod world).  Every rank must push every sequence number with the same F."""
+
+    def __init__(self, n_streams: int, stride: int, max_frames: int, device, group: Optional[dist.ProcessGroup] = None,
+                 n_slots: int = 4):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.device = torch.device(device)
+        self.n_streams, self.stride, self.max_frames, self.n_slots = n_streams, stride, int(max_frames), n_slots
+        self.local = local_streams(n_streams, self.rank, self.world)
+        self.per_rank = (n_streams + self.world - 1) // self.world
+        self.bytes_per_frame = self.per_rank * stride * 4
+        cap = (self.max_frames * self.bytes_per_frame + 15) // 16 * 16
+        self._h = ctypes.c_void_p()
+        lib = _lib.lib()
+        with torch.cuda.device(self.device):
+            _lib.check(lib.b200_peer_gather_create(ctypes.byref(self._h), self.rank, self.world, cap, n_slots))
+            if self.world > 1:
+                mine = (ctypes.c_ubyte * 64)()
+                _lib.check(lib.b200_peer_gather_handle(self._h, mine))
+                send = torch.tensor(list(mine), dtype=torch.uint8, device=self.device)
+                recv = torch.empty(64 * self.world, dtype=torch.uint8, device=self.device)
+                dist.all_gather_into_tensor(recv, send, group=group)
+                handles = bytes(recv.cpu().tolist())
+                rc = lib.b200_peer_gather_connect(self._h, handles)
+                ok = torch.tensor([1 if rc == 0 else 0], device=self.device)
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)      # all ranks agree before anyone pushes
+                if int(ok.item()) == 0:
+                    msg = lib.b200_last_error().decode("utf-8", "replace") if rc else "a peer could not map this rank's ring"
+                    lib.b200_peer_gather_destroy(self._h)
+                    self._h = ctypes.c_void_p()
+                    raise _lib.B200Error("peer memory exchange unavailable: " + msg)
+        idx = torch.tensor([(s % self.world) * self.per_rank + s // self.world for s in range(n_streams)],
+                           dtype=torch.long, device=self.device)
+        self._index = idx
+        self.stream = torch.cuda.Stream(self.device)
+        self._seq = 0
+        self._frames = {}
+
+    def push_frames(self, local_results: torch.Tensor, after=None) -> int:
+        """local_results: int32 [F, n_local, stride] (F <= max_frames).  Queued on the gatherer's side stream behind
+        ``after`` (a CUDA event recorded where the tables were produced) or the caller's current stream."""
+        n = len(self.local)
+        if local_results.dim() != 3 or local_results.shape[1:] != (n, self.stride) or local_results.shape[0] > self.max_frames:
+            raise ValueError("expected local results of shape [F <= %d, %d, %d]" % (self.max_frames, n, self.stride))
+        F = local_results.shape[0]
+        if after is not None:
+            self.stream.wait_event(after)
+        else:
+            self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self.stream):
+            nbytes = (F * self.bytes_per_frame + 15) // 16 * 16
+            if n == self.per_rank and local_results.is_contiguous() and local_results.data_ptr() % 16 == 0 \
+                    and nbytes == F * self.bytes_per_frame:
+                send = local_results                        # pushed from where the tracker wrote it
+            else:
+                send = torch.zeros(nbytes // 4, dtype=torch.int32, device=self.device)
+                send[:F * self.per_rank * self.stride].view(F, self.per_rank, self.stride)[:, :n].copy_(local_results)
+            send.record_stream(self.stream)
+            seq = self._seq
+            _lib.check(_lib.lib().b200_peer_gather_push(self._h, _lib.ptr(send), nbytes, seq,
+                                                        ctypes.c_void_p(self.stream.cuda_stream)))
+        self._seq += 1
+        self._frames[seq] = (F, nbytes)
+        return seq
+
+    def collect(self, seq: int) -> torch.Tensor:
+        """Tensor[F, n_streams, stride] of sequence number ``seq`` (asynchronous on the side stream; a consumer on another
+        stream waits for ``gatherer.stream``).  Sequence numbers must be collected in order, each once."""
+        F, nbytes = self._frames.pop(seq)
+        with torch.cuda.stream(self.stream):
+            recv = torch.empty((self.world, nbytes // 4), dtype=torch.int32, device=self.device)
+            _lib.check(_lib.lib().b200_peer_gather_collect(self._h, _lib.ptr(recv), nbytes, seq,
+                                                           ctypes.c_void_p(self.stream.cuda_stream)))
+            flat = recv[:, :F * self.per_rank * self.stride].view(self.world, F, self.per_rank, self.stride)
+            flat = flat.permute(1, 0, 2, 3).reshape(F, self.world * self.per_rank, self.stride)
+            return flat.index_select(1, self._index)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            torch.cuda.synchronize(self.device)
+            if self.world > 1 and dist.is_initialized():
+                dist.barrier(group=self.group)              # no peer is still storing into this rank's ring
+            _lib.lib().b200_peer_gather_destroy(self._h)
+            self._h = ctypes.c_void_p()

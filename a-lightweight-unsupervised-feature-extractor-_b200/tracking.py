@@ -177,8 +177,10 @@ class MultiStreamTracker:
         # capacity: live tracks are only known up to the last collected result; every pending step may have added
         # all of its detections
         bound = self.n_live + self._pending_births + np.maximum(n_det, 0)
-        if int(bound.max()) > self.max_tracks and (self._pending or self._n_live_stale):
-            self.drain()
+        while int(bound.max()) > self.max_tracks and self._pending:     # collect the oldest results until the bound fits
+            self._pending[0]._collect()
+            bound = self.n_live + self._pending_births + np.maximum(n_det, 0)
+        if int(bound.max()) > self.max_tracks and self._n_live_stale:
             bound = self.n_live_now() + np.maximum(n_det, 0)
         if int(bound.max()) > self.max_tracks:         # the reference is unbounded: migrate to a larger handle
             if not self.auto_grow:

@@ -27,8 +27,8 @@ streams.  Synthetic inputs follow SURVEY.md section 8d.  Prints ONE JSON line (r
               (256-map ROI extraction), c4 (512 x 512 association), c5 (64 1088x1920 streams), the
               single-stream latency mode, channels-last maps, the public API with device-resident maps.
 --impl reference times the CPU path alone.  N > 1 (torchrun): one stream group per GPU (weak
-scaling), result tables all-gathered with NCCL (one-CTA collectives on a side stream, 16 frames at
-a time), value = total frames / max time; extra.c5_strong is BASELINE configs[4] as written: 64 c5
+scaling), result tables pushed into every peer's ring over NVLink peer memory (PeerResultGatherer, 16
+frames at a time; NCCL all-gather if CUDA IPC is unavailable), value = total frames / max time; extra.c5_strong is BASELINE configs[4] as written: 64 c5
 streams in total, 64/N per GPU (strong scaling).
 """
 import argparse
@@ -440,16 +440,30 @@ def main():
     pre = max(0, SETUP_FRAMES - W)
     n_total = pre + W + K
 
+    gather_kind = {}
+
     def make_gather(grp, n_streams_global, frames_total, boundaries):
-        """The only inter-GPU traffic: the per-stream result tables, all-gathered for the consumer of tracking.py:329,
-        GATHER_EVERY frames per collective ("optionally gather every K frames") through the
-        product's ResultGatherer: one-CTA NCCL kernels on a side stream that waits for an event on the association
-        stream, so neither pipeline stream ever waits for another rank."""
+        """The only inter-GPU traffic: the per-stream result tables, brought together for the consumer of tracking.py:329,
+        GATHER_EVERY frames at a time ("optionally gather every K frames").  Product path:
+        PeerResultGatherer -- every rank pushes its tables into every peer's ring over NVLink peer memory (one short
+        kernel on a side stream behind an event on the association stream; nobody waits for another rank) and collects
+        two gathers behind.  If CUDA IPC is not available on the box: ResultGatherer (one-CTA NCCL all-gather on a side
+        stream).  Returns (after_step, flush, close)."""
         if world == 1:
-            return None, lambda: None
+            return None, (lambda: None), (lambda: None)
         G = max(1, args.gather_every)
-        gat = bdist.ResultGatherer(n_streams_global, grp.trk.stride, dev)
+        try:
+            gat = bdist.PeerResultGatherer(n_streams_global, grp.trk.stride, G, dev)
+            gather_kind["kind"] = "peer memory push over NVLink (b200_peer_gather_*), collected two gathers behind"
+        except Exception as exc:                                    # noqa: BLE001
+            gat = bdist.ResultGatherer(n_streams_global, grp.trk.stride, dev)
+            gather_kind["kind"] = "NCCL all-gather, one-CTA kernels on a side stream (peer memory unavailable: %r)" % (exc,)
+        peer = isinstance(gat, bdist.PeerResultGatherer)
         pending = []
+
+        def collect_oldest():
+            h = pending.pop(0)
+            return gat.collect(h) if peer else gat.wait(h)
 
         def after_step(i):
             full = (i + 1) % G == 0
@@ -458,15 +472,20 @@ def main():
             i0 = (i // G) * G
             ev = torch.cuda.Event()
             ev.record(grp.sB)
-            pending.append(gat.gather_frames(grp.results[i0:i + 1], async_op=True, after=ev))
+            tables = grp.results[i0:i + 1]
+            pending.append(gat.push_frames(tables, after=ev) if peer else gat.gather_frames(tables, async_op=True, after=ev))
             while len(pending) > 2:
-                gat.wait(pending.pop(0))
+                collect_oldest()
 
         def flush():
             while pending:
-                gat.wait(pending.pop(0))
+                collect_oldest()
             torch.cuda.current_stream(dev).wait_stream(gat.stream)
-        return after_step, flush
+
+        def close():
+            if peer:
+                gat.close()
+        return after_step, flush, close
 
     def lineup():
         """All ranks' first timing event lands right behind the same collective (start skew of microseconds)."""
@@ -474,7 +493,7 @@ def main():
             dist.all_reduce(torch.zeros(1, device=dev))
 
     grp = StreamGroup(sh, S, n_total, rank, dev)
-    after_step, flush = make_gather(grp, world * S, n_total, {pre + W})
+    after_step, flush, close_gather = make_gather(grp, world * S, n_total, {pre + W})
     grp.timed(0, pre + W, after_step=after_step)
     flush()
 
@@ -497,6 +516,7 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     elapsed_ms = float(t.item())
+    close_gather()
     last = grp.results[pre + W + K - 1].cpu().numpy()
     assert (last[:, 5] == 0).all() and (last[:, 0] > 0).all(), "device path produced no matches"
 
@@ -519,7 +539,7 @@ def main():
             del grp.maps, grp.outs
             torch.cuda.empty_cache()
             g5 = StreamGroup(sh5, S5, n5, 300 + rank, dev)
-            a5, f5 = make_gather(g5, 64, n5, {SETUP_FRAMES + 5})
+            a5, f5, c5close = make_gather(g5, 64, n5, {SETUP_FRAMES + 5})
             g5.timed(0, SETUP_FRAMES + 5, after_step=a5)
             f5()
             if world > 1:
@@ -532,6 +552,7 @@ def main():
                 dist.all_reduce(t5, op=dist.ReduceOp.MAX)
             ms5 = float(t5.item())
             roi5 = g5.probe_roi(8, first=SETUP_FRAMES + 5)
+            c5close()
             extra["c5_strong"] = {"value": 64 * K5 / (ms5 * 1e-3), "unit": "frames/s", "scaling": "strong",
                                   "streams_total": 64, "streams_per_gpu": S5, "steps": K5, "ms_per_step": ms5 / K5,
                                   "step_ms": dist_summary(step5), "roi_us_per_launch": float(np.mean(roi5)),
@@ -543,7 +564,9 @@ def main():
             extra["c5_strong_error"] = repr(exc)
 
     # ---- end to end through the public API with host (pinned) buffers --------------------------------
-    ms2 = alufe_b200.MultiStreamTracker(S, alufe_b200.SHIPPED_CONF, max_tracks=max(256, 2 * NB), max_dets=NB, device=dev)
+    # capacity 512 like Tracking()'s default: with results collected two frames behind, the host-side bound on live tracks
+    # (last known count + every detection of the pending frames) stays below it and step_async never has to drain
+    ms2 = alufe_b200.MultiStreamTracker(S, alufe_b200.SHIPPED_CONF, max_tracks=max(512, 4 * NB), max_dets=NB, device=dev)
     NPIN = 2
     pin_maps = torch.randn((NPIN, S, C, sh.HF, sh.WF), generator=torch.Generator().manual_seed(99 + rank)).pin_memory()
     pin_rois = torch.from_numpy(grp.rois).pin_memory()
@@ -595,6 +618,14 @@ def main():
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     assert (res[:, 0] > 0).all()
+    # what this box's host link gives a plain pinned -> device copy of the same maps (e2e is bound by it)
+    pa, pb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pa.record()
+    for k in range(6):
+        feat_dev[k & 1].copy_(pin_maps[k % NPIN], non_blocking=True)
+    pb.record()
+    torch.cuda.synchronize()
+    pcie_probe_gbps = 6 * grp.map_b / (pa.elapsed_time(pb) * 1e-3) / 1e9
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -779,14 +810,15 @@ def main():
                        "l2": "inputs larger than L2: each step reads %d maps (%.0f MB) and writes %.0f MB; %d map sets and %d "
                              "output buffers rotate" % (S, grp.map_b / 1e6, grp.out_b / 1e6, grp.nmap, grp.nout),
                        "pipeline": "ROI Align of frame t+1 (stream A) overlaps the association of frame t (stream B)",
-                       "gather": ("result tables of all ranks all-gathered with NCCL (one-CTA kernels, side stream) every %d "
-                                  "frames; the last gather completes inside the timed region" % max(1, args.gather_every))
+                       "gather": ("result tables of all ranks brought together every %d frames: %s; the last gather completes "
+                                  "inside the timed region" % (max(1, args.gather_every), gather_kind.get("kind")))
                        if world > 1 else "single GPU: none",
                        "state_dtype": "f64 Kalman/assignment duals, f32 ROI/cost"},
             "clocks": sampler.summary(),
             "e2e": {"value": world * S * n_e2e / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": n_e2e, "api": "alufe_b200.roi_align + MultiStreamTracker.step_async(pinned=True).result() (pinned host buffers)",
-                    "h2d_gbps": h2d * n_e2e / e2e_s / 1e9, "host_cpus_near_gpu": near_cpus},
+                    "h2d_gbps": h2d * n_e2e / e2e_s / 1e9, "pcie_probe_gbps": pcie_probe_gbps,
+                    "host_cpus_near_gpu": near_cpus},
             "gpu_launches": int(launches),
             "roofline": {"kernel": "roi_prep_kernel + roi_align_tma_kernel<10,10,float> (one ROI Align launch, NCHW maps)",
                          "bound": "hbm", "achieved": grp.roi_alg_bytes / roi_us_avg / 1e3, "peak": peak, "unit": "GB/s",

@@ -208,8 +208,9 @@ int  b200_tracker_update_matched(b200_tracker* t, int stream_idx, const int32_t*
                                  double cost_update_max, double maha_thr, void* stream);
 
 /* The same step without the wait (the reference's consumer is a queue, tracking.py:329): stages the inputs in a
- * pinned ring inside the handle, queues upload + step + download on `stream` and returns a ticket; at most four
- * steps may be in flight.  b200_tracker_step_result blocks until THAT step's result table is on the host and copies
+ * pinned ring inside the handle and returns a ticket; at most four steps may be in flight.  The kernels run on
+ * `stream`; the upload and the download of the result table run on two private streams of the handle, ordered with
+ * `stream` by events, so the DMA of step k+1 / k-1 overlaps the kernels of step k.  b200_tracker_step_result blocks until THAT step's result table is on the host and copies
  * it out.  b200_tracker_step_host is exactly step_host_async followed by step_result. */
 int  b200_tracker_step_host_async(b200_tracker* t, const int32_t* n_det_host, const double* boxes_host,
                                   const double* confs_host, const float* embs_host,
@@ -238,6 +239,26 @@ int  b200_tracker_import(b200_tracker* t, int stream_idx, int n, const int32_t* 
                          const int32_t* bank_len, const int32_t* miss, const int32_t* age,
                          const double* last_bbox, const double* last_conf, const double* last_cost,
                          int32_t next_id, void* stream);
+
+/* ---- result tables of all GPUs in one place, over NVLink peer memory --------------------
+ * The reference runs one inference process and hands every frame's matches to one consumer queue
+ * (tracking.py:329, :363); with streams sharded over the GPUs of a node (one process per GPU) the per-stream result
+ * tables have to meet again.  Every rank owns a receive ring of n_slots cells x world sources that its peers map
+ * through CUDA IPC.  push: one kernel stores `bytes` of this rank's tables into cell (seq % n_slots, rank) of EVERY
+ * rank's ring (plain 16-byte stores over NVLink / NVSwitch) and raises that cell's flag; it never waits for a peer
+ * unless the cell still holds tables the peer has not collected (n_slots pushes ago).  collect: one kernel waits until
+ * the cells of `seq` from all ranks are flagged, copies them to dst as [world][bytes] and acknowledges the slot.
+ * Sequence numbers count from 0 and every rank pushes every sequence number; pushes of one handle go to one stream.
+ * handle / connect: exchange the B200_IPC_HANDLE_BYTES-byte handles of all ranks (rank order) by any means
+ * (torch.distributed all_gather in dist.py) and connect once.  All ranks must synchronise before destroy. */
+typedef struct b200_peer_gather b200_peer_gather;
+#define B200_IPC_HANDLE_BYTES 64
+int  b200_peer_gather_create(b200_peer_gather** out, int rank, int world, int64_t bytes_per_rank, int n_slots);
+int  b200_peer_gather_handle(b200_peer_gather* g, void* handle_host);
+int  b200_peer_gather_connect(b200_peer_gather* g, const void* handles_host);
+int  b200_peer_gather_push(b200_peer_gather* g, const void* src, int64_t bytes, int64_t seq, void* stream);
+int  b200_peer_gather_collect(b200_peer_gather* g, void* dst, int64_t bytes, int64_t seq, void* stream);
+void b200_peer_gather_destroy(b200_peer_gather* g);
 
 #ifdef __cplusplus
 }
