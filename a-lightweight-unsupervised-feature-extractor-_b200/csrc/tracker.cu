@@ -656,6 +656,24 @@ __device__ __forceinline__ void update_entries(const Dev& d, int first, int tota
         const double cmax = reid ? d.reid_only_cost_max : d.cost_update_max;   // :563 / :530
         int app = on && !(conf < d.conf_update_min) && !(c > cmax);             // :418-421
         const int nst = st < 2 ? st + 1 : 2;
+        // Inputs of the EMA / bank push of this warp's four matches: they do not depend on the Kalman result (only whether
+        // they are USED does, through the posterior gate), so they are requested now and arrive during the float64 work.
+        float4 e[4], o[4];
+        size_t slots[4];
+        int len[4], head[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const bool on_u = __shfl_sync(0xffffffffu, (int)on, u * 8) != 0;
+            const unsigned long long sl = __shfl_sync(0xffffffffu, (unsigned long long)slot, u * 8);
+            const unsigned long long dt = __shfl_sync(0xffffffffu, (unsigned long long)det, u * 8);
+            slots[u] = (size_t)sl;
+            if (on_u) {
+                e[u] = reinterpret_cast<const float4*>(d.det_unit + (size_t)dt * cost::kD)[lane];
+                o[u] = reinterpret_cast<const float4*>(d.ema + slots[u] * cost::kD)[lane];
+                len[u] = d.bank_len[slots[u]];
+                head[u] = d.bank_head[slots[u]];
+            }
+        }
         double d2 = 0.0;
 #pragma unroll
         for (int v = 0; v < 6; ++v) {               // arithmetic variant x (stage 1: posterior gate, stage 2: none)
@@ -672,24 +690,10 @@ __device__ __forceinline__ void update_entries(const Dev& d, int first, int tota
         }
         if (on && sub == 0) d.kf_stage[slot] = (uint8_t)nst;
         if (app && !reid && d2 > d.maha_thr) app = 0;                           // :424-426
-        // EMA + bank push for this warp's four matches, all loads first
-        float4 e[4], o[4];
-        size_t slots[4];
-        int len[4], head[4];
+        // EMA + bank push for this warp's four matches
         bool go[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            go[u] = __shfl_sync(0xffffffffu, app, u * 8) != 0;
-            const unsigned long long sl = __shfl_sync(0xffffffffu, (unsigned long long)slot, u * 8);
-            const unsigned long long dt = __shfl_sync(0xffffffffu, (unsigned long long)det, u * 8);
-            slots[u] = (size_t)sl;
-            if (go[u]) {
-                e[u] = reinterpret_cast<const float4*>(d.det_unit + (size_t)dt * cost::kD)[lane];
-                o[u] = reinterpret_cast<const float4*>(d.ema + slots[u] * cost::kD)[lane];
-                len[u] = d.bank_len[slots[u]];
-                head[u] = d.bank_head[slots[u]];
-            }
-        }
+        for (int u = 0; u < 4; ++u) go[u] = __shfl_sync(0xffffffffu, app, u * 8) != 0;
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             if (!go[u]) continue;
@@ -775,14 +779,16 @@ __device__ inline int spawn_tracks(const Dev& d, int s, const int* born, int wan
 // Returns true when stream s has nothing more to do in this step (idle / empty frame / the assignment failed / stage 2
 // done).  FUSED (back_kernel): both stages, the ReID cost and the updates of a stream run in ONE CTA, so nothing is queued
 // for other kernels and the matches go to the stream's own update queue.
-template <int STAGE, bool FUSED>
+// INLINE: the caller computes the ReID cost itself between the stages (back_kernel) instead of queueing it for
+// cost2_kernel; OWNQ: the matches go to the stream's own update queue instead of the step's global one.
+template <int STAGE, bool INLINE, bool OWNQ>
 __device__ inline bool assign_body(const Dev& d, int s, unsigned char* smem_raw, int smem_matrix_floats) {
     __shared__ int scratch[kThreads / 32];
     __shared__ int s_rc;
     const int tid = threadIdx.x;
     int* cnt = d.cnt + s * kHdr;
     // both cost launches of this step are done: clear their queues for the next step
-    if (!FUSED && STAGE == 2 && s == 0 && tid == 0) { d.wcount[0] = 0; d.wcount[1] = 0; }
+    if (!INLINE && STAGE == 2 && s == 0 && tid == 0) { d.wcount[0] = 0; d.wcount[1] = 0; }
     int* hdr = d.hdr + s * kHdr;
     int* res = d.result + (size_t)s * d.res_stride;
     if (STAGE == 2 && cnt[C_MODE] == MODE_FAILED) {
@@ -850,7 +856,7 @@ __device__ inline bool assign_body(const Dev& d, int s, unsigned char* smem_raw,
                 out_ut[ut0 + pos] = d.tid[slot];
             }, scratch);
             __syncthreads();
-            note_matches(d, s, n_match, rows, C, d.MD, m_col, STAGE == 2, scratch, FUSED ? (int)sb + match0 : -1);
+            note_matches(d, s, n_match, rows, C, d.MD, m_col, STAGE == 2, scratch, OWNQ ? (int)sb + match0 : -1);
         }
     } else if (M > 0) {                             // no detections left for these rows: all missed
         for (int r = tid; r < M; r += blockDim.x) {
@@ -871,7 +877,7 @@ __device__ inline bool assign_body(const Dev& d, int s, unsigned char* smem_raw,
         n_left = block_compact(N, [&](int j) { return d.det_used[db + j] == 0; },
                                [&](int pos, int j) { d.ud1[db + pos] = j; }, scratch);
         if (tid == 0) { cnt[C_NU] = n_left; cnt[C_NMATCH] = n_match; cnt[C_NUT] = n_ut; }
-        if (!FUSED) enqueue_cost_work(d.work2, d.wcount + 1, s, n_left > 0 ? cnt[C_M2] : 0, n_left, scratch);
+        if (!INLINE) enqueue_cost_work(d.work2, d.wcount + 1, s, n_left > 0 ? cnt[C_M2] : 0, n_left, scratch);
         TRK_STAMP(5);
         __syncthreads();
         return false;
@@ -914,7 +920,7 @@ __global__ void __launch_bounds__(kThreads) assign_kernel(Dev d, int smem_matrix
     Span span((d.frame_id[0] & 7) * 6 + (STAGE == 1 ? 2 : 4));
     TRK_PDL_PROLOGUE();
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    assign_body<STAGE, false>(d, blockIdx.x, smem_raw, smem_matrix_floats);
+    assign_body<STAGE, false, false>(d, blockIdx.x, smem_raw, smem_matrix_floats);
 }
 
 // ---- fused step for tracking-sized streams (max_tracks <= 512, max_dets <= 256, hist_max <= 32): two launches ------
@@ -927,7 +933,10 @@ __global__ void __launch_bounds__(kThreads) assign_kernel(Dev d, int smem_matrix
 // back_kernel (one CTA of 256 threads per stream): stage-1 assignment and bookkeeping, the ReID-only cost of the
 // stream's long-lost rows (usually none), stage-2 assignment, births, purge, result table, and finally the Kalman / EMA
 // / bank updates of the stream's own matches.  Streams are independent, so nothing inside waits for another CTA.
-constexpr int kFrontWarps = 4;
+#ifndef B200_TRK_FRONT_WARPS
+#define B200_TRK_FRONT_WARPS 4
+#endif
+constexpr int kFrontWarps = B200_TRK_FRONT_WARPS;
 
 __global__ void __launch_bounds__(kFrontWarps * 32, 2) front_kernel(Dev d) {
     Span span((d.frame_id[0] & 7) * 6 + 0);
@@ -941,6 +950,7 @@ __global__ void __launch_bounds__(kFrontWarps * 32, 2) front_kernel(Dev d) {
     const size_t sb = (size_t)s * d.MT;
     const int n = d.n_det[s], nl = hdr[H_NLIVE];
     const int* order = d.order + sb;
+    if (s == 0 && g == 0 && tid == 0) d.wcount[2] = 0;     // three-launch chain: last step's update_kernel is done
     if (n < 0) {                                   // stream idle this step
         if (g == 0 && tid == 0) {
             cnt[C_MODE] = MODE_SKIP;
@@ -1019,7 +1029,11 @@ __device__ __forceinline__ void cluster_sync_all() {       // release / acquire 
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
-__global__ void __launch_bounds__(kThreads, 1) back_kernel(Dev d, int smem_matrix_floats) {
+// UPDATES = false (three-launch chain of stream groups): the same kernel without the update phase -- its matches go to
+// the step's global queue and update_kernel, spread over the whole GPU, does the arithmetic; at ~80 registers the CTA then
+// fits beside resident ROI Align CTAs, which the 238-register form does not.
+template <bool UPDATES>
+__global__ void __launch_bounds__(kThreads, UPDATES ? 1 : 2) back_kernel(Dev d, int smem_matrix_floats) {
     Span span((d.frame_id[0] & 7) * 6 + 2);
     TRK_PDL_PROLOGUE();
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1029,7 +1043,7 @@ __global__ void __launch_bounds__(kThreads, 1) back_kernel(Dev d, int smem_matri
     const int* cnt = d.cnt + s * kHdr;
     TRK_GSTAMP(4);
     if (rank == 0) {
-        if (!assign_body<1, true>(d, s, smem_raw, smem_matrix_floats)) {
+        if (!assign_body<1, true, UPDATES>(d, s, smem_raw, smem_matrix_floats)) {
             TRK_GSTAMP(5);
             // ReID-only cost (:552-558) of this stream's long-lost rows against the leftover detections
             const int M2 = cnt[C_M2], NU = cnt[C_NU];
@@ -1041,10 +1055,11 @@ __global__ void __launch_bounds__(kThreads, 1) back_kernel(Dev d, int smem_matri
             __syncthreads();
         }
         TRK_GSTAMP(6);
-        assign_body<2, true>(d, s, smem_raw, smem_matrix_floats);
+        assign_body<2, true, UPDATES>(d, s, smem_raw, smem_matrix_floats);
         __syncthreads();
         TRK_GSTAMP(7);
     }
+    if (!UPDATES) return;
     if (nrank > 1) cluster_sync_all();
     if (cnt[C_MODE] != MODE_NORMAL) return;        // idle, empty or failed in stage 1: nothing was matched
     // ---- update_matched, arithmetic half, for this stream's own queue (stage 1 then stage 2 entries) ----
@@ -1222,7 +1237,9 @@ struct b200_tracker {
     int cost_grid = 0, cost1_grid = 0, upd_grid = 0;   // persistent CTAs of the cost kernels (resident CTAs per SM x SMs)
     size_t assign_smem = 0;
     int smem_matrix_floats = 0;
-    bool fused = false;                 // tracking-sized streams: front_kernel + back_kernel instead of the six-kernel chain
+    // tracking-sized streams: 2 = front_kernel + back_kernel (a few streams, latency mode), 3 = front_kernel + back_kernel
+    // without updates + update_kernel (stream groups), 6 = the six-kernel chain (any size)
+    int chain = 6;
     int front_resident = 0;             // CTAs of front_kernel the device holds at once
     size_t front_smem = 0, back_smem = 0;
 };
@@ -1373,22 +1390,32 @@ extern "C" int b200_tracker_create(b200_tracker** out, int n_streams, int max_tr
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trk::cost1_sparse_kernel, trk::kCost1Warps * 32, 0);
         t->cost1_grid = sms * (per_sm > 0 ? per_sm : 1);
         t->upd_grid = sms * 2;
-        // Two-launch step for a handful of tracking-sized streams (latency mode).  Measured (profiles/r02_group_probe.txt):
-        // one stream 43.5 -> 40.8 us per frame; with 64 streams the chain alone is faster (68 -> 59 us) but its CTAs need
-        // a whole SM each and cannot start beside ROI Align of the next frame (overlapped step 232 -> 273 us), so stream
-        // groups keep the six-kernel chain.  B200TRACK_LEGACY_CHAIN=1 / B200TRACK_FUSED_CHAIN=1 force either path (tests).
-        t->fused = max_tracks <= 512 && max_dets <= 256 && d.HIST <= 32 && getenv("B200TRACK_LEGACY_CHAIN") == nullptr &&
-                   (n_streams <= 8 || getenv("B200TRACK_FUSED_CHAIN") != nullptr);
-        if (t->fused) {
+        // Fewer, fatter launches for tracking-sized streams.  Two launches for a handful of streams (latency mode: one
+        // stream 43.5 -> 35.8 us per frame).  With a stream group the chain shares the GPU with ROI Align of the next frame,
+        // where every kernel boundary costs 25-40 us of waiting for SM slots and a CTA that needs a whole SM (back_kernel
+        // with the updates: 238 registers x 256 threads) waits longest (two launches: chain alone 68 -> 59 us but the
+        // overlapped step 232 -> 273 us), so groups use three launches: front, back without updates (80 registers), and
+        // the update kernel spread over the GPU.  B200TRACK_CHAIN=2|3|6 forces a path (tests, experiments).
+        const bool fits = max_tracks <= 512 && max_dets <= 256 && d.HIST <= 32;
+        t->chain = !fits ? 6 : n_streams <= 8 ? 2 : 3;
+        if (const char* e = getenv("B200TRACK_CHAIN")) {
+            const int want = atoi(e);
+            if (want == 6 || (fits && (want == 2 || want == 3))) t->chain = want;
+        }
+        if (t->chain != 6) {
             t->front_smem = sizeof(int) * 2 * (size_t)max_tracks;
             size_t bs = t->assign_smem;
             if (cost::smem_bytes(d.HIST) > bs) bs = cost::smem_bytes(d.HIST);
             if (sizeof(double) * (trk::kThreads / 32) * 4 * 96 > bs) bs = sizeof(double) * (trk::kThreads / 32) * 4 * 96;
             t->back_smem = bs;
-            cudaFuncSetAttribute(trk::back_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
+            cudaFuncSetAttribute(trk::back_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
+            cudaFuncSetAttribute(trk::back_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
             per_sm = 1;
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trk::front_kernel, trk::kFrontWarps * 32, t->front_smem);
             t->front_resident = sms * (per_sm > 0 ? per_sm : 1);
+            // experiment knobs: total CTAs of the front / update kernels (a smaller footprint leaves SM room to ROI Align)
+            if (const char* e = getenv("B200TRACK_FRONT_CTAS")) t->front_resident = atoi(e) > 0 ? atoi(e) : t->front_resident;
+            if (const char* e = getenv("B200TRACK_UPD_CTAS")) t->upd_grid = atoi(e) > 0 ? atoi(e) : t->upd_grid;
         }
     }
     *out = t;
@@ -1447,13 +1474,21 @@ extern "C" int b200_tracker_step(b200_tracker* t, const int32_t* n_det, const do
     const size_t csm = cost::smem_bytes(d.HIST);
     const int cost_grid = t->cost_grid;
     int rc;
-    if (t->fused) {
+    if (t->chain != 6) {
         // CTAs per stream of the front kernel: fill the device once, never more than one CTA per four rows
         int G = t->front_resident / d.S;
         const int gmax = (d.MT + 3) / 4;
         G = G < 1 ? 1 : G > gmax ? gmax : G;
         trk::front_kernel<<<dim3(G, d.S), trk::kFrontWarps * 32, t->front_smem, st>>>(d);
         if ((rc = check_launch("trk front_kernel"))) return rc;
+        if (t->chain == 3) {
+            trk::back_kernel<false><<<d.S, trk::kThreads, t->assign_smem > cost::smem_bytes(d.HIST) ? t->assign_smem
+                                                                                                    : cost::smem_bytes(d.HIST), st>>>(
+                d, t->smem_matrix_floats);
+            if ((rc = check_launch("trk back_kernel<false>"))) return rc;
+            trk::update_kernel<<<t->upd_grid, trk::kUpdWarps * 32, 0, st>>>(d);
+            return check_launch("trk update_kernel");
+        }
         // few streams: a cluster of CTAs per stream shares the updates, and the kernel is resident when the front one ends
         const bool few = d.S <= 8;
         const int cl = few ? trk::kBackCluster : 1;
@@ -1466,7 +1501,7 @@ extern "C" int b200_tracker_step(b200_tracker* t, const int32_t* n_det, const do
         attr[1].val.clusterDim.x = cl; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = few ? 2 : 0;
-        (void)cudaLaunchKernelEx(&cfg, trk::back_kernel, d, t->smem_matrix_floats);
+        (void)cudaLaunchKernelEx(&cfg, trk::back_kernel<true>, d, t->smem_matrix_floats);
         return check_launch("trk back_kernel");
     }
     trk::begin_kernel<<<dim3(d.S, 2), t->begin_threads, 0, st>>>(d);

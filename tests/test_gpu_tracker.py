@@ -86,15 +86,15 @@ def _oracle_state(ref):
     dict(n=512, H=1280, W=1280, frames=12, scene=dict(drop=0.1, churn=0.1, churn_every=4),
          conf=dict(lost_reid_after=3, max_age=8), every=3),
 ])
-@pytest.mark.parametrize("chain", ["fused", "six_kernels"])
+@pytest.mark.parametrize("chain", ["2", "3", "6"])
 def test_tracker_vs_oracle(case, chain, monkeypatch):
-    """Both device paths of the step: the two-launch fused chain (handles of at most 512 tracks x 256 detections) and the
-    six-kernel chain that larger handles use (forced with B200TRACK_LEGACY_CHAIN for the small cases)."""
+    """All device paths of the step: the two-launch chain (few streams), the three-launch chain (stream groups) -- both
+    for handles of at most 512 tracks x 256 detections -- and the six-kernel chain that larger handles use (each forced
+    with B200TRACK_CHAIN)."""
     cfg = dict(SHIPPED_CONF, **case["conf"])
-    if chain == "fused" and case["n"] > 128:
+    if chain != "6" and case["n"] > 128:
         pytest.skip("crowds need more than 512 track slots: six-kernel chain only")
-    if chain == "six_kernels":
-        monkeypatch.setenv("B200TRACK_LEGACY_CHAIN", "1")
+    monkeypatch.setenv("B200TRACK_CHAIN", chain)
     ref = tracker_ref.TrackerRef(cfg)
     big = case["n"] > 128
     trk = Tracking(conf=cfg, max_tracks=max(768, 3 * case["n"]) if big else 512, max_dets=max(192, case["n"]))
@@ -209,10 +209,10 @@ def test_tracker_grows_like_the_unbounded_reference():
     assert trk.next_id == ref.next_id
 
 
-@pytest.mark.parametrize("chain", ["default", "fused", "six_kernels"])
+@pytest.mark.parametrize("chain", ["default", "2", "3", "6"])
 def test_multistream_equals_independent_trackers(chain, monkeypatch):
     if chain != "default":
-        monkeypatch.setenv("B200TRACK_FUSED_CHAIN" if chain == "fused" else "B200TRACK_LEGACY_CHAIN", "1")
+        monkeypatch.setenv("B200TRACK_CHAIN", chain)
     cfg = dict(SHIPPED_CONF, lost_reid_after=5, max_age=15)
     S, MD = 5, 48
     ms = MultiStreamTracker(S, cfg, max_tracks=128, max_dets=MD)
@@ -479,10 +479,12 @@ def _check_async(ms, handle, want, f):
         assert got[0] == w[0] and got[1] == w[1] and got[2] == w[2], (f, s)
 
 
-@pytest.mark.parametrize("seed", range(10))
-def test_tracker_fuzz_vs_oracle(seed):
+@pytest.mark.parametrize("seed,chain", [(k, None) for k in range(10)] + [(k, "3") for k in range(10, 16)] + [(16, "6"), (17, "6")])
+def test_tracker_fuzz_vs_oracle(seed, chain, monkeypatch):
     """Randomised differential test: random hyper-parameters (including degenerate ones: one-row banks,
     top-1, immediate purge, ReID stage almost always on), random scene dynamics, empty and idle frames."""
+    if chain is not None:
+        monkeypatch.setenv("B200TRACK_CHAIN", chain)
     rng = np.random.default_rng(1000 + seed)
     cfg = dict(SHIPPED_CONF,
                hist_max=int(rng.choice([1, 2, 5, 30, 33, 64])), emb_top_k=int(rng.choice([1, 3, 5, 9])),
