@@ -11,6 +11,9 @@ __global__ void sleeper_kernel(long long ns) {
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     } while ((long long)(t - t0) < ns);
 }
+extern "C" int sleeper_carveout(int percent) {      // -1 = driver default, 100 = maximum shared memory
+    return (int)cudaFuncSetAttribute(sleeper_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, percent);
+}
 extern "C" int sleeper_launch(int grid, int block, int smem, long long ns, void* stream) {
     static int configured = 0;
     if (!configured) {

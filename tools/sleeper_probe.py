@@ -23,7 +23,13 @@ cases = [("no kernel on stream B", None),
          ("6 kernels of 296 x 1024 thr, 10 us each", [(296, 1024, 0, 10000)] * 6),
          ("148 x 32 thr, 150 us", [(148, 32, 0, 150000)]),
          ("148 x 1024 thr, 150 us", [(148, 1024, 0, 150000)])]
-for name, ks in cases:
+cases = [(n + "  [default carve-out]", k, -1) for n, k in cases[:4]] + \
+        [(n + "  [max-shared carve-out]", k, 100) for n, k in cases[1:4]] + \
+        [(n + "  [default carve-out]", k, -1) for n, k in cases[4:]] + \
+        [("296 x 128 thr, 60 us  [max-shared carve-out]", [(296, 128, 0, 60000)], 100),
+         ("148 x 256 thr, 120 us  [max-shared carve-out]", [(148, 256, 0, 120000)], 100)]
+for name, ks, carve in cases:
+    sl.sleeper_carveout(carve)
     def assoc(i, ks=ks):
         if ks is None:
             return
@@ -32,4 +38,4 @@ for name, ks in cases:
     g.assoc = assoc
     g.timed(0, W)
     ms, _ = g.timed(W, K)
-    print("  %-44s %7.1f us per step" % (name, ms / K * 1e3), flush=True)
+    print("  %-72s %7.1f us per step" % (name, ms / K * 1e3), flush=True)
