@@ -523,6 +523,14 @@ __device__ __forceinline__ void cost1_row32(const Dev& d, int s, int r, size_t s
         }
         unsigned todo = __ballot_sync(0xffffffffu, alive);
         float c_app = 0.0f;
+        // the first survivor's embedding is requested together with the bank, not after the bank's norms have been
+        // computed: one dependent global round trip per row less
+        float4 dv_first = make_float4(0, 0, 0, 0);
+        if (todo) {
+            const int jf = __ffs(todo) - 1;
+            if (FLY) dv_first = reinterpret_cast<const float4*>(d.embs + (db + j0 + jf) * cost::kD)[lane];
+            else dv_first = reinterpret_cast<const float4*>(d.det_unit + (db + j0 + jf) * cost::kD)[lane];
+        }
         if (todo && !have_bank) {
             float q[32];
 #pragma unroll
@@ -538,12 +546,17 @@ __device__ __forceinline__ void cost1_row32(const Dev& d, int s, int r, size_t s
             inv = __fdiv_rn(1.0f, __fadd_rn(sqrtf(q[0]), 1e-12f));
             have_bank = true;
         }
+        bool first = true;
         while (todo) {
             const int jl = __ffs(todo) - 1;
             todo &= todo - 1;
-            float4 dv;
-            if (FLY) dv = cost::unit_row(reinterpret_cast<const float4*>(d.embs + (db + j0 + jl) * cost::kD)[lane]);
-            else dv = reinterpret_cast<const float4*>(d.det_unit + (db + j0 + jl) * cost::kD)[lane];
+            float4 dv = dv_first;
+            if (!first) {
+                if (FLY) dv = reinterpret_cast<const float4*>(d.embs + (db + j0 + jl) * cost::kD)[lane];
+                else dv = reinterpret_cast<const float4*>(d.det_unit + (db + j0 + jl) * cost::kD)[lane];
+            }
+            first = false;
+            if (FLY) dv = cost::unit_row(dv);
             float p[32];
 #pragma unroll
             for (int t = 0; t < 32; ++t) {
@@ -1366,6 +1379,11 @@ extern "C" int b200_tracker_create(b200_tracker** out, int n_streams, int max_tr
     t->assign_smem = wb + mat;
     // The opt-in belongs to the kernel function (per device), not to this handle: always the full budget, so
     // handles of different capacities can be stepped in any order.
+    if (getenv("B200TRACK_CARVEOUT_MAX") != nullptr) {           // experiment: see DESIGN.md section 4, last paragraph
+        const int mx = cudaSharedmemCarveoutMaxShared;
+        cudaFuncSetAttribute(trk::front_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+        cudaFuncSetAttribute(trk::back_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+    }
     cudaFuncSetAttribute(trk::assign_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
     cudaFuncSetAttribute(trk::assign_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
     cudaFuncSetAttribute(trk::cost2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cost::smem_bytes(cost::kMaxBank));
