@@ -594,7 +594,7 @@ __device__ __forceinline__ int row_minima_pass(const float* cost, int R, int Cc,
 // pre_col / pre_val (optional, R entries in global memory): the producer of the matrix already knows every
 // row's unique minimum (column, or -1) and has checked the row (-2 = NaN / -inf): when the matrix is not to be
 // staged, the pass over it is skipped altogether.
-__device__ inline int solve_block(const float* cost, int R, int Cc, int ld, const Work& w, float* stage_or_null,
+__device__ __noinline__ inline int solve_block(const float* cost, int R, int Cc, int ld, const Work& w, float* stage_or_null,
                                   const int* pre_col = nullptr, const float* pre_val = nullptr) {
     const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31;
     int bad = 0;

@@ -1354,11 +1354,6 @@ int launch_tile(const T* feat, int B, int C, int H, int W, const float* rois, lo
     const int dev = device_ordinal();
     if (!configured[dev]) {
         B200_CUDA(cudaFuncSetAttribute(fused, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kBytesPerCta));
-        if (getenv("B200TRACK_CARVEOUT_MAX") != nullptr) {       // experiment: see DESIGN.md section 4, last paragraph
-            B200_CUDA(cudaFuncSetAttribute(fused, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-            B200_CUDA(cudaFuncSetAttribute(roi_prep_kernel<PH, PW>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                           cudaSharedmemCarveoutMaxShared));
-        }
         configured[dev] = true;
     }
     const int ctiles = (C + 31) / 32;

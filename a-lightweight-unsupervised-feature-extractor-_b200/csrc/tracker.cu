@@ -1379,11 +1379,6 @@ extern "C" int b200_tracker_create(b200_tracker** out, int n_streams, int max_tr
     t->assign_smem = wb + mat;
     // The opt-in belongs to the kernel function (per device), not to this handle: always the full budget, so
     // handles of different capacities can be stepped in any order.
-    if (getenv("B200TRACK_CARVEOUT_MAX") != nullptr) {           // experiment: see DESIGN.md section 4, last paragraph
-        const int mx = cudaSharedmemCarveoutMaxShared;
-        cudaFuncSetAttribute(trk::front_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-        cudaFuncSetAttribute(trk::back_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-    }
     cudaFuncSetAttribute(trk::assign_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
     cudaFuncSetAttribute(trk::assign_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
     cudaFuncSetAttribute(trk::cost2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cost::smem_bytes(cost::kMaxBank));

@@ -161,6 +161,30 @@ def test_app_cost_vs_oracle(M, N, T):
         assert_close(got.cpu().numpy(), want, rtol=1e-5, atol=2e-6, what="C_app")
 
 
+@pytest.mark.parametrize("kernel,M,N,T", [("2", 260, 130, 30), ("2", 300, 64, 9), ("2", 512, 512, 30), ("2", 70, 64, 32),
+                                          ("2", 257, 1000, 32), ("1", 512, 512, 30), ("1", 260, 130, 30)])
+def test_app_cost_tensor_core_kernels_vs_oracle(kernel, M, N, T, monkeypatch):
+    """Both tcgen05 forms of the dense appearance cost, each forced with B200TRACK_TC_KERNEL: 1 = a CTA per (bank tile,
+    detection tile) pair, 2 = a CTA keeps its bank tile resident and walks the detection tiles (two TMEM accumulators, the
+    tensor core one tile ahead of the epilogue).  Ragged tiles in both directions, empty / short / full banks, the EMA
+    fallback, top-k beyond five and the max-similarity variant."""
+    monkeypatch.setenv("B200TRACK_TC_KERNEL", kernel)
+    rng = np.random.default_rng(3 * M + 11 * N + T)
+    lens = rng.integers(0, T + 1, M)
+    lens[0], lens[1], lens[2], lens[M - 1] = T, 0, 1, T
+    bank = rng.standard_normal((M, T, 128)).astype(np.float32)
+    ema = rng.standard_normal((M, 128)).astype(np.float32)
+    det = rng.standard_normal((N, 128)).astype(np.float32) * 0.3
+    banks = [[bank[i, t] for t in range(lens[i])] for i in range(M)]
+    for topk, mean, fb in [(5, True, True), (5, True, False), (1, False, True), (9, True, True)]:
+        want = cost_ref.app_cost_topk(banks, list(det), topk=topk, use_topk_mean=mean,
+                                      fallback_embs=list(ema) if fb else None)
+        got = cost.app_cost_topk(torch.from_numpy(bank).cuda(), torch.from_numpy(lens.astype(np.int32)).cuda(),
+                                 torch.from_numpy(det).cuda(), topk=topk, use_topk_mean=mean,
+                                 fallback=torch.from_numpy(ema).cuda() if fb else None)
+        assert_close(got.cpu().numpy(), want, rtol=1e-5, atol=2e-6, what="C_app kernel %s topk %d" % (kernel, topk))
+
+
 def test_app_cost_c4_size_properties():
     """512 x 512 x 30 banks (BASELINE config 4): a track whose bank holds a detection's own
     embedding k times scores exactly that detection with cost ~0; costs lie in [0, 2]."""
