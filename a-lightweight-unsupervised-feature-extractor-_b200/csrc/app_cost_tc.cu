@@ -272,7 +272,7 @@ constexpr int kWalkImageBytes = 3 * kWalkSplitBytes;          // 48 KB
 constexpr int kWalkEpiWarps = 8;
 constexpr int kWalkThreads = (kWalkEpiWarps + 1) * 32;
 constexpr int kWalkScratch = kWalkEpiWarps * 32 * 33 * 4;
-constexpr int kWalkSmem = kImageBytes + 2 * kWalkImageBytes + kWalkScratch + 64;
+constexpr int kWalkSmem = kImageBytes + 2 * kWalkImageBytes + kWalkScratch + 96;
 constexpr unsigned kIdescWalk = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(kWalkCols >> 3) << 17) | ((unsigned)(kRows >> 4) << 24);
 
 __device__ __forceinline__ void tc_mbar_arrive(unsigned bar) {
@@ -288,8 +288,17 @@ app_tc_walk_kernel(const unsigned char* __restrict__ imgA, const unsigned char* 
     unsigned char* sB = smem + kImageBytes;                                   // two buffers of kWalkImageBytes
     float* scratch = reinterpret_cast<float*>(smem + kImageBytes + 2 * kWalkImageBytes);
     const unsigned bar0 = smem_u32(smem + kImageBytes + 2 * kWalkImageBytes + kWalkScratch);
-    // bar0: bank image landed; +8 / +16: detection buffer landed; +24 / +32: accumulator full; +40 / +48: accumulator free
-    unsigned* tmem_slot = reinterpret_cast<unsigned*>(smem + kImageBytes + 2 * kWalkImageBytes + kWalkScratch + 56);
+    // bar0: bank image landed; +8 / +16: detection buffer landed; +24 / +32: accumulator full; +40 / +48: accumulator free;
+    // +56 / +64: the products that read detection buffer 0 / 1 have completed in EVERY CTA of the cluster
+    unsigned* tmem_slot = reinterpret_cast<unsigned*>(smem + kImageBytes + 2 * kWalkImageBytes + kWalkScratch + 72);
+    // A cluster of two CTAs (two bank tiles) shares the delivery of the detection tiles: each CTA fetches HALF of every tile
+    // and the copy engine delivers it to the same place in both CTAs (.multicast::cluster), which halves the L2 traffic of
+    // the detection images.  No cluster-wide barrier in the loop: "buffer free everywhere" is an mbarrier that both CTAs'
+    // tcgen05.commit arrive on (commit with .multicast::cluster), "tile landed" counts the bytes of both halves.
+    unsigned rank, nrank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(nrank));
+    const unsigned short cta_mask = (unsigned short)((1u << nrank) - 1u);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int tile_m = blockIdx.x;
 
@@ -302,10 +311,13 @@ app_tc_walk_kernel(const unsigned char* __restrict__ imgA, const unsigned char* 
         tc_mbar_init(bar0 + 8, 1); tc_mbar_init(bar0 + 16, 1);
         tc_mbar_init(bar0 + 24, 1); tc_mbar_init(bar0 + 32, 1);
         tc_mbar_init(bar0 + 40, kWalkEpiWarps); tc_mbar_init(bar0 + 48, kWalkEpiWarps);
+        tc_mbar_init(bar0 + 56, nrank); tc_mbar_init(bar0 + 64, nrank);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
+    if (nrank > 1)                               // the peer's barriers exist before anything is delivered to them
+        asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     const unsigned tmem = *tmem_slot;
 
@@ -315,8 +327,16 @@ app_tc_walk_kernel(const unsigned char* __restrict__ imgA, const unsigned char* 
             auto load_b = [&](int step) {
                 const int buf = step & 1;
                 tc_mbar_expect_tx(bar0 + 8 + 8 * buf, (unsigned)kWalkImageBytes);
-                tc_bulk_load(smem_u32(sB + buf * kWalkImageBytes), imgB + (size_t)step * kWalkImageBytes, kWalkImageBytes,
-                             bar0 + 8 + 8 * buf);
+                if (nrank > 1) {                 // my share of the tile, delivered to every CTA of the cluster
+                    const unsigned part = (unsigned)kWalkImageBytes / nrank;
+                    const unsigned dst = smem_u32(sB + buf * kWalkImageBytes) + rank * part;
+                    const unsigned char* src = imgB + (size_t)step * kWalkImageBytes + (size_t)rank * part;
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;\n"
+                                 ::"r"(dst), "l"(src), "r"(part), "r"(bar0 + 8 + 8 * buf), "h"(cta_mask) : "memory");
+                } else {
+                    tc_bulk_load(smem_u32(sB + buf * kWalkImageBytes), imgB + (size_t)step * kWalkImageBytes, kWalkImageBytes,
+                                 bar0 + 8 + 8 * buf);
+                }
             };
             tc_mbar_expect_tx(bar0, (unsigned)kImageBytes);
             tc_bulk_load(smem_u32(sA), imgA + (size_t)tile_m * kImageBytes, kImageBytes, bar0);
@@ -350,9 +370,14 @@ app_tc_walk_kernel(const unsigned char* __restrict__ imgA, const unsigned char* 
                 }
                 asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
                              ::"r"(bar0 + 24 + 8 * buf) : "memory");
-                // the products of step - 1 have finished reading the other detection buffer: refill it with tile step + 1
+                if (nrank > 1)                   // ... and tell every CTA of the cluster that this buffer has been read here
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n"
+                                 ::"r"(bar0 + 56 + 8 * buf), "h"(cta_mask) : "memory");
+                // the products of step - 1 have finished reading the other detection buffer (in every CTA that receives
+                // what is loaded into it): refill it with tile step + 1
                 if (step >= 1 && step + 1 < n_steps) {
-                    tc_mbar_wait(bar0 + 24 + 8 * (buf ^ 1), (unsigned)(((step - 1) >> 1) & 1));
+                    if (nrank > 1) tc_mbar_wait(bar0 + 56 + 8 * (buf ^ 1), (unsigned)(((step - 1) >> 1) & 1));
+                    else tc_mbar_wait(bar0 + 24 + 8 * (buf ^ 1), (unsigned)(((step - 1) >> 1) & 1));
                     load_b(step + 1);
                 }
             }
@@ -433,6 +458,8 @@ app_tc_walk_kernel(const unsigned char* __restrict__ imgA, const unsigned char* 
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
+    if (nrank > 1)                               // no CTA leaves while its peer may still deliver to it or arrive on its barriers
+        asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(128u) : "memory");
 }
 
@@ -474,8 +501,20 @@ int app_cost_tc(const float* bank, const int32_t* bank_len, const float* fallbac
     rc = check_launch("app_tc_prep_kernel");
     if (rc == B200_OK) {
         if (walk) {
-            app_tc_walk_kernel<<<m_tiles, kWalkThreads, kWalkSmem, st>>>(imgA, imgB, bank_len, fallback != nullptr, M, N, T, topk,
-                                                                         use_topk_mean, C_app, ldc, n_tiles);
+            int cl = m_tiles % 2 == 0 ? 2 : 1;  // pairs of bank tiles share the delivery of the detection tiles
+            if (const char* e = getenv("B200TRACK_TC_CLUSTER")) cl = (atoi(e) == 2 && m_tiles % 2 == 0) ? 2 : 1;
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)m_tiles);
+            cfg.blockDim = dim3(kWalkThreads);
+            cfg.dynamicSmemBytes = kWalkSmem;
+            cfg.stream = st;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            (void)cudaLaunchKernelEx(&cfg, app_tc_walk_kernel, (const unsigned char*)imgA, (const unsigned char*)imgB, bank_len,
+                                     (int)(fallback != nullptr), M, N, T, topk, use_topk_mean, C_app, ldc, n_tiles);
             rc = check_launch("app_tc_walk_kernel");
         } else {
             app_tc_kernel<<<dim3(n_tiles, m_tiles), 128, kTcSmem, st>>>(imgA, imgB, bank_len, fallback != nullptr, M, N, T, topk,
