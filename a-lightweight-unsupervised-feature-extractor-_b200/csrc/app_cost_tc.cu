@@ -256,15 +256,16 @@ app_tc_kernel(const unsigned char* __restrict__ imgA, const unsigned char* __res
 //                        so the tensor core runs one tile ahead of the epilogue;
 //   warps 0-7            epilogue: warp w waits for "accumulator full", reads TMEM lanes 32 (w % 4) .. + 31 (track w % 4 of
 //                        the tile) and columns 32 (w / 4) .. + 31 of the tile, reduces the top-k and signals "accumulator free".
-// No CTA-wide barrier inside the loop.  BASELINE config 4: 30.1 us (first form) -> 23.7 us, whole call 49 -> 41 us.
+// No CTA-wide barrier inside the loop.  BASELINE config 4: 30.1 us (first form) -> 23.4 us, whole call 49 -> 40 us.
 // (First version of this form: thread 0 issued the products AND ran its share of the epilogue, with a __syncthreads per
-// step: ncu showed the other warps 46 % of their time at that barrier; 28.5 us.  What limits it now is the delivery of the
-// detection tiles: every CTA pulls all of them out of L2 (128 CTAs x 384 KB + 12 MB of bank images = 61 MB, ~11 us at L2
-// bandwidth) and with two buffers a 48 KB copy has one tile's worth of tensor time to arrive, so the epilogue warps wait
-// for "accumulator full" half the time (profiles/r02_app_cost_tc.md).  A variant that delivered every tile once per
-// cluster with .multicast::cluster and a cluster barrier per step was slower -- 57 / 56 / 99 us for clusters of 2 / 4 / 8:
-// 230 KB CTAs are one per SM, and such clusters schedule badly; the next step is the same multicast with per-buffer
-// remote mbarriers instead of cluster barriers, or operands converted from float32 inside the kernel (-33 % bytes).)
+// step: ncu showed the other warps 46 % of their time at that barrier; 28.5 us.  Then, each measured and none of them the
+// limit: the products' issue loop (descriptors rebuilt per product inside an ELECT loop, 13 -> 8 instructions per
+// UTCHMMA), the L2 traffic of the detection tiles (half-tile multicast between CTA pairs: 24.5 us; cluster-wide multicast
+// with cluster barriers: 57 / 56 / 99 us for clusters of 2 / 4 / 8), L2 hot-spotting (every CTA pair now starts its walk
+// at a different tile).  What is left is shared-memory bandwidth: per step the six products read 288 KB of operands out
+// of shared memory while 48 KB land and the epilogue transposes 64 KB through it -- ~3 100 cycles at 128 B/clk before
+// any contention.  profiles/r02_app_cost_tc.md.  Next: a wider detection tile per product (fewer re-reads of the bank
+// image), which needs the two-CTA form of the instruction to fit in shared memory.)
 constexpr int kWalkCols = 64;                                 // detections per step
 constexpr int kWalkLBO = kWalkCols * 16;                      // next K chunk inside a 64-row image
 constexpr int kWalkSplitBytes = kChunks * kWalkCols * 16;     // 16 KB
@@ -299,8 +300,12 @@ app_tc_walk_kernel(const unsigned char* __restrict__ imgA, const unsigned char* 
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
     asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(nrank));
     const unsigned short cta_mask = (unsigned short)((1u << nrank) - 1u);
+
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int tile_m = blockIdx.x;
+    // Every CTA (pair) starts its walk at a different detection tile: if all of them asked L2 for the same 48 KB at the same
+    // time, the few L2 slices that hold those lines would serve 128 SMs while the rest of the L2 idles.
+    const int first_tile = (int)((unsigned)tile_m / nrank) % n_steps;
 
     if (warp == 0) {                             // two accumulators of 64 float32 columns
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(128u) : "memory");
@@ -322,44 +327,54 @@ app_tc_walk_kernel(const unsigned char* __restrict__ imgA, const unsigned char* 
     const unsigned tmem = *tmem_slot;
 
     if (warp == kWalkEpiWarps) {
-        // ---- producer: bulk copies + tcgen05.mma, one thread ----
-        if (lane == 0) {
-            auto load_b = [&](int step) {
-                const int buf = step & 1;
-                tc_mbar_expect_tx(bar0 + 8 + 8 * buf, (unsigned)kWalkImageBytes);
-                if (nrank > 1) {                 // my share of the tile, delivered to every CTA of the cluster
-                    const unsigned part = (unsigned)kWalkImageBytes / nrank;
-                    const unsigned dst = smem_u32(sB + buf * kWalkImageBytes) + rank * part;
-                    const unsigned char* src = imgB + (size_t)step * kWalkImageBytes + (size_t)rank * part;
-                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;\n"
-                                 ::"r"(dst), "l"(src), "r"(part), "r"(bar0 + 8 + 8 * buf), "h"(cta_mask) : "memory");
-                } else {
-                    tc_bulk_load(smem_u32(sB + buf * kWalkImageBytes), imgB + (size_t)step * kWalkImageBytes, kWalkImageBytes,
-                                 bar0 + 8 + 8 * buf);
-                }
-            };
+        // ---- producer: bulk copies + tcgen05.mma.  The whole warp walks the loop so that every operand is warp-uniform
+        // (uniform registers feed UTCHMMA / UBLKCP directly; with operands computed by one lane inside a divergent branch
+        // ptxas wraps each of them in an ELECT / R2UR / BRA.U.ANY loop); lane 0 alone issues. ----
+        const bool leader = lane == 0;
+        const unsigned tm = __shfl_sync(0xffffffffu, tmem, 0);
+        auto load_b = [&](int step) {            // leader only
+            const int buf = step & 1;
+            const int tile_n = (first_tile + step) % n_steps;
+            tc_mbar_expect_tx(bar0 + 8 + 8 * buf, (unsigned)kWalkImageBytes);
+            if (nrank > 1) {                     // my share of the tile, delivered to every CTA of the cluster
+                const unsigned part = (unsigned)kWalkImageBytes / nrank;
+                const unsigned dst = smem_u32(sB + buf * kWalkImageBytes) + rank * part;
+                const unsigned char* src = imgB + (size_t)tile_n * kWalkImageBytes + (size_t)rank * part;
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;\n"
+                             ::"r"(dst), "l"(src), "r"(part), "r"(bar0 + 8 + 8 * buf), "h"(cta_mask) : "memory");
+            } else {
+                tc_bulk_load(smem_u32(sB + buf * kWalkImageBytes), imgB + (size_t)tile_n * kWalkImageBytes, kWalkImageBytes,
+                             bar0 + 8 + 8 * buf);
+            }
+        };
+        if (leader) {
             tc_mbar_expect_tx(bar0, (unsigned)kImageBytes);
             tc_bulk_load(smem_u32(sA), imgA + (size_t)tile_m * kImageBytes, kImageBytes, bar0);
             load_b(0);
             if (n_steps > 1) load_b(1);
-            tc_mbar_wait(bar0, 0);
-            for (int step = 0; step < n_steps; ++step) {
-                const int buf = step & 1;
-                const unsigned use = (unsigned)((step >> 1) & 1);             // parity of this use of buffer / accumulator `buf`
-                if (step >= 2) tc_mbar_wait(bar0 + 40 + 8 * buf, use ^ 1u);   // the epilogue of step - 2 has released the accumulator
-                tc_mbar_wait(bar0 + 8 + 8 * buf, use);                        // the detection tile has landed
-                asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-                // six split products, smallest first; eight K steps of 16 each
-                const int pa[6] = {2, 0, 1, 1, 0, 0}, pb[6] = {0, 2, 1, 0, 1, 0};
-                const unsigned acc = tmem + (unsigned)(buf * kWalkCols);
+        }
+        __syncwarp();
+        tc_mbar_wait(bar0, 0);
+        const unsigned long long dA = umma_desc(smem_u32(sA));
+        for (int step = 0; step < n_steps; ++step) {
+            const int buf = step & 1;
+            const unsigned use = (unsigned)((step >> 1) & 1);                 // parity of this use of buffer / accumulator `buf`
+            if (step >= 2) tc_mbar_wait(bar0 + 40 + 8 * buf, use ^ 1u);       // the epilogue of step - 2 has released the accumulator
+            tc_mbar_wait(bar0 + 8 + 8 * buf, use);                            // the detection tile has landed
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            // six split products, smallest first; eight K steps of 16 each.  A descriptor is the tile's base descriptor plus
+            // a compile-time constant in its 14-bit address field.
+            const int pa[6] = {2, 0, 1, 1, 0, 0}, pb[6] = {0, 2, 1, 0, 1, 0};
+            const unsigned acc = tm + (unsigned)(buf * kWalkCols);
+            const unsigned long long dB = umma_desc(smem_u32(sB + buf * kWalkImageBytes), kWalkLBO);
+            if (leader) {
                 unsigned accumulate = 0;
 #pragma unroll
                 for (int p = 0; p < 6; ++p) {
-                    const unsigned a0 = smem_u32(sA) + pa[p] * kSplitBytes;
-                    const unsigned b0 = smem_u32(sB + buf * kWalkImageBytes) + pb[p] * kWalkSplitBytes;
 #pragma unroll
                     for (int ks = 0; ks < kChunks / 2; ++ks) {
-                        const unsigned long long da = umma_desc(a0 + ks * 2 * kLBO), db = umma_desc(b0 + ks * 2 * kWalkLBO, kWalkLBO);
+                        const unsigned long long da = dA + (unsigned long long)((pa[p] * kSplitBytes + ks * 2 * kLBO) >> 4);
+                        const unsigned long long db = dB + (unsigned long long)((pb[p] * kWalkSplitBytes + ks * 2 * kWalkLBO) >> 4);
                         asm volatile(
                             "{\n\t.reg .pred p;\n\t"
                             "setp.ne.b32 p, %4, 0;\n\t"
@@ -373,13 +388,15 @@ app_tc_walk_kernel(const unsigned char* __restrict__ imgA, const unsigned char* 
                 if (nrank > 1)                   // ... and tell every CTA of the cluster that this buffer has been read here
                     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n"
                                  ::"r"(bar0 + 56 + 8 * buf), "h"(cta_mask) : "memory");
-                // the products of step - 1 have finished reading the other detection buffer (in every CTA that receives
-                // what is loaded into it): refill it with tile step + 1
-                if (step >= 1 && step + 1 < n_steps) {
-                    if (nrank > 1) tc_mbar_wait(bar0 + 56 + 8 * (buf ^ 1), (unsigned)(((step - 1) >> 1) & 1));
-                    else tc_mbar_wait(bar0 + 24 + 8 * (buf ^ 1), (unsigned)(((step - 1) >> 1) & 1));
-                    load_b(step + 1);
-                }
+            }
+            __syncwarp();
+            // the products of step - 1 have finished reading the other detection buffer (in every CTA that receives what
+            // is loaded into it): refill it with tile step + 1
+            if (step >= 1 && step + 1 < n_steps) {
+                if (nrank > 1) tc_mbar_wait(bar0 + 56 + 8 * (buf ^ 1), (unsigned)(((step - 1) >> 1) & 1));
+                else tc_mbar_wait(bar0 + 24 + 8 * (buf ^ 1), (unsigned)(((step - 1) >> 1) & 1));
+                if (leader) load_b(step + 1);
+                __syncwarp();
             }
         }
     } else {
@@ -452,7 +469,7 @@ app_tc_walk_kernel(const unsigned char* __restrict__ imgA, const unsigned char* 
                 }
                 c = __fsub_rn(1.0f, __fdiv_rn(sum, (float)kk));
             }
-            const int n = step * kWalkCols + half * 32 + lane;
+            const int n = ((first_tile + step) % n_steps) * kWalkCols + half * 32 + lane;
             if (m < M && n < N) C_app[(size_t)m * ldc + n] = c;
         }
     }
@@ -501,7 +518,11 @@ int app_cost_tc(const float* bank, const int32_t* bank_len, const float* fallbac
     rc = check_launch("app_tc_prep_kernel");
     if (rc == B200_OK) {
         if (walk) {
-            int cl = m_tiles % 2 == 0 ? 2 : 1;  // pairs of bank tiles share the delivery of the detection tiles
+            // B200TRACK_TC_CLUSTER=2: pairs of bank tiles share the delivery of the detection tiles (half-tile multicast).
+            // Measured at BASELINE config 4: 24.5 us against 23.4 us without -- the kernel is bound by shared-memory
+            // bandwidth (operand reads of the products + the landing copy + the epilogue's transposes), not by L2 -- so
+            // it is off by default and kept as a tested option.
+            int cl = 1;
             if (const char* e = getenv("B200TRACK_TC_CLUSTER")) cl = (atoi(e) == 2 && m_tiles % 2 == 0) ? 2 : 1;
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3((unsigned)m_tiles);

@@ -169,6 +169,8 @@ def test_app_cost_tensor_core_kernels_vs_oracle(kernel, M, N, T, monkeypatch):
     tensor core one tile ahead of the epilogue).  Ragged tiles in both directions, empty / short / full banks, the EMA
     fallback, top-k beyond five and the max-similarity variant."""
     monkeypatch.setenv("B200TRACK_TC_KERNEL", kernel)
+    if kernel == "2" and (M * 32 + 127) // 128 % 2 == 0 and N > 64:
+        monkeypatch.setenv("B200TRACK_TC_CLUSTER", "2")       # CTA pairs sharing the detection tiles (half-tile multicast)
     rng = np.random.default_rng(3 * M + 11 * N + T)
     lens = rng.integers(0, T + 1, M)
     lens[0], lens[1], lens[2], lens[M - 1] = T, 0, 1, T
