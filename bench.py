@@ -355,8 +355,11 @@ class StreamGroup:
 
 
 def dist_summary(ms):
+    """Distribution of the per-step times of a timed region (+ the first 64 of them in microseconds, in order: the first
+    step carries the pipeline fill, a scheduling hiccup shows as one long step)."""
     a = np.asarray(ms, dtype=np.float64)
-    return {"min": float(a.min()), "median": float(np.median(a)), "max": float(a.max()), "n": int(a.size)}
+    return {"min": float(a.min()), "median": float(np.median(a)), "max": float(a.max()), "n": int(a.size),
+            "first_us": [int(round(v * 1e3)) for v in a[:64]]}
 
 
 def oracle_check(dev, frames=40):
