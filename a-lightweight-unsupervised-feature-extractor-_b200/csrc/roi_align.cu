@@ -153,11 +153,28 @@ __device__ __forceinline__ void cp_async_wait_all() {
 
 // One bulk async copy shared -> global issued by a single lane (TMA engine, SASS UBLKCP).  The
 // source tile may be overwritten only after bulk_store_wait_read() on the issuing lane.
+// B200_ROI_L2_HINT: 0 = none; 1 = the output tiles (written once, never read by this library) leave with an L2 evict-first
+// policy; 2 = the footprint loads too.  ROI Align streams ~1 GB per 64-stream step through a 126 MB L2; without a hint
+// it evicts the tracker's banks and Kalman state between two association steps.
+#ifndef B200_ROI_L2_HINT
+#define B200_ROI_L2_HINT 0
+#endif
+__device__ __forceinline__ unsigned long long l2_evict_first_policy() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(pol));
+    return pol;
+}
 __device__ __forceinline__ void bulk_store_issue(void* gdst, const void* ssrc, unsigned bytes) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(ssrc);
+#if B200_ROI_L2_HINT >= 1
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;\n" ::"l"(gdst), "r"(s),
+                 "r"(bytes), "l"(l2_evict_first_policy())
+                 : "memory");
+#else
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gdst), "r"(s),
                  "r"(bytes)
                  : "memory");
+#endif
     asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
 }
 __device__ __forceinline__ void bulk_store_wait_read() {
@@ -875,8 +892,13 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
         "DONE_%=:\n\t}\n" ::"r"(bar), "r"(parity) : "memory");
 }
 __device__ __forceinline__ void tma_box_4d(unsigned dst, const CUtensorMap* tm, int x, int y, int c, int b, unsigned bar) {
+#if B200_ROI_L2_HINT >= 2
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4, %5}], [%6], %7;\n"
+                 ::"r"(dst), "l"(tm), "r"(x), "r"(y), "r"(c), "r"(b), "r"(bar), "l"(l2_evict_first_policy()) : "memory");
+#else
     asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];\n"
                  ::"r"(dst), "l"(tm), "r"(x), "r"(y), "r"(c), "r"(b), "r"(bar) : "memory");
+#endif
 }
 __device__ __forceinline__ void bulk_load(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
