@@ -441,7 +441,8 @@ def main():
     # takes 35 frames.  If the caller asks for fewer warm-up steps, the difference is run as untimed set-up
     # before the W warm-up steps, so the timed K steps always see the same workload.
     pre = max(0, SETUP_FRAMES - W)
-    n_total = pre + W + K
+    N_E2E, N_API = min(K, 60), 44                  # steps of the two public-API legs; they continue the same scenes in time
+    n_total = pre + W + max(K, N_E2E + N_API)
 
     gather_kind = {}
 
@@ -582,7 +583,7 @@ def main():
     pin_confs = torch.from_numpy(grp.confs).pin_memory()
     pin_embs = torch.from_numpy(grp.embs).pin_memory()
     hb, hc, he = pin_boxes.numpy(), pin_confs.numpy(), pin_embs.numpy()
-    n_e2e = min(K, 60)
+    n_e2e = N_E2E
     scale = sh.HF / float(sh.H_IN)
     copy_stream = torch.cuda.Stream(dev)
     uploaded = [torch.cuda.Event() for _ in range(2)]
@@ -647,14 +648,14 @@ def main():
                 """roi_align (stream A) + step_async (stream B, behind that frame's ROI Align, as the encoder would be) of
                 frame i; the result of frame i - 1 is collected afterwards, as a consumer reading from a queue would
                 (tracking.py:329).  Two user streams, so ROI Align of frame i + 1 overlaps the association of frame i."""
-                j = pre + W + (i % K)              # frames of the timed region again (the state has moved on; same shapes)
+                j = pre + W + n_e2e + i            # the frames that follow the e2e leg's (same tracker, time moves on)
                 with torch.cuda.stream(sA):
                     rois_dev[i & 1].copy_(pin_rois[j % len(pin_rois)], non_blocking=True)
                     patches = alufe_b200.roi_align(feat_dev[i & 1], rois_dev[i & 1], (PS, PS), scale, 2, True)
                     roi_ev[i & 3].record(sA)
                 with torch.cuda.stream(sB):
                     sB.wait_event(roi_ev[i & 3])
-                    h = ms2.step_async(n_det, hb[j], hc[j], he[j], np.full(S, n_total + i, np.int32), pinned=True)
+                    h = ms2.step_async(n_det, hb[j], hc[j], he[j], np.full(S, j, np.int32), pinned=True)
                 return patches, h
             sA.wait_stream(torch.cuda.current_stream(dev))
             sB.wait_stream(torch.cuda.current_stream(dev))
