@@ -268,6 +268,9 @@ roi_prep_kernel(const float* __restrict__ rois, long long K, int B, int H, int W
                 RoiPrep* __restrict__ prep, float* __restrict__ tabs, int xalign) {
     using L = TileSmem<PH, PW>;
     __shared__ __align__(16) float sTabs[4][L::kTabFloats];
+    // programmatic dependent launch: the tile kernel that follows may become resident now and wait (griddepcontrol.wait)
+    // for this grid to finish, instead of paying its launch latency after it
+    asm volatile("griddepcontrol.launch_dependents;");
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long k = (long long)blockIdx.x * 4 + warp;
     if (k >= K) return;
@@ -1035,6 +1038,7 @@ roi_align_tma_kernel(const __grid_constant__ TmaMaps tmap, const T* __restrict__
     unsigned t = grp * window + (gw - grp * stride);
     const unsigned total = (unsigned)min((long long)(grp + 1) * window, K * ctiles);
     if (t >= total) return;
+    asm volatile("griddepcontrol.wait;" ::: "memory");      // roi_prep_kernel's records and tables are complete and visible
     const int span_slot = (int)((reinterpret_cast<uintptr_t>(rois) / (size_t)(K * 20)) & 7);   // debug: step index mod 8
     B200_SPAN_BEGIN(span_slot);
     if (lane == 0) {
@@ -1327,8 +1331,18 @@ int launch_tma(const T* feat, int B, int C, int H, int W, const float* rois, lon
     const long long groups = (tiles + window - 1) / window;
     const long long last = tiles - (groups - 1) * window;
     const long long warps = (groups - 1) * resident + (last < resident ? last : resident);
-    kern<<<(unsigned)((warps + kTmaWarps - 1) / kTmaWarps), kTmaWarps * 32, smem_bytes, st>>>(
-        tmap, feat, B, C, H, W, rois, K, scale, sr, aligned, out, ctiles, prep, tabs, resident, (int)tpw);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)((warps + kTmaWarps - 1) / kTmaWarps));
+    cfg.blockDim = dim3(kTmaWarps * 32);
+    cfg.dynamicSmemBytes = (size_t)smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;     // resident while roi_prep_kernel still runs
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    (void)cudaLaunchKernelEx(&cfg, kern, tmap, feat, B, C, H, W, rois, K, scale, sr, aligned, out, ctiles, prep, tabs, resident,
+                             (int)tpw);
     return check_launch("roi_align_tma_kernel");
 }
 
