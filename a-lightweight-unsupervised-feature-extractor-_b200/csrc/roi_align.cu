@@ -570,6 +570,7 @@ roi_align_multi_kernel(const T* __restrict__ feat, int B, int C, int H, int W, c
     unsigned t = grp * window + (gw - grp * stride);
     const unsigned total = (unsigned)min((long long)(grp + 1) * window, K * ctiles);
     if (t >= total) return;
+    asm volatile("griddepcontrol.wait;" ::: "memory");      // roi_prep_kernel's records and tables are complete and visible
     const int span_slot = (int)((reinterpret_cast<uintptr_t>(rois) / (size_t)(K * 20)) & 7);   // debug: step index mod 8
     B200_SPAN_BEGIN(span_slot);
     float* sMain = smem + (size_t)warp * L::kFloatsPerWarp;
@@ -692,6 +693,7 @@ roi_align_pipe_kernel(const T* __restrict__ feat, int B, int C, int H, int W, co
     unsigned t = grp * window + (gw - grp * stride);
     const unsigned total = (unsigned)min((long long)(grp + 1) * window, K * ctiles);
     if (t >= total) return;
+    asm volatile("griddepcontrol.wait;" ::: "memory");      // roi_prep_kernel's records and tables are complete and visible
     const int span_slot = (int)((reinterpret_cast<uintptr_t>(rois) / (size_t)(K * 20)) & 7);   // debug: step index mod 8
     B200_SPAN_BEGIN(span_slot);
 
@@ -1278,6 +1280,23 @@ EncodeTiledFn encode_tiled_fn() {
     return reinterpret_cast<EncodeTiledFn>(fn);
 }
 
+// Launch of a tile kernel that follows roi_prep_kernel in the stream, as its programmatic dependent: it becomes resident
+// while the prep kernel still runs and waits for it with griddepcontrol.wait before it reads a record.
+template <typename Kern, typename... Args>
+void launch_after_prep(Kern kern, unsigned grid, unsigned block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    (void)cudaLaunchKernelEx(&cfg, kern, args...);      // errors surface in check_launch()
+}
+
 // Launches the TMA-staged kernel when it applies: NCHW map whose rows are a multiple of 16 bytes (the tensor map's
 // stride rule), 16-byte aligned base, dimensions inside the descriptor's limits.  Returns 1 when it does not.
 // The TMA-staged kernel applies to float32 NCHW maps whose rows are a multiple of 16 bytes (the tensor map's stride
@@ -1331,18 +1350,8 @@ int launch_tma(const T* feat, int B, int C, int H, int W, const float* rois, lon
     const long long groups = (tiles + window - 1) / window;
     const long long last = tiles - (groups - 1) * window;
     const long long warps = (groups - 1) * resident + (last < resident ? last : resident);
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)((warps + kTmaWarps - 1) / kTmaWarps));
-    cfg.blockDim = dim3(kTmaWarps * 32);
-    cfg.dynamicSmemBytes = (size_t)smem_bytes;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;     // resident while roi_prep_kernel still runs
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    (void)cudaLaunchKernelEx(&cfg, kern, tmap, feat, B, C, H, W, rois, K, scale, sr, aligned, out, ctiles, prep, tabs, resident,
-                             (int)tpw);
+    launch_after_prep(kern, (unsigned)((warps + kTmaWarps - 1) / kTmaWarps), kTmaWarps * 32, (size_t)smem_bytes, st, tmap, feat, B, C,
+                      H, W, rois, K, scale, sr, aligned, out, ctiles, prep, tabs, resident, (int)tpw);
     return check_launch("roi_align_tma_kernel");
 }
 
@@ -1373,8 +1382,8 @@ int launch_pipe(const T* feat, int B, int C, int H, int W, const float* rois, lo
         const long long groups = (tiles + window - 1) / window;
         const long long last = tiles - (groups - 1) * window;                 // tiles in the last window
         const long long warps = (groups - 1) * resident_warps + (last < resident_warps ? last : resident_warps);
-        kern<<<(unsigned)((warps + kPipeWarps - 1) / kPipeWarps), kPipeWarps * 32, P::kBytesPerCta, st>>>(
-            feat, B, C, H, W, rois, K, scale, sr, aligned, out, ctiles, prep, tabs, resident_warps, kPipeTilesPerWarp);
+        launch_after_prep(kern, (unsigned)((warps + kPipeWarps - 1) / kPipeWarps), kPipeWarps * 32, (size_t)P::kBytesPerCta, st, feat,
+                          B, C, H, W, rois, K, scale, sr, aligned, out, ctiles, prep, tabs, resident_warps, (int)kPipeTilesPerWarp);
         return check_launch("roi_align_pipe_kernel");
     } else {
         return 1;
@@ -1429,9 +1438,9 @@ int launch_tile(const T* feat, int B, int C, int H, int W, const float* rois, lo
                 const long long groups = (warps + window - 1) / window;
                 const long long last = warps - (groups - 1) * window;
                 const long long nw = (groups - 1) * resident_warps + (last < resident_warps ? last : resident_warps);
-                multi<<<(unsigned)((nw + kWarpsPerCta - 1) / kWarpsPerCta), kWarpsPerCta * 32, L::kBytesPerCta, st>>>(
-                    feat, B, C, H, W, rois, K, scale, sr, aligned, out, ctiles, prep, tabs, resident_warps,
-                    B200_ROI_MULTI_TILES);
+                launch_after_prep(multi, (unsigned)((nw + kWarpsPerCta - 1) / kWarpsPerCta), kWarpsPerCta * 32, (size_t)L::kBytesPerCta,
+                                  st, feat, B, C, H, W, rois, K, scale, sr, aligned, out, ctiles, prep, tabs, resident_warps,
+                                  (int)B200_ROI_MULTI_TILES);
                 rc = check_launch("roi_align_multi_kernel");
             }
         }
