@@ -711,6 +711,38 @@ def main():
     side("single_stream", single(sh))
     side("c1", single(WORKLOADS["c1"]))
 
+    # ---- the same single-stream loop captured ONCE as a CUDA graph: 150 consecutive frames, ROI Align on one
+    # captured stream, the association step behind each frame's ROI launch on the other, replayed with one graph launch ----
+    def single_graph():
+        KG = 150
+        g1 = StreamGroup(sh, 1, SETUP_FRAMES + 5 + KG, 7000, dev)
+        g1.timed(0, SETUP_FRAMES + 5)                        # banks full, eagerly
+        cap = torch.cuda.Stream(dev)
+        cap.wait_stream(torch.cuda.current_stream(dev))
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=cap):
+            g1.sA.wait_stream(cap)
+            g1.sB.wait_stream(cap)
+            g1.roi_done = [torch.cuda.Event() for _ in range(KG)]      # one event per frame inside the capture
+            for k in range(KG):
+                g1.step(SETUP_FRAMES + 5 + k)
+            cap.wait_stream(g1.sA)
+            cap.wait_stream(g1.sB)
+        torch.cuda.synchronize(dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(cap):
+            a.record(cap)
+            graph.replay()                                   # ONE launch: 150 frames of ROI Align + association
+            b.record(cap)
+        torch.cuda.synchronize(dev)
+        ms = a.elapsed_time(b)
+        last = g1.results[SETUP_FRAMES + 5 + KG - 1].cpu().numpy()
+        assert int(last[0, 5]) == 0 and int(last[0, 0]) > 0
+        return {"value": KG / (ms * 1e-3), "unit": "frames/s", "ms_per_frame": ms / KG, "frames_in_graph": KG,
+                "matches_last_frame": int(last[0, 0]),
+                "workload": "one stream, " + sh.desc + "; 150 frames captured once with torch.cuda.graph, one replay timed"}
+    side("single_stream_graph", single_graph)
+
     # ---- the same stream group fed channels-last maps (what a channels_last detector would hand over) ----
     def channels_last():
         Kc = min(K, 100)
