@@ -1026,7 +1026,10 @@ __global__ void __launch_bounds__(kFrontWarps * 32, 2) front_kernel(Dev d) {
 // of the cluster runs the serial part (assignments, births, purge, result table) while the others wait at the cluster
 // barrier, then all CTAs of the cluster share the stream's Kalman / EMA / bank updates -- 12.5 -> 6 us for 64 matches,
 // 23 -> 6 us for 128 (profiles/r02_fused_timeline.txt).  Without the cluster attribute the cluster is the CTA itself.
-constexpr int kBackCluster = 4;
+#ifndef B200_TRK_BACK_CLUSTER
+#define B200_TRK_BACK_CLUSTER 4
+#endif
+constexpr int kBackCluster = B200_TRK_BACK_CLUSTER;
 
 __device__ __forceinline__ unsigned cluster_ctarank() {
     unsigned r;
