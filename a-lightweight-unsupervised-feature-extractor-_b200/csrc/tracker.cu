@@ -1560,8 +1560,11 @@ extern "C" int b200_tracker_step(b200_tracker* t, const int32_t* n_det, const do
 // direct = the caller's arrays are page-locked and stay untouched until the result is collected: they are read by DMA
 // straight from where they are (no staging memcpy, which at 64 streams x 64 detections is 2.3 MB = most of the host time).
 namespace {
+// inline_dma (the synchronous b200_tracker_step_host): nothing can overlap anyway, so the copies go on the caller's stream
+// as well and the cross-stream event hops are saved.
 int step_host_submit(b200_tracker* t, const int32_t* n_det_host, const double* boxes_host, const double* confs_host,
-                     const float* embs_host, const int32_t* frame_id_host, int64_t* ticket, void* stream, bool direct) {
+                     const float* embs_host, const int32_t* frame_id_host, int64_t* ticket, void* stream, bool direct,
+                     bool inline_dma = false) {
     B200_REQUIRE(t && n_det_host && frame_id_host && ticket, "tracker_step_host_async: null pointer");
     cudaStream_t st = as_stream(stream);
     const trk::Dev& d = t->d;
@@ -1595,7 +1598,7 @@ int step_host_submit(b200_tracker* t, const int32_t* n_det_host, const double* b
     double* d_confs = reinterpret_cast<double*>(dev_of(t->in_confs));
     float* d_embs = reinterpret_cast<float*>(dev_of(t->in_embs));
     int* d_res = reinterpret_cast<int*>(dslot + ((t->in_bytes + 255) & ~(size_t)255));
-    cudaStream_t up = t->up_stream, down = t->down_stream;
+    cudaStream_t up = inline_dma ? st : t->up_stream, down = inline_dma ? st : t->down_stream;
     if (direct) {
         const void* arrs[3] = {boxes_host, confs_host, embs_host};
         for (int k = 0; k < 3 && n_max > 0; ++k) {
@@ -1630,12 +1633,16 @@ int step_host_submit(b200_tracker* t, const int32_t* n_det_host, const double* b
         }
         B200_CUDA(cudaMemcpyAsync(dslot, pin, t->in_bytes, cudaMemcpyHostToDevice, up));
     }
-    B200_CUDA(cudaEventRecord(t->up[slot], up));
-    B200_CUDA(cudaStreamWaitEvent(st, t->up[slot], 0));            // the caller's stream runs the kernels
+    if (!inline_dma) {
+        B200_CUDA(cudaEventRecord(t->up[slot], up));
+        B200_CUDA(cudaStreamWaitEvent(st, t->up[slot], 0));        // the caller's stream runs the kernels
+    }
     const int rc = b200_tracker_step(t, d_ndet, d_boxes, d_confs, d_embs, d_frame, d_res, stream);
     if (rc) return rc;
-    B200_CUDA(cudaEventRecord(t->ran[slot], st));
-    B200_CUDA(cudaStreamWaitEvent(down, t->ran[slot], 0));
+    if (!inline_dma) {
+        B200_CUDA(cudaEventRecord(t->ran[slot], st));
+        B200_CUDA(cudaStreamWaitEvent(down, t->ran[slot], 0));
+    }
     char* h_res = pin + ((t->in_bytes + 255) & ~(size_t)255);
     B200_CUDA(cudaMemcpyAsync(h_res, d_res, t->res_bytes, cudaMemcpyDeviceToHost, down));
     B200_CUDA(cudaEventRecord(t->done[slot], down));
@@ -1674,7 +1681,7 @@ extern "C" int b200_tracker_step_host(b200_tracker* t, const int32_t* n_det_host
                                       int32_t* result_host, void* stream) {
     B200_REQUIRE(result_host, "tracker_step_host: null pointer");
     int64_t ticket = -1;
-    const int rc = b200_tracker_step_host_async(t, n_det_host, boxes_host, confs_host, embs_host, frame_id_host, &ticket, stream);
+    const int rc = step_host_submit(t, n_det_host, boxes_host, confs_host, embs_host, frame_id_host, &ticket, stream, false, true);
     if (rc) return rc;
     return b200_tracker_step_result(t, ticket, result_host);
 }

@@ -147,7 +147,17 @@ class MultiStreamTracker:
         n_det [S], boxes [S,max_dets,4] float64 xyxy, confs [S,max_dets] float64, embs [S,max_dets,128] float32,
         frame_ids [S].  Returns the int32 result table [S, stride] (``decode`` turns a row into the reference's
         return value); raises ValueError where scipy would (NaN / infeasible cost matrix, hung.py:28)."""
-        return self.step_async(n_det, boxes, confs, embs, frame_ids).result()
+        self.drain()                                   # earlier asynchronous steps first (their results stay on their handles)
+        n_det, boxes, confs, embs, frame_ids = self._prepare(n_det, boxes, confs, embs, frame_ids, False)
+        res = np.zeros((self.S, self.stride), dtype=np.int32)
+        p = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+        with torch.cuda.device(self.device):           # synchronous entry point: copies and kernels on one stream
+            rc = _lib.lib().b200_tracker_step_host(self._h, p(n_det), p(boxes), p(confs), p(embs), p(frame_ids), p(res),
+                                                   _lib.stream_ptr(self.device))
+        _lib.check(rc)
+        h = StepHandle(self, -1, np.zeros(self.S, np.int64))
+        h._finish(res)
+        return h.result()
 
     def step_async(self, n_det, boxes, confs, embs, frame_ids, *, pinned: bool = False) -> "StepHandle":
         """``step`` without the wait: uploads the detections, queues the step and the download of the result table on the
@@ -159,6 +169,24 @@ class MultiStreamTracker:
         ``pinned=True``: ``boxes`` / ``confs`` / ``embs`` are page-locked arrays of the exact dtype and shape (numpy views
         of ``torch.empty(..., pin_memory=True)``, or tensors) that the caller leaves untouched until the result is
         collected; they are uploaded by DMA from where they are instead of through the handle's staging ring."""
+        n_det, boxes, confs, embs, frame_ids = self._prepare(n_det, boxes, confs, embs, frame_ids, pinned)
+        if len(self._pending) >= 4:
+            raise _lib.B200Error("step_async: four steps are already pending; collect their results first")
+        p = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+        ticket = ctypes.c_int64(-1)
+        fn = _lib.lib().b200_tracker_step_pinned_async if pinned else _lib.lib().b200_tracker_step_host_async
+        with torch.cuda.device(self.device):
+            rc = fn(self._h, p(n_det), p(boxes), p(confs), p(embs), p(frame_ids), ctypes.byref(ticket),
+                    _lib.stream_ptr(self.device))
+        _lib.check(rc)
+        h = StepHandle(self, int(ticket.value), np.maximum(n_det, 0).astype(np.int64))
+        h._keep = (boxes, confs, embs) if pinned else None     # the DMA reads these after this call returns
+        self._pending.append(h)
+        self._pending_births = self._pending_births + h._births
+        return h
+
+    def _prepare(self, n_det, boxes, confs, embs, frame_ids, pinned):
+        """Argument conversion and the capacity check shared by ``step`` and ``step_async``."""
         n_det = np.ascontiguousarray(n_det, dtype=np.int32).reshape(self.S)
         frame_ids = np.ascontiguousarray(frame_ids, dtype=np.int32).reshape(self.S)
         if pinned:
@@ -187,20 +215,7 @@ class MultiStreamTracker:
                 raise _lib.B200Error("tracker capacity: live tracks + detections could exceed max_tracks=%d; "
                                      "construct the tracker with a larger max_tracks" % self.max_tracks)
             self.grow(max_tracks=max(int(bound.max()), 2 * self.max_tracks))
-        if len(self._pending) >= 4:
-            raise _lib.B200Error("step_async: four steps are already pending; collect their results first")
-        p = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
-        ticket = ctypes.c_int64(-1)
-        fn = _lib.lib().b200_tracker_step_pinned_async if pinned else _lib.lib().b200_tracker_step_host_async
-        with torch.cuda.device(self.device):
-            rc = fn(self._h, p(n_det), p(boxes), p(confs), p(embs), p(frame_ids), ctypes.byref(ticket),
-                    _lib.stream_ptr(self.device))
-        _lib.check(rc)
-        h = StepHandle(self, int(ticket.value), np.maximum(n_det, 0).astype(np.int64))
-        h._keep = (boxes, confs, embs) if pinned else None     # the DMA reads these after this call returns
-        self._pending.append(h)
-        self._pending_births = self._pending_births + h._births
-        return h
+        return n_det, boxes, confs, embs, frame_ids
 
     def drain(self):
         """Waits for every pending ``step_async`` (their results stay available on their handles)."""
@@ -284,6 +299,11 @@ class StepHandle:
         except Exception as exc:                       # noqa: BLE001
             self._error = exc
             return
+        self._finish(res)
+
+    def _finish(self, res):
+        """Takes the step's result table: live counts, last_result, and the error ``result()`` will raise, if any."""
+        ms = self._ms
         self._res = self.table = res
         ms._res = res
         ms.n_live[:] = res[:, R_NLIVE]
