@@ -5,7 +5,7 @@
                                    (= tracking_win.py:239-267, infer.py:143-170).
 * ``preprocess_roi``             - PreProcess._preprocess_roi, trainingCard.py:24-79.
 """
-from typing import List, Sequence, Tuple, Union
+from typing import Sequence, Tuple, Union
 
 import numpy as np
 import torch

@@ -1,7 +1,7 @@
 """Experiment: ROI Align of a 64-stream group on stream A; on the high-priority stream B, behind each frame's ROI launch, a
 kernel that only WAITS for a fixed time with a chosen footprint (tools/sleeper.cu) in place of the association chain.  Shows
 what co-residency itself costs: period of the combined loop vs ROI Align alone."""
-import ctypes, os, sys, json
+import ctypes, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
